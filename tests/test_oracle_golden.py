@@ -1,0 +1,94 @@
+"""Pin the CPU oracle against fixtures produced by the REAL reference
+(tests/golden/make_golden.py).  Bit-exact for every operator / rhs adjustment / BC
+application; exact iteration counts and (CPU, same torch) bit-equal tolerances for solvers."""
+import warnings
+
+import pytest
+import torch
+
+from oracle import fd_oracle as O
+from tests import _util as U
+
+OPS = U.load("ops.pt")
+SOL = U.load("solvers.pt")
+
+
+@pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
+def test_operator_fixtures(case):
+    dtype = U.TDTYPE[case["spec"]["dtype"]]
+    torch.set_default_dtype(dtype)  # what the reference's Mesh(dtype=...) does globally
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    phi = case["phi"].clone()
+    out = case["out"]
+    nd = phi.dim() - 1
+
+    def eq(*terms):
+        return O.Equation(list(terms), dx, xs, bcs).build(phi)
+
+    for tag, term in (
+        ("lap", O.Term("laplacian", 1.0, None)),
+        ("lap_c", O.Term("laplacian", 1.0, 0.37)),
+        ("neg_lap_c", O.Term("laplacian", -1.0, 2.5)),
+    ):
+        e = eq(term)
+        assert torch.equal(e.aop(phi), out[tag]), tag
+        assert torch.equal(e.adjust_rhs(phi, torch.zeros_like(phi)), out[tag + "_rhs_adj"]), tag
+
+    g = O.apply_grad(O.grad_coeffs(phi, dx, bcs), phi)
+    assert torch.equal(g, out["grad"])
+    assert torch.equal(O.grad_rhs_adjust(phi, dx, bcs), out["grad_rhs_adj"])
+
+    u_c, u_t = case["u_const"], out["u_tensor"]
+    for u, tag in ((u_c, "const"), (u_t, "tensor")):
+        got = O.apply_scalar_op(O.div_coeffs(u, phi, dx, bcs, "upwind"), phi)
+        assert torch.equal(got, out[f"div_upwind_{tag}"]), tag
+        assert torch.equal(O.div_rhs_adjust(u, phi, dx, bcs, "upwind"), out[f"div_upwind_{tag}_rhs_adj"])
+    if "div_central_const" in out:
+        for u, tag in ((u_c, "const"), (u_t, "tensor")):
+            got = O.apply_scalar_op(O.div_coeffs(u, phi, dx, bcs, "none"), phi)
+            assert torch.equal(got, out[f"div_central_{tag}"]), tag
+        assert torch.equal(O.div_rhs_adjust(u_t, phi, dx, bcs, "none"), out["div_central_tensor_rhs_adj"])
+    else:
+        with pytest.raises(IndexError):
+            O.div_coeffs(u_c, phi, dx, bcs, "none")
+
+    e = eq(O.Term("div", 1.0, u_c, "upwind"), O.Term("laplacian", -1.0, 0.1))
+    assert torch.equal(e.aop(phi), out["advdiff"])
+    assert torch.equal(e.adjust_rhs(phi, torch.zeros_like(phi)), out["advdiff_rhs_adj"])
+    if nd == 1:
+        e = eq(O.Term("grad", 1.0, None), O.Term("laplacian", -1.0, 0.5))
+        assert torch.equal(e.aop(phi), out["grad_minus_lap"])
+        assert torch.equal(e.adjust_rhs(phi, torch.zeros_like(phi)), out["grad_minus_lap_rhs_adj"])
+
+    x = phi.clone()
+    O.apply_bcs(x, xs, bcs)
+    assert torch.equal(x, out["bc_applied"])
+
+
+@pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
+def test_solver_fixtures(case):
+    if case["name"] == "rand_3d_64_cg":
+        pytest.skip("64^3 replay is covered on the GPU side; keeps the CPU suite short")
+    dtype = U.TDTYPE[case["spec"]["dtype"]]
+    torch.set_default_dtype(dtype)
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    shape = (1, *case["spec"]["nx"])
+    x = torch.zeros(shape, dtype=dtype) + case["init"]
+    rhs = U.case_rhs(case, shape, dtype)
+    eq = O.Equation(U.oracle_terms(case), dx, xs, bcs).build(x)
+    eq.adjust_rhs(x, rhs)
+    assert rhs.double().sum().item() == case["rhs_adjusted_sum"]
+    fn = {"cg": O.cg, "bicgstab": O.bicgstab}[case["method"]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol, rep, _ = fn(eq, x, rhs, case["tol"], case["max_it"])
+    assert rep["itr"] == case["report"]["itr"]
+    assert rep["converge"] == case["report"]["converge"]
+    # same torch build, same thread count as the generator -> the reductions agree bitwise;
+    # a different host may differ in the last bits of the reductions, so allow 1e-10 relative
+    assert rep["tol"] == pytest.approx(case["report"]["tol"], rel=1e-10, abs=1e-300)
+    if "solution" in case:
+        scale = case["solution"].abs().max().item() + 1e-300
+        assert (sol - case["solution"]).abs().max().item() <= 1e-9 * scale
