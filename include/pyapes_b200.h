@@ -1,0 +1,213 @@
+/*
+ * pyapes_b200 — C ABI of the B200-native finite-difference hot path.
+ *
+ * Drop-in boundary for the three Python seams of the reference (pyapes v0.2.13; file:line
+ * are relative to the reference tree):
+ *   - operator application  OPStype["Aop"] / ops._Aop        (solver/ops.py:122-154,
+ *                                                             solver/fdc.py:67-118,171-200)
+ *   - solver                linalg.solve / cg / bicgstab     (solver/linalg.py:33-279)
+ *   - BC application        BC.apply / _apply_bc_otf         (variables/bcs.py:197-280,
+ *                                                             solver/linalg.py:282-299)
+ * plus the two paths BASELINE.json's north_star adds that the reference lacks
+ * (Jacobi, explicit Euler Ddt).
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no torch types.  All array pointers are DEVICE pointers
+ *     unless the function name ends in `_host`.  `stream` is a cudaStream_t passed as void*.
+ *   - Fields are contiguous row-major scalar fields (the reference's `(1, *nx)` tensor,
+ *     variables/fields.py:52-58).  Meshes of dimension d<3 are embedded in kernel
+ *     coordinates (n0,n1,n2) with LEADING singleton axes: mesh axis j -> kernel axis
+ *     j + 3 - d, so the last (contiguous) axis is always kernel axis 2.
+ *   - dtype: PA_F64 (reference default) or PA_F32 (backend.py:28-42).
+ *   - Every function returns 0 on success or a negative pa_status; pa_last_error() gives
+ *     the message.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with PA_ERR_CUDA.
+ */
+#ifndef PYAPES_B200_H
+#define PYAPES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1
+#define PA_MAX_OPS 4
+#define PA_MAX_FACES 6
+
+typedef enum { PA_F32 = 0, PA_F64 = 1 } pa_dtype;
+
+typedef enum {
+  PA_OK = 0,
+  PA_ERR_ARG = -1,     /* bad argument (shape, dtype, null pointer, workspace too small) */
+  PA_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+  PA_ERR_UNSUPPORTED = -3,
+  PA_ERR_NCCL = -4
+} pa_status;
+
+/* boundary-condition kinds (variables/bcs.py:197-280) */
+typedef enum {
+  PA_BC_DIRICHLET = 1,
+  PA_BC_NEUMANN = 2,
+  PA_BC_SYMMETRY = 3,
+  PA_BC_PERIODIC = 4
+} pa_bc_kind;
+
+/* One boundary face, in the order the reference applies them (the BC config list,
+ * bcs.py:363-440).  `value`:
+ *   Dirichlet: the face value (bcs.py:205-211).
+ *   Neumann  : the additive term  2/3 * V * (x_face - x_inner) * n_dir  already rounded
+ *              in the field dtype by the host (bcs.py:251-253); the kernel computes
+ *              4/3*phi[1] - 1/3*phi[2] + value.
+ * `values` (optional, device, field dtype): one entry per face cell, row-major over the
+ * two other kernel axes — used instead of `value` (callable / tensor bc_val). */
+typedef struct {
+  int32_t axis; /* kernel axis 0..2 */
+  int32_t side; /* -1 lower, +1 upper */
+  int32_t kind; /* pa_bc_kind */
+  int32_t reserved;
+  double value;
+  const void* values;
+} pa_face_bc;
+
+/* Local grid block.  Single GPU: gn0 == n[0], goff0 == 0.  Slab decomposition along kernel
+ * axis 0: n[0] counts the locally allocated planes including ghost planes,
+ * goff0 is the global index of local plane 0, gn0 the global extent.
+ * [lo,hi) is the reference's boundary_slicer (mesh/tools.py:7-20) in LOCAL indices: the
+ * region every solver vector is written in.  [olo0,ohi0) are the locally OWNED planes
+ * along axis 0 (norms and dot products are taken over owned cells only). */
+typedef struct {
+  int32_t n[3];
+  int32_t lo[3];
+  int32_t hi[3];
+  int32_t gn0;
+  int32_t goff0;
+  int32_t olo0;
+  int32_t ohi0;
+  int32_t ndim; /* mesh dimension 1..3; active kernel axes are 3-ndim .. 2 */
+  int32_t reserved;
+} pa_grid;
+
+/* Operator kinds.  Every constant-coefficient operator of the reference (Laplacian with
+ * any BC mix, Grad, Div with a constant advection speed, all limiters) is a 3-point-per-axis
+ * star whose coefficients depend only on whether the cell's index along that axis is 1,
+ * n-2 or anything else (fdc.py:388-421, 575-609): PA_OP_STAR.  The host computes the three
+ * coefficient triples with the reference's own rounding sequence. */
+typedef enum {
+  PA_OP_STAR = 0,
+  PA_OP_DIV_CENTRAL_FIELD = 1, /* limiter "none",  advection from a field (fdc.py:708-743) */
+  PA_OP_DIV_UPWIND_FIELD = 2,  /* limiter "upwind", reference formula (fdc.py:746-772) */
+  PA_OP_DIV_UPWINDFD_FIELD = 3 /* first-order upwind difference (not in the reference) */
+} pa_op_kind;
+
+typedef struct {
+  int32_t kind;      /* pa_op_kind */
+  int32_t has_param; /* multiply by `param` after the stencil (fdm.py:166-169) */
+  double sign;       /* +1 / -1 (fdm.py:95-105, ops.py:140-143) */
+  double param;
+  /* coef[axis][cls][k]: k = 0:Ap (phi[+1]) 1:Ac 2:Am (phi[-1]);
+   * cls = 0 default, 1 index==1 along axis, 2 index==n-2 along axis */
+  double coef[3][3][3];
+  const void* adv;    /* *_FIELD kinds: advection speed, same shape/dtype as the field */
+  double two_dx[3];   /* central field div: divisor 2*dx (fdc.py:607-609) */
+  double dx[3];       /* upwind_fd field div */
+  int32_t zero_am_lo[3]; /* periodic edits of the central scheme (fdc.py:596-602) */
+  int32_t zero_ap_hi[3];
+} pa_op;
+
+/* sum_k sign_k * param_k * Op_k(phi), accumulated in list order (ops.py:130-149) */
+typedef struct {
+  int32_t nops;
+  int32_t reserved;
+  pa_op ops[PA_MAX_OPS];
+} pa_equation;
+
+/* solver report (linalg.py:22-30) + where the result lives */
+typedef enum {
+  PA_RUNNING = 0,
+  PA_CONVERGED = 1,   /* loop left through its condition */
+  PA_MAXIT = 2,       /* "Maximum iteration reached!" RuntimeWarning (linalg.py:146-150,268-271) */
+  PA_BAD_TOL = 3      /* "Invalid tolerance detected!" RuntimeError (linalg.py:334-336) */
+} pa_solve_status;
+
+typedef struct {
+  int32_t itr;
+  int32_t status;        /* pa_solve_status */
+  double tol;
+  int32_t result_in_alt; /* 1: the final iterate is in x_alt and the previous one in x */
+  int32_t launches;      /* kernels launched by this call */
+} pa_report;
+
+typedef struct {
+  double tol;
+  int32_t max_it;
+  int32_t check_every; /* iterations between host polls of the device-side done flag (0 = default) */
+  int32_t use_graph;   /* capture the iteration in a CUDA graph */
+  int32_t variant;     /* 0 = default (fused tiled kernels when applicable), 1 = generic kernels */
+} pa_solver_cfg;
+
+const char* pa_last_error(void);
+int pa_abi_version(void);
+int pa_device_count(void);
+
+/* --- operator application: out = sum_k sign*param*Op_k(phi) on EVERY cell, with the
+ *     wrap-around semantics of torch.roll (fdc.py:171-200).  Replaces ops._Aop. */
+int pa_stencil_apply(const pa_grid* g, const pa_equation* eq, int dtype, const void* phi,
+                     void* out, void* stream);
+
+/* --- explicit gradient: out has shape (ndim, n0, n1, n2); op must be PA_OP_STAR.
+ *     Replaces fdc.Grad.apply (fdc.py:80-87). */
+int pa_grad_apply(const pa_grid* g, const pa_op* op, int dtype, const void* phi, void* out,
+                  void* stream);
+
+/* --- boundary conditions, in place, faces in list order.  Replaces _apply_bc_otf. */
+int pa_bc_apply(const pa_grid* g, int nfaces, const pa_face_bc* faces, int dtype, void* phi,
+                void* stream);
+
+/* --- Krylov / stationary solvers.  x: initial guess in, solution out (or in x_alt, see
+ *     pa_report.result_in_alt); x_alt: same size, receives the other of {last, previous}
+ *     iterate (the reference's Field.VARo, fields.py:129-140).  rhs must already carry the
+ *     reference's adjust_rhs terms (ops.py:63-77).  `ws` is a device workspace of at least
+ *     pa_solver_workspace_bytes(). */
+size_t pa_solver_workspace_bytes(const pa_grid* g, int dtype, int method);
+int pa_cg_solve(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg,
+                void* ws, size_t ws_bytes, pa_report* report, void* stream);
+int pa_bicgstab_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
+                      const pa_face_bc* faces, int dtype, void* x, void* x_alt,
+                      const void* rhs, const pa_solver_cfg* cfg, void* ws, size_t ws_bytes,
+                      pa_report* report, void* stream);
+int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
+                    const pa_face_bc* faces, int dtype, void* x, void* x_alt, const void* rhs,
+                    const pa_solver_cfg* cfg, void* ws, size_t ws_bytes, pa_report* report,
+                    void* stream);
+
+/* --- explicit Euler:  phi_new[slicer] = phi + dt*(rhs - A(phi)), then BCs on phi_new.
+ *     rhs may be NULL (zero source).  phi and phi_new must not alias. */
+int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, const void* phi, void* phi_new, const void* rhs, double dt,
+                  void* stream);
+
+/* --- end-to-end entry with HOST buffers: copies x and rhs to the device, solves with CG,
+ *     copies the solution back.  x_host, rhs_host: n0*n1*n2 elements of dtype (pinned
+ *     memory recommended).  Device scratch is allocated and freed inside the call. */
+int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,
+                     const pa_face_bc* faces, int dtype, void* x_host, const void* rhs_host,
+                     const pa_solver_cfg* cfg, pa_report* report);
+
+/* --- instrumented CG pass (measurement only): `iters` iterations with every section bracketed
+ *     by CUDA events on the launching stream.  out_ms[6] = average per iteration of
+ *     {phase A (d update + d.Ad), phase B (x,r update), BC faces + shell norm, whole iteration,
+ *      kernel launches} and [5] = 1 if the tiled kernels ran. */
+int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
+                  size_t ws_bytes, double* out_ms, void* stream);
+
+enum { PA_METHOD_CG = 0, PA_METHOD_BICGSTAB = 1, PA_METHOD_JACOBI = 2 };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYAPES_B200_H */

@@ -1,0 +1,315 @@
+"""Lowering of the Python objects (Mesh / Field / BC / operator dicts) to the plain C structs of
+include/pyapes_b200.h.  Host-side setup code only; nothing here runs per iteration.
+
+Rounding contract: every coefficient the kernels multiply with is produced HERE with the same
+sequence of torch operations, in the field dtype, that the reference uses to fill its
+coefficient tensors (cited per function), so the device arithmetic reproduces the reference's
+values bit for bit.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import torch
+from torch import Tensor
+
+from pyapes_b200 import _native as N
+
+
+def kernel_axis(mesh_axis: int, ndim: int) -> int:
+    """Mesh axis j -> kernel axis j + 3 - ndim (leading singleton axes for 1-D / 2-D)."""
+    return mesh_axis + 3 - ndim
+
+
+def lower_grid(nx, bcs) -> N.Grid:
+    """Grid block + the solver region of mesh/tools.py:7-20 (single GPU)."""
+    nd = len(nx)
+    g = N.Grid()
+    n = [1] * (3 - nd) + [int(v) for v in nx]
+    lo = [0] * (3 - nd) + [1] * nd
+    hi = [1] * (3 - nd) + [int(v) - 1 for v in nx]
+    for bc in bcs or []:
+        if bc.bc_type == "periodic":
+            a = kernel_axis(bc.bc_face_dim, nd)
+            if bc.bc_n_dir < 0:
+                lo[a] = 0
+            else:
+                hi[a] = n[a]
+    for a in range(3):
+        g.n[a], g.lo[a], g.hi[a] = n[a], lo[a], max(hi[a], lo[a])
+    g.gn0, g.goff0, g.olo0, g.ohi0 = n[0], 0, 0, n[0]
+    g.ndim = nd
+    return g
+
+
+def _face_points(bc, grid) -> tuple[Tensor, Tensor]:
+    """Coordinate of the face plane and of the plane one cell inside, as 0-d tensors
+    (bcs.py:228-231 takes them from the meshgrid through the masks)."""
+    a = bc.bc_face_dim
+    g = grid[a]
+    n = g.shape[a]
+    pf = 0 if bc.bc_n_dir < 0 else n - 1
+    p1 = (pf - bc.bc_n_dir) % n
+    idx_f = tuple(pf if i == a else 0 for i in range(g.dim()))
+    idx_1 = tuple(p1 if i == a else 0 for i in range(g.dim()))
+    return g[idx_f], g[idx_1]
+
+
+def face_value(bc, grid, var: Tensor, var_dim: int) -> tuple[float | None, Tensor | None]:
+    """(scalar, per-cell array) form of bc.bc_val (bcs.py:203-213, 240-249)."""
+    v = bc.bc_val
+    if callable(v):
+        out = v(grid, bc.bc_mask, var, bc.bc_val_opt)
+        if not isinstance(out, Tensor):
+            return float(out), None
+        return (float(out), None) if out.numel() == 1 else (None, out)
+    if isinstance(v, list):
+        return float(v[var_dim]), None
+    if isinstance(v, (int, float)):
+        return float(v), None
+    if isinstance(v, Tensor):
+        return (float(v), None) if v.numel() == 1 else (None, v)
+    return None, None
+
+
+def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int) -> tuple[N.FaceBC, Any]:
+    """One pa_face_bc.  Returns the struct and the tensor (if any) that must stay alive."""
+    f = N.FaceBC()
+    f.axis = kernel_axis(bc.bc_face_dim, nd)
+    f.side = bc.bc_n_dir
+    f.kind = N.BC_KIND[bc.bc_type]
+    f.value = 0.0
+    f.values = None
+    keep = None
+    dt, dev = var.dtype, var.device
+    if bc.bc_type == "dirichlet":
+        assert bc.bc_val is not None, "BC: bc_val is not specified!"
+        s, arr = face_value(bc, grid, var, var_dim)
+        if arr is None and s is None:
+            raise TypeError("Dirichlet: bc_val must be float, int, callable or list!")
+        if arr is not None:
+            keep = arr.to(device=dev, dtype=dt).contiguous().reshape(-1)
+        else:
+            f.value = s
+    elif bc.bc_type == "neumann":
+        assert bc.bc_val is not None, "BC: bc_val is not specified!"
+        s, arr = face_value(bc, grid, var, var_dim)
+        if arr is None and s is None:
+            raise TypeError("Neumann: bc_val must be float, int, callable or list!")
+        xf, x1 = _face_points(bc, grid)
+        dxv = xf - x1  # grid[mask] - grid[mask_prev]                          bcs.py:228-231
+        if arr is not None:
+            c = 2 / 3 * arr.to(device=dev, dtype=dt) * dxv * bc.bc_n_dir  # bcs.py:252
+            keep = c.contiguous().reshape(-1)
+        else:
+            f.value = float(2 / 3 * s * dxv * bc.bc_n_dir)
+    if keep is not None:
+        N.require_cuda(keep, "boundary value array")
+        f.values = keep.data_ptr()
+    return f, keep
+
+
+def lower_faces(bcs, grid, var: Tensor, var_dim: int, nd: int):
+    arr = (N.FaceBC * max(len(bcs), 1))()
+    keep = []
+    for i, bc in enumerate(bcs):
+        arr[i], k = lower_face(bc, grid, var, var_dim, nd)
+        keep.append(k)
+    return arr, len(bcs), keep
+
+
+# ---------------------------------------------------------------------------------------
+# coefficient classes of the constant-coefficient stars
+# ---------------------------------------------------------------------------------------
+class StarCoeffs:
+    """What the reference stores as 15 full-size tensors (`[App, Ap, Ac, Am, Amm]`, each a
+    list over mesh axes, tools.py:29-112) collapses, for constant coefficients, to three
+    numbers per axis and per plane class (index 1 / index n-2 / elsewhere).  `vec[j]` keeps the
+    per-axis 1-D coefficient vectors [Ap, Ac, Am] (length n_j) they were read from."""
+
+    kind = N.OP_STAR
+
+    def __init__(self, vecs: list[list[Tensor]], name: str):
+        self.vec = vecs
+        self.name = name
+        self.adv = None
+
+    def classes(self, j: int) -> list[list[float]]:
+        ap, ac, am = self.vec[j]
+        n = ap.numel()
+        pick = (0, 1 % n, (n - 2) % n)
+        return [[float(ap[i]), float(ac[i]), float(am[i])] for i in pick]
+
+
+class FieldCoeffs:
+    """Div with a tensor / Field advection speed: coefficients are formed in-kernel from the
+    live field (fdc.py:708-772); only scalars and periodic flags are kept here."""
+
+    def __init__(self, kind: int, adv: Tensor, dx: list[float], zero_am_lo, zero_ap_hi, name: str):
+        self.kind, self.adv, self.dx = kind, adv, dx
+        self.zero_am_lo, self.zero_ap_hi = zero_am_lo, zero_ap_hi
+        self.name = name
+
+
+def _axis_bcs(bcs, j):
+    return [bc for bc in (bcs or []) if bc.bc_face_dim == j]
+
+
+def laplacian_star(nx, dx: list[float], bcs, dtype) -> StarCoeffs:
+    """fdc.py:375-423 with tools.py:79-85 on one 1-D vector per axis."""
+    dxt = torch.tensor(dx, dtype=dtype)
+    vecs = []
+    for j, n in enumerate(nx):
+        ap, ac, am = torch.ones(n, dtype=dtype), -2.0 * torch.ones(n, dtype=dtype), torch.ones(n, dtype=dtype)
+        for bc in _axis_bcs(bcs, j):
+            if bc.bc_type in ("neumann", "symmetry"):
+                alpha = torch.zeros(1, dtype=dtype)
+                if bc.bc_n_dir < 0:
+                    ap[1 % n] = 2 / 3 + alpha
+                    ac[1 % n] = -(2 / 3 + alpha)
+                    am[1 % n] = 0.0
+                else:
+                    ap[(n - 2) % n] = 0.0
+                    ac[(n - 2) % n] = -(2 / 3 + alpha)
+                    am[(n - 2) % n] = 2 / 3 + alpha
+        ap /= dxt[j] ** 2
+        ac /= dxt[j] ** 2
+        am /= dxt[j] ** 2
+        vecs.append([ap, ac, am])
+    return StarCoeffs(vecs, "Laplacian")
+
+
+def _central_star(nx, dx, bcs, dtype, ap0, ac0, am0, gamma, name, allow_ns=True) -> StarCoeffs:
+    """fdc.py:543-609: central-difference edits with a constant gamma, then / (2 dx)."""
+    dxt = torch.tensor(dx, dtype=dtype)
+    vecs = []
+    for j, n in enumerate(nx):
+        ap, ac, am = ap0(n), ac0(n), am0(n)
+        g = torch.ones(1, dtype=dtype) * gamma
+        for bc in _axis_bcs(bcs, j):
+            if bc.bc_type in ("neumann", "symmetry"):
+                if not allow_ns:
+                    raise IndexError(
+                        "FDC Div: central scheme with Neumann/Symmetry faces is not usable "
+                        "(the reference raises IndexError in fdc.py:583-584 as well)"
+                    )
+                if bc.bc_n_dir < 0:
+                    ap[1 % n] += (1 / 3 * g)[0]
+                    ac[1 % n] -= (1 / 3 * g)[0]
+                    am[1 % n] = 0.0
+                else:
+                    ap[(n - 2) % n] = 0.0
+                    ac[(n - 2) % n] += (1 / 3 * g)[0]
+                    am[(n - 2) % n] -= (1 / 3 * g)[0]
+            elif bc.bc_type == "periodic":
+                if bc.bc_n_dir < 0:
+                    am[1 % n] = 0.0
+                else:
+                    ap[(n - 2) % n] = 0.0
+        ap /= 2.0 * dxt[j]
+        ac /= 2.0 * dxt[j]
+        am /= 2.0 * dxt[j]
+        vecs.append([ap, ac, am])
+    return StarCoeffs(vecs, name)
+
+
+def grad_star(nx, dx, bcs, dtype) -> StarCoeffs:
+    """fdc.py:479-492."""
+    one = lambda n: torch.ones(n, dtype=dtype)  # noqa: E731
+    return _central_star(nx, dx, bcs, dtype, one, lambda n: torch.zeros(n, dtype=dtype),
+                         lambda n: -1.0 * one(n), 1.0, "Grad")
+
+
+def div_star_const(u: float, nx, dx, bcs, dtype, limiter: str) -> StarCoeffs:
+    """Div with a constant advection speed (fdc.py:622-664, 708-772)."""
+    adv = torch.ones(1, dtype=dtype) * u  # fdc.py:779
+    if limiter == "none":
+        if any(bc.bc_type in ("neumann", "symmetry") for bc in (bcs or [])):
+            raise IndexError(
+                "FDC Div: central scheme with Neumann/Symmetry faces is not usable "
+                "(the reference raises IndexError in fdc.py:583-584 as well)"
+            )
+        a = adv[0]
+        return _central_star(nx, dx, bcs, dtype,
+                             lambda n: torch.ones(n, dtype=dtype) * a,
+                             lambda n: torch.zeros(n, dtype=dtype) * a,
+                             lambda n: -1.0 * torch.ones(n, dtype=dtype) * a, u, "Div", allow_ns=False)
+    vecs = []
+    zero = torch.zeros(1, dtype=dtype)
+    if limiter == "upwind":  # fdc.py:765-770: no 1/dx, centre coefficient 0 * 2u
+        for n in nx:
+            ap = (2.0 * torch.min(adv, zero)).expand(n).clone()
+            ac = (torch.zeros(1, dtype=dtype) * (2.0 * adv)).expand(n).clone()
+            am = (2.0 * torch.max(adv, zero)).expand(n).clone()
+            vecs.append([ap, ac, am])
+    elif limiter == "upwind_fd":  # not in the reference: u+ (phi - phi[-1])/dx + u- (phi[+1] - phi)/dx
+        dxt = torch.tensor(dx, dtype=dtype)
+        up, um = torch.max(adv, zero), torch.min(adv, zero)
+        for j, n in enumerate(nx):
+            vecs.append([(um / dxt[j]).expand(n).clone(), ((up - um) / dxt[j]).expand(n).clone(),
+                         (-up / dxt[j]).expand(n).clone()])
+    elif limiter == "quick":
+        raise NotImplementedError("FDC Div: quick scheme is not implemented yet.")
+    else:
+        raise RuntimeError(f"FDC Div: {limiter=} is an unknown limiter type.")
+    return StarCoeffs(vecs, "Div")
+
+
+def div_field(adv: Tensor, nx, dx, bcs, limiter: str) -> FieldCoeffs:
+    nd = len(nx)
+    zl, zh = [0] * 3, [0] * 3
+    if limiter == "none":
+        if any(bc.bc_type in ("neumann", "symmetry") for bc in (bcs or [])):
+            raise IndexError(
+                "FDC Div: central scheme with Neumann/Symmetry faces is not usable "
+                "(the reference raises IndexError in fdc.py:583-584 as well)"
+            )
+        for bc in bcs or []:
+            if bc.bc_type == "periodic":
+                a = kernel_axis(bc.bc_face_dim, nd)
+                if bc.bc_n_dir < 0:
+                    zl[a] = 1
+                else:
+                    zh[a] = 1
+        kind = N.OP_DIV_CENTRAL_FIELD
+    elif limiter == "upwind":
+        kind = N.OP_DIV_UPWIND_FIELD
+    elif limiter == "upwind_fd":
+        kind = N.OP_DIV_UPWINDFD_FIELD
+    elif limiter == "quick":
+        raise NotImplementedError("FDC Div: quick scheme is not implemented yet.")
+    else:
+        raise RuntimeError(f"FDC Div: {limiter=} is an unknown limiter type.")
+    return FieldCoeffs(kind, adv, dx, zl, zh, "Div")
+
+
+def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param: float | None = None) -> tuple[N.Op, Any]:
+    """StarCoeffs / FieldCoeffs -> pa_op."""
+    op = N.Op()
+    op.kind = coeffs.kind
+    op.sign = float(sign)
+    op.has_param = 0 if param is None else 1
+    op.param = 1.0 if param is None else float(param)
+    keep = None
+    if isinstance(coeffs, StarCoeffs):
+        for j in range(nd):
+            a = kernel_axis(j, nd)
+            cls = coeffs.classes(j)
+            for c in range(3):
+                for k in range(3):
+                    op.coef[a][c][k] = cls[c][k]
+    else:
+        adv = coeffs.adv
+        N.require_cuda(adv, "advection field")
+        keep = adv
+        op.adv = adv.data_ptr()
+        dxt = torch.tensor(coeffs.dx, dtype=dtype)
+        for j in range(nd):
+            a = kernel_axis(j, nd)
+            op.two_dx[a] = float(2.0 * dxt[j])
+            op.dx[a] = float(dxt[j])
+        for a in range(3):
+            op.zero_am_lo[a] = coeffs.zero_am_lo[a]
+            op.zero_ap_hi[a] = coeffs.zero_ap_hi[a]
+    return op, keep

@@ -1,0 +1,705 @@
+// C-ABI entry points + host-side iteration drivers.  See include/pyapes_b200.h.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_tiled.cuh"
+
+namespace pa {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PA_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(PA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+static int check_grid(const pa_grid* g) {
+  if (!g) return fail(PA_ERR_ARG, "grid is null");
+  if (g->ndim < 1 || g->ndim > 3) return fail(PA_ERR_ARG, "grid.ndim must be 1..3");
+  for (int a = 0; a < 3; ++a) {
+    if (g->n[a] < 1) return fail(PA_ERR_ARG, "grid.n must be >= 1");
+    if (a < 3 - g->ndim && g->n[a] != 1)
+      return fail(PA_ERR_ARG, "leading (inactive) kernel axes must have extent 1");
+    if (g->lo[a] < 0 || g->hi[a] > g->n[a] || g->lo[a] > g->hi[a])
+      return fail(PA_ERR_ARG, "grid.lo/hi out of range");
+  }
+  if (g->olo0 < 0 || g->ohi0 > g->n[0] || g->olo0 > g->ohi0)
+    return fail(PA_ERR_ARG, "grid.olo0/ohi0 out of range");
+  if ((long long)g->n[0] * g->n[1] * g->n[2] >= (1LL << 40))
+    return fail(PA_ERR_ARG, "grid too large");
+  return PA_OK;
+}
+
+static int check_eq(const pa_equation* eq) {
+  if (!eq) return fail(PA_ERR_ARG, "equation is null");
+  if (eq->nops < 1 || eq->nops > PA_MAX_OPS)
+    return fail(PA_ERR_UNSUPPORTED, "equation must have 1..PA_MAX_OPS operators");
+  for (int k = 0; k < eq->nops; ++k) {
+    int kind = eq->ops[k].kind;
+    if (kind < PA_OP_STAR || kind > PA_OP_DIV_UPWINDFD_FIELD)
+      return fail(PA_ERR_ARG, "unknown operator kind");
+    if (kind != PA_OP_STAR && eq->ops[k].adv == nullptr)
+      return fail(PA_ERR_ARG, "field-advection operator without adv pointer");
+  }
+  return PA_OK;
+}
+
+static int check_faces(int nfaces, const pa_face_bc* faces) {
+  if (nfaces < 0 || nfaces > PA_MAX_FACES) return fail(PA_ERR_ARG, "nfaces must be 0..6");
+  if (nfaces > 0 && !faces) return fail(PA_ERR_ARG, "faces is null");
+  for (int f = 0; f < nfaces; ++f) {
+    if (faces[f].axis < 0 || faces[f].axis > 2) return fail(PA_ERR_ARG, "face axis");
+    if (faces[f].side != -1 && faces[f].side != 1) return fail(PA_ERR_ARG, "face side");
+    if (faces[f].kind < PA_BC_DIRICHLET || faces[f].kind > PA_BC_PERIODIC)
+      return fail(PA_ERR_ARG, "face kind");
+  }
+  return PA_OK;
+}
+
+static inline int grid_blocks(long long cells) {
+  long long b = (cells + kBlock - 1) / kBlock;
+  long long cap = (long long)kNumSMs * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct Launcher {
+  cudaStream_t s;
+  int count = 0;
+};
+
+template <typename T>
+static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_bc* faces, T* phi,
+                       const SolverState* st) {
+  for (int f = 0; f < nfaces; ++f) {
+    FaceDev<T> fd;
+    fd.axis = faces[f].axis;
+    fd.side = faces[f].side;
+    fd.kind = faces[f].kind;
+    fd.value = (T)faces[f].value;
+    fd.values = (const T*)faces[f].values;
+    if (!g.act[fd.axis]) continue;
+    // along the slab axis only the rank that owns the face plane applies it
+    if (fd.axis == 0) {
+      int gi = fd.side < 0 ? 0 : g.gn0 - 1;
+      int pl = gi - g.goff0;
+      if (pl < g.olo0 || pl >= g.ohi0) continue;
+      if (g.goff0 != 0 || g.gn0 != g.n[0]) {
+        // slab-decomposed: face plane indices are local; handled by k_bc_face via n[0]
+        // only when the block spans the whole axis.  Multi-rank x faces go through
+        // launch_bcs_slab (dist.cu).
+        continue;
+      }
+    }
+    int b = (fd.axis == 0) ? 1 : 0, c = (fd.axis == 2) ? 1 : 2;
+    long long ncell = (long long)g.n[b] * g.n[c];
+    int blocks = (int)((ncell + kBlock - 1) / kBlock);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    if (blocks < 1) blocks = 1;
+    k_bc_face<T><<<blocks, kBlock, 0, L.s>>>(g, fd, phi, st);
+    ++L.count;
+  }
+}
+
+template <typename T>
+static void launch_shell(Launcher& L, const GridDev& g, const T* a, const T* b, SolverState* st,
+                         double* partials, int stage) {
+  long long m = 1;
+  for (int ax = 0; ax < 3; ++ax) {
+    int bb = (ax == 0) ? 1 : 0, cc = (ax == 2) ? 1 : 2;
+    long long nc = (long long)g.n[bb] * g.n[cc];
+    if (g.act[ax] && nc > m) m = nc;
+  }
+  int bx = (int)((m + kBlock - 1) / kBlock);
+  if (bx > 128) bx = 128;
+  dim3 grid(bx, 6);
+  k_shell_norm<T><<<grid, kBlock, 0, L.s>>>(g, a, b, st, partials, stage);
+  ++L.count;
+}
+
+__global__ void k_state_init(SolverState* st, double tolerance, int max_it) {
+  for (int i = 0; i < 8; ++i) {
+    st->sum[i] = 0.0;
+    st->scal[i] = 0.0;
+    st->ticket[i] = 0u;
+  }
+  st->tol = 1.0;
+  st->tolerance = tolerance;
+  st->itr = 0;
+  st->max_it = max_it;
+  st->done = 0;
+  st->status = PA_RUNNING;
+  st->finished_flag = 0;
+}
+
+// ---- workspace carving -------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  SolverState* st;
+  double* partials;
+  char* vec[8];
+};
+
+static size_t ws_bytes(long long cells, size_t esz, int nvec) {
+  size_t s = align_up(sizeof(SolverState), 256);
+  s += align_up(sizeof(double) * kNumSums * kMaxPartials, 256);
+  s += (size_t)nvec * align_up((size_t)cells * esz, 256);
+  return s;
+}
+
+static void carve(void* ws, long long cells, size_t esz, int nvec, Workspace& w) {
+  char* p = (char*)ws;
+  w.st = (SolverState*)p;
+  p += align_up(sizeof(SolverState), 256);
+  w.partials = (double*)p;
+  p += align_up(sizeof(double) * kNumSums * kMaxPartials, 256);
+  for (int i = 0; i < nvec; ++i) {
+    w.vec[i] = p;
+    p += align_up((size_t)cells * esz, 256);
+  }
+}
+
+static int method_nvec(int method) {
+  switch (method) {
+    case PA_METHOD_CG: return 3;
+    case PA_METHOD_BICGSTAB: return 6;
+    default: return 0;
+  }
+}
+
+// pinned mailbox for polling the device-side state
+static SolverState* host_mailbox() {
+  static SolverState* p = nullptr;
+  if (!p) {
+    if (cudaHostAlloc((void**)&p, sizeof(SolverState), cudaHostAllocDefault) != cudaSuccess)
+      p = nullptr;
+  }
+  return p;
+}
+
+static int poll_state(cudaStream_t s, const SolverState* dev, SolverState** out) {
+  SolverState* h = host_mailbox();
+  if (!h) return fail(PA_ERR_CUDA, "cudaHostAlloc failed");
+  PA_CUDA(cudaMemcpyAsync(h, dev, sizeof(SolverState), cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  *out = h;
+  return PA_OK;
+}
+
+static void fill_report(pa_report* rep, const SolverState* h, int launches) {
+  rep->itr = h->itr;
+  rep->status = h->status;
+  rep->tol = h->tol;
+  rep->result_in_alt = 0;
+  rep->launches = launches;
+}
+
+// The iteration loop runs on a private non-blocking stream (stream capture is not allowed
+// on the legacy default stream torch hands us); it is ordered after the caller's stream by
+// an event, and the call returns only after that stream has drained (poll_state).
+static int solver_stream(cudaStream_t caller, cudaStream_t* out) {
+  static cudaStream_t s = nullptr;
+  static cudaEvent_t ev = nullptr;
+  if (!s) {
+    PA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    PA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  PA_CUDA(cudaEventRecord(ev, caller));
+  PA_CUDA(cudaStreamWaitEvent(s, ev, 0));
+  *out = s;
+  return PA_OK;
+}
+
+// ---- CG -----------------------------------------------------------------------------------
+// One iteration = [d update] -> d.Ad -> x/r update -> BC faces -> shell norm + scalars.
+// Tiled variant fuses the first two and recomputes Ad in the third (8 words / cell).
+template <typename T>
+static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
+                         const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt, bool tiled,
+                         const TilePlan& plan, int parity, cudaEvent_t* marks = nullptr) {
+  auto mark = [&](int i) {
+    if (marks) cudaEventRecord(marks[i], L.s);
+  };
+  mark(0);
+  T* r = (T*)w.vec[0];
+  T* d = (T*)w.vec[1];
+  int nb = grid_blocks(g.cells);
+  if (tiled) {
+    // the fused d-update recomputes d_new on tile halos, so d is double-buffered: neighbours
+    // must still see d_old there (kernels_tiled.cuh)
+    T* d_old = (T*)w.vec[1 + parity];
+    T* d_new = (T*)w.vec[2 - parity];
+    launch_cg_phaseA<T>(L.s, plan, g, eq, r, d_old, d_new, w.st, w.partials);
+    ++L.count;
+    mark(1);
+    launch_cg_phaseB<T>(L.s, plan, g, eq, cur, nxt, d_new, r, w.st, w.partials);
+    ++L.count;
+  } else {
+    k_cg_dupdate<T><<<nb, kBlock, 0, L.s>>>(g, r, d, w.st);
+    k_cg_dAd<T><<<nb, kBlock, 0, L.s>>>(g, eq, d, w.st, w.partials, ST_CG_DAD);
+    mark(1);
+    k_cg_update<T><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, d, r, w.st, w.partials);
+    L.count += 3;
+  }
+  mark(2);
+  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+  launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_CG_FIN);
+  mark(3);
+}
+
+// Instrumented CG pass for bench.py: `iters` iterations, no graph, every section bracketed by
+// CUDA events on the launching stream.  out_ms = {phase A, phase B, BC faces + shell norm,
+// whole loop, launches per iteration} (averages per iteration).
+template <typename T>
+static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, const pa_face_bc* faces,
+                      T* x, T* x_alt, const T* rhs, int iters, int variant, void* ws, size_t ws_size,
+                      double* out_ms, cudaStream_t caller_stream) {
+  cudaStream_t stream;
+  int rcs = solver_stream(caller_stream, &stream);
+  if (rcs != PA_OK) return rcs;
+  GridDev g = make_grid(*pg);
+  EqDev<T> eq = make_eq<T>(*peq);
+  if (ws_size < ws_bytes(g.cells, sizeof(T), method_nvec(PA_METHOD_CG)))
+    return fail(PA_ERR_ARG, "workspace too small");
+  Workspace w;
+  carve(ws, g.cells, sizeof(T), method_nvec(PA_METHOD_CG), w);
+  Launcher L{stream};
+  TilePlan plan;
+  bool tiled = variant == 0 && plan_tiles<T>(g, *peq, plan);
+  k_state_init<<<1, 1, 0, stream>>>(w.st, 1e-300, iters + 10);
+  launch_bcs<T>(L, g, nfaces, faces, x, nullptr);
+  k_residual_init<T><<<grid_blocks(g.cells), kBlock, 0, stream>>>(g, eq, x, rhs, (T*)w.vec[0],
+                                                                 (T*)w.vec[1], w.st, w.partials,
+                                                                 ST_CG_INIT);
+  std::vector<cudaEvent_t> ev(4 * (size_t)iters);
+  for (auto& e : ev) PA_CUDA(cudaEventCreate(&e));
+  int before = L.count;
+  for (int it = 0; it < iters; ++it) {
+    T* cur = (it & 1) ? x_alt : x;
+    T* nxt = (it & 1) ? x : x_alt;
+    cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, it & 1, &ev[4 * (size_t)it]);
+  }
+  PA_CUDA(cudaStreamSynchronize(stream));
+  double a = 0, b = 0, c = 0;
+  for (int it = 0; it < iters; ++it) {
+    float ms;
+    cudaEventElapsedTime(&ms, ev[4 * it], ev[4 * it + 1]);
+    a += ms;
+    cudaEventElapsedTime(&ms, ev[4 * it + 1], ev[4 * it + 2]);
+    b += ms;
+    cudaEventElapsedTime(&ms, ev[4 * it + 2], ev[4 * it + 3]);
+    c += ms;
+  }
+  float tot;
+  cudaEventElapsedTime(&tot, ev[0], ev[4 * (size_t)iters - 1]);
+  out_ms[0] = a / iters;
+  out_ms[1] = b / iters;
+  out_ms[2] = c / iters;
+  out_ms[3] = (double)tot / iters;
+  out_ms[4] = (double)(L.count - before) / iters;
+  out_ms[5] = tiled ? 1.0 : 0.0;
+  for (auto& e : ev) cudaEventDestroy(e);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
+template <typename T>
+static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
+                               const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt) {
+  T* r0 = (T*)w.vec[0];
+  T* r = (T*)w.vec[1];
+  T* p = (T*)w.vec[2];
+  T* v = (T*)w.vec[3];
+  T* s = (T*)w.vec[4];
+  T* t = (T*)w.vec[5];
+  int nb = grid_blocks(g.cells);
+  k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
+  k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_BI_V);
+  k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_BI_S);
+  k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_BI_T);
+  k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
+  L.count += 5;
+  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+  k_finalize<T><<<1, 1, 0, L.s>>>(ST_BI_FIN, w.st);
+  ++L.count;
+}
+
+template <typename T>
+static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
+                             const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt,
+                             const T* rhs) {
+  int nb = grid_blocks(g.cells);
+  k_pointwise_update<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, rhs, (T)0, w.st, w.partials);
+  ++L.count;
+  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+  launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_JA_FIN);
+}
+
+// Shared driver: init, then iterate in pairs (x -> x_alt -> x) so that a pair can be
+// captured once in a CUDA graph and replayed; poll the device-side done flag every
+// `check_every` iterations.  Launches after `done` are no-ops (each kernel tests st->done).
+template <typename T>
+static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int nfaces,
+                      const pa_face_bc* faces, T* x, T* x_alt, const T* rhs,
+                      const pa_solver_cfg* cfg, void* ws, size_t ws_size, pa_report* rep,
+                      cudaStream_t caller_stream) {
+  cudaStream_t stream;
+  {
+    int rcs = solver_stream(caller_stream, &stream);
+    if (rcs != PA_OK) return rcs;
+  }
+  GridDev g = make_grid(*pg);
+  EqDev<T> eq = make_eq<T>(*peq);
+  int nvec = method_nvec(method);
+  if (ws_size < ws_bytes(g.cells, sizeof(T), nvec))
+    return fail(PA_ERR_ARG, "workspace too small (see pa_solver_workspace_bytes)");
+  Workspace w;
+  carve(ws, g.cells, sizeof(T), nvec, w);
+  Launcher L{stream};
+
+  TilePlan plan;
+  bool tiled = false;
+  if (method == PA_METHOD_CG && cfg->variant == 0) tiled = plan_tiles<T>(g, *peq, plan);
+
+  k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
+  ++L.count;
+  launch_bcs<T>(L, g, nfaces, faces, x, nullptr);
+  int nb = grid_blocks(g.cells);
+  size_t vbytes = (size_t)g.cells * sizeof(T);
+
+  if (method == PA_METHOD_CG) {
+    T* r = (T*)w.vec[0];
+    T* d = (T*)w.vec[1];
+    k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r, d, w.st, w.partials,
+                                                  ST_CG_INIT);
+    ++L.count;
+  } else if (method == PA_METHOD_BICGSTAB) {
+    T* r0 = (T*)w.vec[0];
+    T* r = (T*)w.vec[1];
+    for (int i = 2; i < 6; ++i) PA_CUDA(cudaMemsetAsync(w.vec[i], 0, vbytes, stream));
+    k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials,
+                                                  ST_BI_INIT);
+    ++L.count;
+  }
+  PA_CUDA(cudaGetLastError());
+
+  // while-loop entry condition of cg/jacobi: tol = 1.0 > tolerance (linalg.py:90,109)
+  if (method != PA_METHOD_BICGSTAB && !(1.0 > cfg->tol)) {
+    PA_CUDA(cudaStreamSynchronize(stream));
+    rep->itr = 0;
+    rep->status = PA_CONVERGED;
+    rep->tol = 1.0;
+    rep->result_in_alt = 0;
+    rep->launches = L.count;
+    return PA_OK;
+  }
+
+  auto iteration = [&](T* cur, T* nxt) {
+    if (method == PA_METHOD_CG)
+      cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1);
+    else if (method == PA_METHOD_BICGSTAB)
+      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt);
+    else
+      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs);
+  };
+
+  const long long max_iters = (method == PA_METHOD_BICGSTAB)
+                                  ? (cfg->max_it > 1 ? cfg->max_it : 1)
+                                  : (long long)cfg->max_it + 1;
+  int check_every = cfg->check_every > 0 ? cfg->check_every : 32;
+  if (check_every & 1) ++check_every;  // whole pairs
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int per_pair = 0;
+  if (cfg->use_graph) {
+    int before = L.count;
+    PA_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    iteration(x, x_alt);
+    iteration(x_alt, x);
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    per_pair = L.count - before;
+    L.count = before;
+    if (ce != cudaSuccess) return fail(PA_ERR_CUDA, "graph capture failed");
+    PA_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  }
+
+  SolverState* h = nullptr;
+  long long it = 0;
+  int rc = PA_OK;
+  while (true) {
+    long long chunk = check_every;
+    for (long long k = 0; k < chunk; k += 2) {
+      if (gexec) {
+        cudaError_t e = cudaGraphLaunch(gexec, stream);
+        if (e != cudaSuccess) {
+          rc = fail(PA_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+          break;
+        }
+        L.count += per_pair;
+      } else {
+        iteration(x, x_alt);
+        iteration(x_alt, x);
+      }
+    }
+    if (rc != PA_OK) break;
+    it += chunk;
+    rc = poll_state(stream, w.st, &h);
+    if (rc != PA_OK) break;
+    if (h->done) break;
+    if (it > max_iters + 2) {
+      rc = fail(PA_ERR_CUDA, "solver did not latch `done` (internal error)");
+      break;
+    }
+  }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc != PA_OK) return rc;
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(PA_ERR_CUDA, cudaGetErrorString(le));
+  fill_report(rep, h, L.count);
+  // iterations completed with an update == number of ping-pong swaps
+  int swaps = h->itr;
+  if (h->status == PA_BAD_TOL && method != PA_METHOD_BICGSTAB) swaps += 1;  // x was written, itr not bumped
+  rep->result_in_alt = swaps & 1;
+  return PA_OK;
+}
+
+template <typename T>
+static int apply_impl(const pa_grid* pg, const pa_equation* peq, const T* phi, T* out,
+                      cudaStream_t s) {
+  GridDev g = make_grid(*pg);
+  EqDev<T> eq = make_eq<T>(*peq);
+  k_apply<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, out);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
+}  // namespace pa
+
+using namespace pa;
+
+extern "C" {
+
+const char* pa_last_error(void) { return g_err.c_str(); }
+int pa_abi_version(void) { return PA_ABI_VERSION; }
+int pa_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+#define PA_REQUIRE_DEVICE()                                                               \
+  do {                                                                                    \
+    if (pa_device_count() < 1)                                                            \
+      return fail(PA_ERR_CUDA, "no CUDA device: pyapes_b200 has no CPU path");            \
+  } while (0)
+
+#define PA_DISPATCH(dtype, CALL)                                                          \
+  do {                                                                                    \
+    if ((dtype) == PA_F64) {                                                              \
+      typedef double T;                                                                   \
+      return CALL;                                                                        \
+    } else if ((dtype) == PA_F32) {                                                       \
+      typedef float T;                                                                    \
+      return CALL;                                                                        \
+    }                                                                                     \
+    return fail(PA_ERR_ARG, "dtype must be PA_F32 or PA_F64");                            \
+  } while (0)
+
+int pa_stencil_apply(const pa_grid* g, const pa_equation* eq, int dtype, const void* phi,
+                     void* out, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq))) return rc;
+  if (!phi || !out || phi == out) return fail(PA_ERR_ARG, "phi/out null or aliased");
+  PA_DISPATCH(dtype, apply_impl<T>(g, eq, (const T*)phi, (T*)out, (cudaStream_t)stream));
+}
+
+}  // extern "C"
+template <typename T>
+static int grad_impl(const pa_grid* pg, const pa_op* op, const T* phi, T* out, cudaStream_t s) {
+  GridDev g = make_grid(*pg);
+  pa_equation e;
+  memset(&e, 0, sizeof(e));
+  e.nops = 1;
+  e.ops[0] = *op;
+  EqDev<T> eq = make_eq<T>(e);
+  k_grad<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq.op[0], phi, out);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+extern "C" {
+
+int pa_grad_apply(const pa_grid* g, const pa_op* op, int dtype, const void* phi, void* out,
+                  void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g))) return rc;
+  if (!op || op->kind != PA_OP_STAR) return fail(PA_ERR_ARG, "grad needs a PA_OP_STAR operator");
+  if (!phi || !out || phi == out) return fail(PA_ERR_ARG, "phi/out null or aliased");
+  PA_DISPATCH(dtype, grad_impl<T>(g, op, (const T*)phi, (T*)out, (cudaStream_t)stream));
+}
+
+}  // extern "C"
+template <typename T>
+static int bc_impl(const pa_grid* pg, int nfaces, const pa_face_bc* faces, T* phi,
+                   cudaStream_t s) {
+  GridDev g = make_grid(*pg);
+  Launcher L{s};
+  launch_bcs<T>(L, g, nfaces, faces, phi, nullptr);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+extern "C" {
+
+int pa_bc_apply(const pa_grid* g, int nfaces, const pa_face_bc* faces, int dtype, void* phi,
+                void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!phi) return fail(PA_ERR_ARG, "phi is null");
+  PA_DISPATCH(dtype, bc_impl<T>(g, nfaces, faces, (T*)phi, (cudaStream_t)stream));
+}
+
+size_t pa_solver_workspace_bytes(const pa_grid* g, int dtype, int method) {
+  if (!g) return 0;
+  long long cells = (long long)g->n[0] * g->n[1] * g->n[2];
+  return ws_bytes(cells, dtype == PA_F64 ? 8 : 4, method_nvec(method));
+}
+
+static int check_solver_args(const pa_grid* g, const pa_equation* eq, int nfaces,
+                             const pa_face_bc* faces, void* x, void* x_alt, const void* rhs,
+                             const pa_solver_cfg* cfg, void* ws, pa_report* rep) {
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!x || !x_alt || !rhs || !cfg || !ws || !rep) return fail(PA_ERR_ARG, "null argument");
+  if (x == x_alt) return fail(PA_ERR_ARG, "x and x_alt must not alias");
+  if (cfg->max_it < 0) return fail(PA_ERR_ARG, "max_it must be >= 0");
+  return PA_OK;
+}
+
+int pa_cg_solve(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg,
+                void* ws, size_t ws_bytes_, pa_report* report, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
+  if (rc) return rc;
+  PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
+                                   (const T*)rhs, cfg, ws, ws_bytes_, report,
+                                   (cudaStream_t)stream));
+}
+
+int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
+                  size_t ws_bytes_, double* out_ms, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!x || !x_alt || !rhs || !ws || !out_ms || iters < 1) return fail(PA_ERR_ARG, "bad argument");
+  PA_DISPATCH(dtype, profile_cg<T>(g, eq, nfaces, faces, (T*)x, (T*)x_alt, (const T*)rhs, iters,
+                                   variant, ws, ws_bytes_, out_ms, (cudaStream_t)stream));
+}
+
+int pa_bicgstab_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
+                      const pa_face_bc* faces, int dtype, void* x, void* x_alt,
+                      const void* rhs, const pa_solver_cfg* cfg, void* ws, size_t ws_bytes_,
+                      pa_report* report, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
+  if (rc) return rc;
+  PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_BICGSTAB, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
+                                   (const T*)rhs, cfg, ws, ws_bytes_, report,
+                                   (cudaStream_t)stream));
+}
+
+int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
+                    const pa_face_bc* faces, int dtype, void* x, void* x_alt, const void* rhs,
+                    const pa_solver_cfg* cfg, void* ws, size_t ws_bytes_, pa_report* report,
+                    void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
+  if (rc) return rc;
+  PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_JACOBI, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
+                                   (const T*)rhs, cfg, ws, ws_bytes_, report,
+                                   (cudaStream_t)stream));
+}
+
+}  // extern "C"
+template <typename T>
+static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
+                      const pa_face_bc* faces, const T* phi, T* phi_new, const T* rhs, double dt,
+                      cudaStream_t s) {
+  GridDev g = make_grid(*pg);
+  EqDev<T> eq = make_eq<T>(*peq);
+  Launcher L{s};
+  k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, phi_new, rhs,
+                                                                   (T)dt, nullptr, nullptr);
+  launch_bcs<T>(L, g, nfaces, faces, phi_new, nullptr);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+extern "C" {
+
+int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, const void* phi, void* phi_new, const void* rhs, double dt,
+                  void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!phi || !phi_new || phi == phi_new) return fail(PA_ERR_ARG, "phi/phi_new null or aliased");
+  PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (const T*)phi, (T*)phi_new,
+                                   (const T*)rhs, dt, (cudaStream_t)stream));
+}
+
+int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,
+                     const pa_face_bc* faces, int dtype, void* x_host, const void* rhs_host,
+                     const pa_solver_cfg* cfg, pa_report* report) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!x_host || !rhs_host || !cfg || !report) return fail(PA_ERR_ARG, "null argument");
+  size_t esz = dtype == PA_F64 ? 8 : 4;
+  size_t vb = (size_t)g->n[0] * g->n[1] * g->n[2] * esz;
+  size_t wsb = pa_solver_workspace_bytes(g, dtype, PA_METHOD_CG);
+  char* dev = nullptr;
+  PA_CUDA(cudaMalloc((void**)&dev, 3 * align_up(vb, 256) + wsb));
+  char* x = dev;
+  char* xa = dev + align_up(vb, 256);
+  char* rhs = dev + 2 * align_up(vb, 256);
+  char* ws = dev + 3 * align_up(vb, 256);
+  cudaStream_t s = nullptr;
+  cudaError_t e = cudaMemcpyAsync(x, x_host, vb, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rhs, rhs_host, vb, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return fail(PA_ERR_CUDA, cudaGetErrorString(e));
+  }
+  rc = pa_cg_solve(g, eq, nfaces, faces, dtype, x, xa, rhs, cfg, ws, wsb, report, (void*)s);
+  if (rc == PA_OK) {
+    e = cudaMemcpyAsync(x_host, report->result_in_alt ? xa : x, vb, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(PA_ERR_CUDA, cudaGetErrorString(e));
+    report->result_in_alt = 0;
+  }
+  cudaFree(dev);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// Shared device-side definitions for the pyapes_b200 kernels (sm_100a).
+//
+// Arithmetic policy: the whole library is compiled with -fmad=false and every update is
+// written in the reference's operation order, so that elementwise results are bit-identical
+// to the reference's eager torch ops (one IEEE rounding per torch op).  See DESIGN.md §3.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pyapes_b200.h"
+
+namespace pa {
+
+constexpr int kMaxOps = PA_MAX_OPS;
+constexpr int kBlock = 256;          // threads per CTA of the generic kernels
+constexpr int kMaxPartials = 4096;   // upper bound on CTAs taking part in a reduction
+constexpr int kNumSums = 4;          // reduction slots per launch
+constexpr int kNumSMs = 148;         // B200
+
+// ---- grid ------------------------------------------------------------------------------
+struct GridDev {
+  int n[3];
+  int lo[3], hi[3];
+  int gn0, goff0, olo0, ohi0;
+  int act[3];  // 1 if the kernel axis carries a mesh axis
+  long long cells;
+};
+
+inline GridDev make_grid(const pa_grid& g) {
+  GridDev d;
+  for (int a = 0; a < 3; ++a) {
+    d.n[a] = g.n[a];
+    d.lo[a] = g.lo[a];
+    d.hi[a] = g.hi[a];
+    d.act[a] = (a >= 3 - g.ndim) ? 1 : 0;
+  }
+  d.gn0 = g.gn0;
+  d.goff0 = g.goff0;
+  d.olo0 = g.olo0;
+  d.ohi0 = g.ohi0;
+  d.cells = (long long)g.n[0] * g.n[1] * g.n[2];
+  return d;
+}
+
+// ---- equation --------------------------------------------------------------------------
+template <typename T>
+struct OpDev {
+  int kind;
+  int has_param;
+  T sign;
+  T param;
+  T coef[3][3][3];
+  const T* adv;
+  T two_dx[3];
+  T dx[3];
+  int zero_am_lo[3];
+  int zero_ap_hi[3];
+};
+
+template <typename T>
+struct EqDev {
+  int nops;
+  OpDev<T> op[kMaxOps];
+};
+
+template <typename T>
+inline EqDev<T> make_eq(const pa_equation& e) {
+  EqDev<T> d;
+  d.nops = e.nops;
+  for (int k = 0; k < e.nops && k < kMaxOps; ++k) {
+    const pa_op& s = e.ops[k];
+    OpDev<T>& o = d.op[k];
+    o.kind = s.kind;
+    o.has_param = s.has_param;
+    o.sign = (T)s.sign;
+    o.param = (T)s.param;
+    for (int a = 0; a < 3; ++a) {
+      for (int c = 0; c < 3; ++c)
+        for (int q = 0; q < 3; ++q) o.coef[a][c][q] = (T)s.coef[a][c][q];
+      o.two_dx[a] = (T)s.two_dx[a];
+      o.dx[a] = (T)s.dx[a];
+      o.zero_am_lo[a] = s.zero_am_lo[a];
+      o.zero_ap_hi[a] = s.zero_ap_hi[a];
+    }
+    o.adv = (const T*)s.adv;
+  }
+  return d;
+}
+
+// ---- faces -----------------------------------------------------------------------------
+template <typename T>
+struct FaceDev {
+  int axis, side, kind;
+  T value;
+  const T* values;
+};
+
+// ---- index helpers ---------------------------------------------------------------------
+struct Cell {
+  int i[3];
+  long long idx;
+};
+
+__device__ __forceinline__ Cell decode(const GridDev& g, long long idx) {
+  Cell c;
+  c.idx = idx;
+  int n12 = g.n[1] * g.n[2];
+  c.i[0] = (int)(idx / n12);
+  int rem = (int)(idx - (long long)c.i[0] * n12);
+  c.i[1] = rem / g.n[2];
+  c.i[2] = rem - c.i[1] * g.n[2];
+  return c;
+}
+
+__device__ __forceinline__ long long stride_of(const GridDev& g, int a) {
+  return a == 2 ? 1LL : (a == 1 ? (long long)g.n[2] : (long long)g.n[1] * g.n[2]);
+}
+
+// coefficient class of index `i` along axis `a` (fdc.py:84-93 masks rolled one inward)
+__device__ __forceinline__ int coef_class(const GridDev& g, int a, int i) {
+  int gi = (a == 0) ? i + g.goff0 : i;
+  int gn = (a == 0) ? g.gn0 : g.n[a];
+  return gi == 1 ? 1 : (gi == gn - 2 ? 2 : 0);
+}
+
+__device__ __forceinline__ bool in_region(const GridDev& g, const Cell& c) {
+  return c.i[0] >= g.lo[0] && c.i[0] < g.hi[0] && c.i[1] >= g.lo[1] && c.i[1] < g.hi[1] &&
+         c.i[2] >= g.lo[2] && c.i[2] < g.hi[2];
+}
+
+// a cell on the outer shell of the GLOBAL box (any active axis index 0 or n-1)
+__device__ __forceinline__ bool on_shell(const GridDev& g, const Cell& c) {
+  bool s = false;
+  if (g.act[0]) {
+    int gi = c.i[0] + g.goff0;
+    s |= (gi == 0) | (gi == g.gn0 - 1);
+  }
+  if (g.act[1]) s |= (c.i[1] == 0) | (c.i[1] == g.n[1] - 1);
+  if (g.act[2]) s |= (c.i[2] == 0) | (c.i[2] == g.n[2] - 1);
+  return s;
+}
+
+__device__ __forceinline__ bool owned(const GridDev& g, const Cell& c) {
+  return c.i[0] >= g.olo0 && c.i[0] < g.ohi0;
+}
+
+// ---- the operator sum at one cell, given a functor that returns field values ------------
+// `val(idx)` returns the field at linear index idx.  Neighbours wrap around like
+// torch.roll (fdc.py:198); on non-periodic axes the wrapped values only reach cells outside
+// the solver region.
+template <typename T, typename F>
+__device__ __forceinline__ T eval_equation(const GridDev& g, const EqDev<T>& eq, const Cell& c,
+                                           F val) {
+  T vc = val(c.idx);
+  T vp[3], vm[3];
+  long long ip[3], im[3];
+  int cls[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!g.act[a]) continue;
+    long long st = stride_of(g, a);
+    int i = c.i[a], n = g.n[a];
+    ip[a] = (i + 1 == n) ? c.idx - (long long)(n - 1) * st : c.idx + st;
+    im[a] = (i == 0) ? c.idx + (long long)(n - 1) * st : c.idx - st;
+    vp[a] = val(ip[a]);
+    vm[a] = val(im[a]);
+    cls[a] = coef_class(g, a, i);
+  }
+  T res = (T)0;
+  for (int k = 0; k < eq.nops; ++k) {
+    const OpDev<T>& o = eq.op[k];
+    T acc = (T)0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (!g.act[a]) continue;
+      T Ap, Ac, Am;
+      if (o.kind == PA_OP_STAR) {
+        Ap = o.coef[a][cls[a]][0];
+        Ac = o.coef[a][cls[a]][1];
+        Am = o.coef[a][cls[a]][2];
+      } else if (o.kind == PA_OP_DIV_CENTRAL_FIELD) {
+        // Ap = 1*u[+1] / 2dx ; Ac = 0 ; Am = -1*u[-1] / 2dx  (fdc.py:736-738, 607-609)
+        Ap = (cls[a] == 2 && o.zero_ap_hi[a]) ? (T)0 : o.adv[ip[a]] / o.two_dx[a];
+        Ac = (T)0;
+        Am = (cls[a] == 1 && o.zero_am_lo[a]) ? (T)0 : (-o.adv[im[a]]) / o.two_dx[a];
+      } else if (o.kind == PA_OP_DIV_UPWIND_FIELD) {
+        T u = o.adv[c.idx];  // fdc.py:765-770 (same u on every axis, no 1/dx)
+        Ap = (T)2 * (u < (T)0 ? u : (T)0);
+        Ac = (T)0;
+        Am = (T)2 * (u > (T)0 ? u : (T)0);
+      } else {
+        T u = o.adv[c.idx];
+        T up = u > (T)0 ? u : (T)0, um = u < (T)0 ? u : (T)0;
+        Ap = um / o.dx[a];
+        Ac = (up - um) / o.dx[a];
+        Am = (-up) / o.dx[a];
+      }
+      // ((0 + 0*v[+2]) + Ap*v[+1]) + Ac*v) + Am*v[-1]) + 0*v[-2]   (fdc.py:188-198)
+      T s = Ap * vp[a];
+      s = s + Ac * vc;
+      s = s + Am * vm[a];
+      acc = acc + s;  // axes accumulate into zeros (fdc.py:103-108)
+    }
+    if (o.has_param) acc = acc * o.param;  // fdm.py:169
+    acc = acc * o.sign;                    // ops.py:140-143
+    res = res + acc;                       // ops.py:149
+  }
+  return res;
+}
+
+// ---- reductions ------------------------------------------------------------------------
+// Device-resident solver state: every scalar of the Krylov recurrences lives here so that an
+// iteration needs no host round trip (SURVEY §7 "hard parts").
+struct SolverState {
+  double sum[8];    // finalized reductions (meaning depends on the solver)
+  double scal[8];   // alpha, beta, omega, rho, ... already rounded to the field dtype
+  double tol;
+  double tolerance;
+  int itr;
+  int max_it;
+  int done;
+  int status;
+  int finished_flag;  // bicgstab's `finished`
+  int pad;
+  unsigned int ticket[8];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NS doubles; result valid in thread 0.  Fixed shuffle/smem order ->
+// deterministic for a fixed launch geometry.
+template <int NS>
+__device__ __forceinline__ void block_sum(double (&v)[NS], double* smem /* NS*32 */) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    double x = warp_sum(v[s]);
+    if (lane == 0) smem[s * 32 + w] = x;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      double x = lane < nw ? smem[s * 32 + lane] : 0.0;
+      x = warp_sum(x);
+      v[s] = x;
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-wide deterministic reduction: every CTA stores its partials, the last CTA to arrive
+// (ticket) sums them in a fixed order and calls fin(sums) from thread 0.
+template <int NS, typename Fin>
+__device__ __forceinline__ void grid_reduce(double (&v)[NS], double* partials, int nblocks,
+                                            int block_id, unsigned int* ticket, Fin fin) {
+  __shared__ double red_smem[NS * 32];
+  __shared__ bool is_last;
+  block_sum<NS>(v, red_smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) partials[s * kMaxPartials + block_id] = v[s];
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == (unsigned int)nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    acc[s] = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+      acc[s] += __ldcg(&partials[s * kMaxPartials + b]);
+  }
+  block_sum<NS>(acc, red_smem);
+  if (threadIdx.x == 0) {
+    *ticket = 0u;
+    fin(acc);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T nan_to_num0(T x) {  // linalg.py:302-305
+  return (isnan(x) || isinf(x)) ? (T)0 : x;
+}
+
+}  // namespace pa

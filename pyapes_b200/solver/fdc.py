@@ -1,0 +1,278 @@
+"""Explicit finite-difference discretisers `FDC().laplacian / .grad / .div`
+(reference: pyapes/solver/fdc.py).
+
+Public surface kept: `Discretizer.build_A_coeffs / adjust_rhs / apply / __call__ / reset /
+set_config`, the attributes `A_coeffs`, `rhs_adj`, and the class-level singletons on `FDC`.
+
+Underneath, `apply` is one CUDA launch (csrc: k_apply / k_grad) with the boundary-adjacent
+coefficient edits resolved in-kernel, instead of 5 rolls x 5 multiplies x 5 adds per axis
+against full-size coefficient tensors (fdc.py:171-200).  `edge=True`, `DiffFlux`, `jacobian`
+and `hessian` are "next" rows of SURVEY.md §8(f) and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any
+
+import torch
+from torch import Tensor
+
+from pyapes_b200 import _lower as L
+from pyapes_b200 import _native as N
+from pyapes_b200.solver.types import DiscretizerConfigType, DivConfigType
+from pyapes_b200.variables import Field
+
+
+def _scalar_field(var: Field, who: str) -> None:
+    if var.dim != 1:
+        raise NotImplementedError(
+            f"pyapes_b200 {who}: only scalar fields (Field.dim == 1) are on the CUDA path; the "
+            "reference's solvers do not work for vector fields either (SURVEY.md §0 item 5)."
+        )
+
+
+def _plane(var: Field, bc, shift: int):
+    a, n = bc.bc_face_dim, var.nx[bc.bc_face_dim]
+    base = 0 if bc.bc_n_dir < 0 else n - 1
+    idx: list[Any] = [slice(None)] * var.mesh.dim
+    idx[a] = (base - bc.bc_n_dir * shift) % n
+    return tuple(idx)
+
+
+def _return_bc_val(bc, var: Field, dim: int, shape) -> Tensor | float:
+    """fdc.py:803-817."""
+    v = bc.bc_val
+    if callable(v):
+        out = v(var.mesh.grid, bc.bc_mask, var(), bc.bc_n_vec)
+        return out.reshape(shape) if isinstance(out, Tensor) and out.numel() > 1 else out
+    if isinstance(v, list):
+        return v[dim]
+    if isinstance(v, (float, int)):
+        return v
+    if v is None:
+        return 0.0
+    raise ValueError(f"Unknown boundary condition value: {v}")
+
+
+def _grad_like_rhs(var: Field, gamma_min: Tensor, gamma_max: Tensor) -> Tensor:
+    """fdc.py:505-540: Neumann faces only; lower faces take gamma_max, upper gamma_min."""
+    out = torch.zeros_like(var())
+    if var.bcs is None:
+        return out
+    for j in range(var.mesh.dim):
+        for bc in var.bcs:
+            if bc.bc_type != "neumann":
+                continue
+            pl = _plane(var, bc, 1)
+            at_bc = _return_bc_val(bc, var, 0, out[0][pl].shape)
+            g = gamma_max if bc.bc_n_dir < 0 else gamma_min
+            out[0][pl] -= (1 / 3) * (at_bc * bc.bc_n_vec[j]) * g[0][pl]
+    return out
+
+
+class Discretizer:
+    A_coeffs: Any = None
+    rhs_adj: Tensor | None = None
+    _op_type: str = "Discretizer"
+    _config: DiscretizerConfigType | None = None
+
+    op_type = property(lambda self: self._op_type)
+    config = property(lambda self: self._config)
+
+    def _edge(self) -> bool:
+        if self.config is not None and self.op_type.lower() in self.config:
+            return bool(self.config[self.op_type.lower()]["edge"])  # type: ignore[literal-required]
+        if self.config is None:
+            warnings.warn("FDC: config is not defined! Using default config (edge=False).")
+        return False
+
+    def apply(self, A_coeffs, var: Field) -> Tensor:
+        """The stencil (fdc.py:67-118) as one kernel launch."""
+        assert A_coeffs is not None, "FDC: A_A_coeffs is not defined!"
+        if self._edge():
+            raise NotImplementedError(
+                "pyapes_b200: edge=True one-sided boundary stencils are not built yet (SURVEY.md §8(f) item 1)"
+            )
+        _scalar_field(var, f"FDC.{self.op_type}")
+        phi = var()
+        N.require_cuda(phi, "field")
+        nd = var.mesh.dim
+        grid = L.lower_grid(var.nx, var.bcs)
+        op, keep = L.lower_op(A_coeffs, nd, phi.dtype)
+        code, stream = N.dtype_code(phi.dtype), N.current_stream(phi.device)
+        if self.op_type == "Grad":
+            out = torch.empty((1, nd, *var.nx), dtype=phi.dtype, device=phi.device)
+            N.check(N.lib().pa_grad_apply(grid, op, code, phi.data_ptr(), out.data_ptr(), stream))
+        else:
+            eq = N.Equation()
+            eq.nops = 1
+            eq.ops[0] = op
+            out = torch.empty_like(phi)
+            N.check(N.lib().pa_stencil_apply(grid, eq, code, phi.data_ptr(), out.data_ptr(), stream))
+        del keep
+        return out
+
+    def reset(self) -> None:
+        self.A_coeffs = None
+        self.rhs_adj = None
+
+    def set_config(self, config: DiscretizerConfigType) -> None:
+        self._config = config
+
+    def __call__(self, *args):
+        if len(args) == 1:
+            assert isinstance(args[0], Field), "FDC: only `Field` is allowed for var!"
+            var = args[0]
+            self.A_coeffs = self.build_A_coeffs(var)
+            self.rhs_adj = self.adjust_rhs(var)
+            return self.apply(self.A_coeffs, var)
+        assert isinstance(args[0], (Field, Tensor, float)), "FDC: for var_j, Field, Tensor and float are allowed!"
+        assert isinstance(args[1], Field), "FDC: only `Field` is allowed for var_i!"
+        self.A_coeffs = self.build_A_coeffs(args[0], args[1], config=self.config)
+        self.rhs_adj = self.adjust_rhs(args[0], args[1], config=self.config)
+        self.var_addition = args[0]
+        return self.apply(self.A_coeffs, args[1])
+
+
+class Laplacian(Discretizer):
+    _op_type = "Laplacian"
+
+    @staticmethod
+    def build_A_coeffs(var: Field) -> L.StarCoeffs:
+        """fdc.py:375-423: Neumann/Symmetry faces edit the plane next to them
+        (2/3, -2/3, 0 | 0, -2/3, 2/3), everything / dx^2."""
+        return L.laplacian_star(var.nx, var.mesh._dx, var.bcs, var().dtype)
+
+    @staticmethod
+    def adjust_rhs(var: Field) -> Tensor:
+        """fdc.py:425-458: Neumann faces add (2/3) V n / dx on the plane next to them."""
+        out = torch.zeros_like(var())
+        if var.bcs is None:
+            return out
+        dx = var.dx
+        for j in range(var.mesh.dim):
+            for bc in var.bcs:
+                if bc.bc_type != "neumann":
+                    continue
+                pl = _plane(var, bc, 1)
+                alpha = torch.zeros_like(out[0][pl])
+                at_bc = _return_bc_val(bc, var, 0, out[0][pl].shape)
+                out[0][pl] += (2 / 3 - alpha) * (at_bc * bc.bc_n_vec[j]) / dx[j]
+        return out
+
+
+class Grad(Discretizer):
+    """Central gradient; result shape `(var.dim, mesh.dim, *nx)` (fdc.py:461-502)."""
+
+    _op_type = "Grad"
+
+    @staticmethod
+    def build_A_coeffs(var: Field) -> L.StarCoeffs:
+        return L.grad_star(var.nx, var.mesh._dx, var.bcs, var().dtype)
+
+    @staticmethod
+    def adjust_rhs(var: Field) -> Tensor:
+        ones = torch.ones_like(var())
+        return _grad_like_rhs(var, ones, ones)
+
+
+def _check_limiter(config: DivConfigType | None) -> str:
+    if config is not None and "limiter" in config:
+        return config["limiter"].lower()
+    warnings.warn("FDM: no limiter is specified. Use `none` (central difference) as a default.")
+    return "none"
+
+
+def _adv_of(var_j, var_i: Field):
+    """fdc.py:775-792 -> float (constant) or a (1,*nx) tensor."""
+    if isinstance(var_j, (float, int)) and not isinstance(var_j, bool):
+        return float(var_j)
+    if isinstance(var_j, Tensor):
+        assert var_j.shape == var_i().shape, "FDC Div: adv shape must match var_i shape"
+        return var_j
+    if isinstance(var_j, Field):
+        return var_j()
+    raise NotImplementedError(
+        "pyapes_b200 FDC.Div: Jac/Hess-driven advection is out of scope (SURVEY.md §8(f) item 3)"
+    )
+
+
+class Div(Discretizer):
+    """d(u_j phi)/dx_j, limiter "none" (central), "upwind" (the reference's formula,
+    fdc.py:746-772: 2 min(u,0) phi[+1] + 2 max(u,0) phi[-1], no 1/dx) or "upwind_fd"
+    (new: the first-order upwind difference the reference's own test intends)."""
+
+    _op_type = "Div"
+
+    @staticmethod
+    def build_A_coeffs(var_j, var_i: Field, config: DiscretizerConfigType):
+        assert "div" in config, "FDC Div: config should contain 'div' key."
+        limiter = _check_limiter(config["div"])
+        adv = _adv_of(var_j, var_i)
+        if isinstance(adv, float):
+            return L.div_star_const(adv, var_i.nx, var_i.mesh._dx, var_i.bcs, var_i().dtype, limiter)
+        if adv.shape[0] != 1:
+            adv = adv[0:1]  # scalar var_i uses adv[0] on every axis (fdc.py:735,760)
+        return L.div_field(adv.contiguous(), var_i.nx, var_i.mesh._dx, var_i.bcs, limiter)
+
+    @staticmethod
+    def adjust_rhs(var_j, var_i: Field, config: DiscretizerConfigType) -> Tensor:
+        """fdc.py:666-694."""
+        if var_i.bcs is None:
+            return torch.zeros_like(var_i())
+        assert "div" in config, "FDC Div: config should contain 'div' key."
+        limiter = _check_limiter(config["div"])
+        adv = _adv_of(var_j, var_i)
+        if isinstance(adv, float):
+            adv = torch.ones_like(var_i()) * adv
+        if limiter == "none":
+            return _grad_like_rhs(var_i, 2.0 * adv, 2.0 * adv)
+        if limiter == "upwind":
+            z = torch.zeros_like(var_i())
+            return _grad_like_rhs(var_i, 2.0 * torch.min(adv, z), 2.0 * torch.max(adv, z))
+        if limiter == "upwind_fd":
+            return torch.zeros_like(var_i())
+        if limiter == "quick":
+            raise NotImplementedError("FDC Div: quick scheme is not implemented yet.")
+        raise RuntimeError(f"FDC Div: {limiter=} is an unknown limiter type.")
+
+
+class DiffFlux:
+    def __call__(self, *_):
+        raise NotImplementedError("pyapes_b200: DiffFlux is out of the hot-path scope (SURVEY.md §8(f) item 1)")
+
+
+class FDC:
+    """Collection of the explicit discretisers; like the reference (fdc.py:860-879) the
+    operators are class-level singletons and the constructor pushes `config` into them."""
+
+    div: Div = Div()
+    laplacian: Laplacian = Laplacian()
+    grad: Grad = Grad()
+    diffFlux: DiffFlux = DiffFlux()
+
+    def __init__(self, config: DiscretizerConfigType | None = None):
+        self.config = config
+        if config is not None:
+            for key in config:
+                scheme = getattr(self, key, None)
+                if isinstance(scheme, Discretizer):
+                    scheme.set_config(config)
+
+    def update_config(self, scheme: str, target: str, val: str):
+        if self.config is not None:
+            self.config.setdefault(scheme, {})[target] = val  # type: ignore[misc]
+        else:
+            self.config = {scheme: {target: val}}  # type: ignore[misc]
+        for key in self.config:
+            s = getattr(self, key, None)
+            if isinstance(s, Discretizer):
+                s.set_config(self.config)
+
+
+def jacobian(var: Field):
+    raise NotImplementedError("pyapes_b200: jacobian() needs edge=True stencils (SURVEY.md §8(f) item 1)")
+
+
+def hessian(var: Field):
+    raise NotImplementedError("pyapes_b200: hessian() needs edge=True stencils (SURVEY.md §8(f) item 1)")

@@ -40,3 +40,41 @@ def oracle_terms(case):
     limiter = (case.get("div_cfg") or {}).get("div", {}).get("limiter", "none")
     return [O.Term(kind, sign=float(sign), param=param, limiter=limiter if kind == "div" else "none")
             for kind, sign, param in case["terms"]]
+
+
+# ---- product-side builders (pyapes_b200 public API) ----------------------------------------
+def product_field(case, device="cuda", init=0.0):
+    """Mesh + Field of the product package from a fixture's spec / frozen BC list."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.variables import Field
+
+    spec = case["spec"]
+    mesh = Mesh(Box(list(spec["lower"]), list(spec["upper"])), None, list(spec["nx"]), device, spec["dtype"])
+    cfg = []
+    for face, kind, val in case["bcs"]:
+        if isinstance(val, torch.Tensor):
+            val = val.to(device)
+        cfg.append({"bc_face": face, "bc_type": kind, "bc_val": val, "bc_val_opt": None})
+    var = Field("p", 1, mesh, {"domain": cfg, "obstacle": None})
+    if init != 0.0:
+        var.set_var_tensor(torch.zeros_like(var()) + init)
+    return mesh, var
+
+
+def product_equation(case, fdm, var, dev):
+    eq = None
+    for kind, sign, param in case["terms"]:
+        if isinstance(param, torch.Tensor):
+            param = param.to(dev)
+        if kind == "laplacian":
+            op = fdm.laplacian(var) if param is None else fdm.laplacian(param, var)
+        elif kind == "grad":
+            op = fdm.grad(var) if param is None else fdm.grad(param, var)
+        else:
+            op = fdm.div(param, var)
+        if eq is None:
+            eq = -op if sign < 0 else op
+        else:
+            eq = eq - op if sign < 0 else eq + op
+    return eq

@@ -140,7 +140,7 @@ def op_case(name, spec, seed=7, u_const=0.7):
 
 
 def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_cfg=None,
-                keep_solution=True, _second_pass=True):
+                keep_solution=True, _second_pass=True, _perturb=0):
     """terms: [(kind, sign, param)], rhs_kind: float | ("rand", seed) | "poisson_nd" | tensor-fn"""
     mesh, var = build(spec)
     if init != 0.0:
@@ -155,6 +155,12 @@ def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_
     else:
         rhs = float(rhs_kind)
     rhs_in = rhs.clone() if isinstance(rhs, torch.Tensor) else rhs
+    if _perturb:
+        # 1-ulp-level relative noise on the RHS: how far does the REFERENCE move against itself?
+        if not isinstance(rhs, torch.Tensor):
+            rhs = torch.zeros_like(var()) + rhs
+        gp = torch.Generator().manual_seed(_perturb)
+        rhs = rhs * (1 + 2.2e-16 * torch.randn(rhs.shape, generator=gp, dtype=torch.float64).to(rhs.dtype))
 
     fdm = FDM(div_cfg) if div_cfg is not None else FDM()
     eq = None
@@ -187,6 +193,14 @@ def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_
         report_1thr = alt["report"]
     else:
         report_1thr = None
+    sens_itr, sens_dsol = None, None
+    if _second_pass and method == "bicgstab" and spec["dtype"] == "double":
+        sens_itr, sens_dsol = [], 0.0
+        for k in range(1, 6):
+            alt = solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init, div_cfg,
+                              keep_solution=True, _second_pass=False, _perturb=k)
+            sens_itr.append(alt["report"]["itr"])
+            sens_dsol = max(sens_dsol, (alt["solution"] - sol).abs().max().item())
     case = {
         "name": name,
         "spec": spec,
@@ -203,6 +217,10 @@ def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_
         "init": init,
         "report": report,
         "report_1thr": report_1thr,
+        # BiCGSTAB only: iteration counts / max solution change of the reference under five
+        # 1-ulp-level RHS perturbations (its own rounding sensitivity)
+        "sens_itr": sens_itr,
+        "sens_dsol": sens_dsol,
         "threads": torch.get_num_threads(),
         "sol_sum": sol.double().sum().item(),
         "sol_abs_sum": sol.double().abs().sum().item(),
@@ -211,7 +229,7 @@ def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_
         case["solution"] = sol.clone()
     if _second_pass:
         print(f"  {name:34s} {method:9s} itr={report['itr']:5d}/{report_1thr['itr']:5d} (8thr/1thr) "
-              f"tol={report['tol']:.16e}/{report_1thr['tol']:.3e} sum={case['sol_sum']!r}")
+              f"tol={report['tol']:.16e}/{report_1thr['tol']:.3e} sum={case['sol_sum']!r} sens={sens_itr} {sens_dsol}")
     return case
 
 
@@ -317,6 +335,12 @@ def main():
                            L1, ("rand", 1234), "cg", 1e-8, 25))
     sol.append(solver_case("rand_3d_16_bicgstab_maxit", dspec([0, 0, 0], [1, 1, 1], [16, 16, 16], [D0] * 6),
                            L1, ("rand", 1234), "bicgstab", 1e-30, 10))
+    for m_it in (5, 20):
+        sol.append(solver_case(f"rand_3d_24_mixed_bicgstab_it{m_it}", dspec([0, 0, 0], [1, 1, 1], [24, 20, 28], mixed3),
+                               L1, ("rand", 1234), "bicgstab", 1e-30, m_it))
+        sol.append(solver_case(f"rand_2d_40_bicgstab_it{m_it}", dspec([0, 0], [1, 2], [40, 36],
+                               [("neumann", 0.3), ("dirichlet", 1.0), ("dirichlet", 0.0), ("symmetry", None)]),
+                               L1, ("rand", 77), "bicgstab", 1e-30, m_it))
     # upwind-div + laplacian steady problem through BiCGSTAB
     sol.append(solver_case("advdiff_2d_33_bicgstab", dspec([0, 0], [1, 1], [33, 33], [D0] * 4),
                            [("div", 1.0, 0.5), ("laplacian", -1.0, 0.1)], ("rand", 1234), "bicgstab", 1e-8, 2000,

@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path (through the public pyapes-style API, which calls the C ABI)
+against the golden fixtures of the real reference and against the CPU oracle.
+
+Bar: operators, rhs adjustment and BC application are BIT-EXACT in fp64 and fp32 (the kernels
+reproduce the reference's rounding sequence); solvers reproduce the iteration count exactly
+and the final tolerance to 1e-10 absolute (north_star); solutions to 1e-9 relative.
+"""
+import warnings
+
+import pytest
+import torch
+
+from oracle import fd_oracle as O
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+OPS = U.load("ops.pt")
+SOL = U.load("solvers.pt")
+DEV = "cuda"
+
+
+def _solver(var, rhs, make_eq, cfg=None):
+    from pyapes_b200.solver.ops import Solver
+
+    s = Solver(cfg)
+    s.set_eq(make_eq == rhs)
+    return s
+
+
+@pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
+def test_operator_fixtures_bit_exact(case):
+    from pyapes_b200.solver.fdc import FDC
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.linalg import _apply_bc_otf
+
+    mesh, var = U.product_field(case, DEV)
+    phi = case["phi"].to(DEV)
+    var.set_var_tensor(phi.clone())
+    out = case["out"]
+    nd = mesh.dim
+
+    def same(got, key):
+        ref = out[key]
+        got = got.cpu()
+        assert got.shape == ref.shape, (key, got.shape, ref.shape)
+        assert torch.equal(got, ref), f"{key}: max|d|={(got - ref).abs().max().item():.3e}"
+
+    for tag, make in (
+        ("lap", lambda f: f.laplacian(var)),
+        ("lap_c", lambda f: f.laplacian(0.37, var)),
+        ("neg_lap_c", lambda f: -f.laplacian(2.5, var)),
+    ):
+        rhs = torch.zeros_like(var())
+        s = _solver(var, rhs, make(FDM()))
+        same(s.Aop(var), tag)
+        same(rhs, tag + "_rhs_adj")
+
+    fdc = FDC({"grad": {"edge": False}})
+    same(fdc.grad(var), "grad")
+    same(fdc.grad.rhs_adj, "grad_rhs_adj")
+
+    u_c, u_t = case["u_const"], out["u_tensor"].to(DEV)
+    fdc = FDC({"div": {"limiter": "upwind", "edge": False}})
+    same(fdc.div(u_c, var), "div_upwind_const")
+    same(fdc.div.rhs_adj, "div_upwind_const_rhs_adj")
+    same(fdc.div(u_t, var), "div_upwind_tensor")
+    same(fdc.div.rhs_adj, "div_upwind_tensor_rhs_adj")
+    fdc = FDC({"div": {"limiter": "none", "edge": False}})
+    if "div_central_const" in out:
+        same(fdc.div(u_c, var), "div_central_const")
+        same(fdc.div(u_t, var), "div_central_tensor")
+        same(fdc.div.rhs_adj, "div_central_tensor_rhs_adj")
+    else:
+        with pytest.raises(IndexError):
+            fdc.div(u_c, var)
+
+    fdm = FDM({"div": {"limiter": "upwind", "edge": False}})
+    rhs = torch.zeros_like(var())
+    s = _solver(var, rhs, fdm.div(u_c, var) - fdm.laplacian(0.1, var))
+    same(s.Aop(var), "advdiff")
+    same(rhs, "advdiff_rhs_adj")
+    if nd == 1:
+        rhs = torch.zeros_like(var())
+        s = _solver(var, rhs, FDM().grad(var) - FDM().laplacian(0.5, var))
+        same(s.Aop(var), "grad_minus_lap")
+        same(rhs, "grad_minus_lap_rhs_adj")
+
+    var.set_var_tensor(phi.clone())
+    _apply_bc_otf(var, mesh)
+    same(var(), "bc_applied")
+    # the per-object seam BC.apply(var, grid, var_dim) gives the same result face by face
+    x = phi.clone()
+    for bc in var.bcs:
+        bc.apply(x, mesh.grid, 0)
+    same(x, "bc_applied")
+
+
+def _run_solver_case(case, **extra):
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+
+    mesh, var = U.product_field(case, DEV, init=case["init"])
+    rhs = U.case_rhs(case, tuple(var().shape), var().dtype).to(DEV)
+    fdm = FDM(case["div_cfg"]) if case["div_cfg"] is not None else FDM()
+    cfg = {"method": case["method"], "tol": case["tol"], "max_it": case["max_it"], "report": False}
+    cfg.update(extra)
+    solver = Solver({"fdm": cfg})
+    solver.set_eq(U.product_equation(case, fdm, var, DEV) == rhs)
+    assert rhs.double().sum().item() == pytest.approx(case["rhs_adjusted_sum"], rel=1e-13, abs=1e-13)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rep = solver.solve()
+    return var, rep, w
+
+
+@pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
+@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "generic"])
+def test_solver_fixtures(case, variant):
+    """Parity bar per solver:
+    CG        — iteration count EXACT, final tol to 1e-10 absolute, solution to 1e-9 relative.
+    BiCGSTAB  — the reference is not reproducible against itself: a 1-ulp perturbation of the
+                RHS moves its own iteration count by ~10 % and, with periodic faces, its solution
+                by 1e-3 (fixtures carry that band, `sens_itr` / `sens_dsol`, measured on the real
+                reference).  Fixed-iteration ("lockstep", itr == max_it) cases must agree tightly;
+                converged cases must land inside the reference's own band.
+    fp32      — reductions cannot follow torch's CPU summation order; nearby count."""
+    f32 = case["spec"]["dtype"] == "single"
+    var, rep, w = _run_solver_case(case, variant=variant)
+    ref = case["report"]
+    sol = var().cpu()
+    if f32:
+        assert abs(rep["itr"] - ref["itr"]) <= max(3, ref["itr"] // 10), (rep, ref)
+        assert rep["converge"] == ref["converge"]
+        return
+    maxit_warn = [x for x in w if issubclass(x.category, RuntimeWarning) and "Maximum iteration" in str(x.message)]
+    scale = case["sol_abs_sum"] / sol.numel() + 1e-300
+    if case["method"] == "cg":
+        assert rep["itr"] == ref["itr"], (rep, ref)
+        assert rep["converge"] == ref["converge"]
+        assert abs(rep["tol"] - ref["tol"]) <= 1e-10, (rep, ref)
+        assert bool(maxit_warn) == (ref["itr"] > case["max_it"])
+        assert sol.double().sum().item() == pytest.approx(case["sol_sum"], rel=1e-9, abs=1e-9)
+        if "solution" in case:
+            smax = case["solution"].abs().max().item() + 1e-300
+            assert (sol - case["solution"]).abs().max().item() <= 1e-9 * smax
+        return
+    # BiCGSTAB
+    lockstep = ref["itr"] >= case["max_it"]
+    dsol = (sol - case["solution"]).abs().max().item()
+    smax = case["solution"].abs().max().item() + 1e-300
+    if lockstep:
+        assert rep["itr"] == ref["itr"], (rep, ref)
+        assert bool(maxit_warn)
+        assert abs(rep["tol"] - ref["tol"]) <= 1e-7 * ref["tol"] + 1e-10, (rep, ref)
+        assert dsol <= max(100 * case["sens_dsol"], 1e-12 * smax), (dsol, case["sens_dsol"])
+    else:
+        band = list(case["sens_itr"]) + [ref["itr"]]
+        slack = max(2, ref["itr"] // 20)
+        assert min(band) - slack <= rep["itr"] <= max(band) + slack, (rep, ref, band)
+        assert rep["converge"] == ref["converge"]
+        assert not maxit_warn
+        assert rep["tol"] <= case["tol"]
+        assert dsol <= max(20 * case["sens_dsol"], 1e-9 * smax), (dsol, case["sens_dsol"])
+
+
+@pytest.mark.parametrize("method", ["cg", "bicgstab", "jacobi"])
+@pytest.mark.parametrize("bcname", ["dirichlet", "mixed"])
+def test_solvers_vs_oracle_48(method, bcname):
+    """Seeded 3-D case at a size the oracle finishes in seconds, compared with the oracle run
+    on this host (not a stored fixture)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    n = [40, 36, 48]
+    if bcname == "dirichlet":
+        kinds, vals = ["dirichlet"] * 6, [0.0, 0.25, 0.0, 0.0, -0.5, 0.0]
+    else:
+        kinds = ["neumann", "dirichlet", "periodic", "periodic", "dirichlet", "symmetry"]
+        vals = [0.3, 0.0, None, None, 1.0, None]
+    if method == "cg" and bcname == "mixed":
+        pytest.skip("CG does not converge on the non-symmetric mixed operator (SURVEY §8c)")
+    if method == "bicgstab" and bcname == "mixed":
+        pytest.skip("reference BiCGSTAB is erratic with periodic faces (covered by the banded fixture tests)")
+    tol, max_it = (1e-8, 3000) if method != "jacobi" else (1e-5, 200)
+    mesh = Mesh(Box[0:1, 0:2, 0:1], None, n, DEV, "double")
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    g = torch.Generator().manual_seed(99)
+    rhs_h = torch.rand(1, *n, generator=g, dtype=torch.float64) - 0.5
+    solver = Solver({"fdm": {"method": method, "tol": tol, "max_it": max_it, "report": False}})
+    solver.set_eq(FDM().laplacian(1.0, var) == rhs_h.to(DEV))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rep = solver.solve()
+
+    xs, dx = O.make_axes([0, 0, 0], [1, 2, 1], n)
+    bcs = [O.FaceBC(f, k, v) for f, k, v in zip(O.FACES, kinds, vals)]
+    x0 = torch.zeros(1, *n, dtype=torch.float64)
+    eq = O.Equation([O.Term("laplacian", 1.0, 1.0)], dx, xs, bcs).build(x0)
+    rhs_o = eq.adjust_rhs(x0, rhs_h.clone())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol, rep_o, x_prev = {"cg": O.cg, "bicgstab": O.bicgstab, "jacobi": O.jacobi}[method](eq, x0, rhs_o, tol, max_it)
+    scale = sol.abs().max().item()
+    if method == "bicgstab":  # banded: see test_solver_fixtures
+        assert abs(rep["itr"] - rep_o["itr"]) <= max(3, rep_o["itr"] // 8), (rep, rep_o)
+        assert rep["converge"] and rep_o["converge"]
+        assert (var().cpu() - sol).abs().max().item() <= 1e-7 * scale
+        return
+    assert rep["itr"] == rep_o["itr"], (rep, rep_o)
+    assert abs(rep["tol"] - rep_o["tol"]) <= 1e-10
+    assert (var().cpu() - sol).abs().max().item() <= 1e-9 * scale
+    assert (var.VARo.cpu() - x_prev).abs().max().item() <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("limiter", ["upwind", "upwind_fd"])
+@pytest.mark.parametrize("shape", [[33, 41], [20, 18, 22]])
+def test_euler_vs_oracle(limiter, shape):
+    """Explicit Euler advection-diffusion steps (config 3 of BASELINE.json, small)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import homogeneous_bcs
+
+    nd = len(shape)
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, DEV, "double")
+    var = Field("c", 1, mesh, {"domain": homogeneous_bcs(nd, 0.0, "dirichlet"), "obstacle": None})
+    g = torch.Generator().manual_seed(1234)
+    phi0 = torch.rand(1, *shape, generator=g, dtype=torch.float64)
+    var.set_var_tensor(phi0.to(DEV))
+    nu, u = 0.1, 1.0
+    dt = 0.2 * min(mesh._dx) ** 2 / nu
+    var.set_time(dt, 0.0)
+    fdm = FDM({"div": {"limiter": limiter, "edge": False}})
+    solver = Solver({"fdm": {"method": "euler", "tol": 0.0, "max_it": 0, "report": False, "n_steps": 7}})
+    solver.set_eq(fdm.ddt(var) + fdm.div(u, var) - fdm.laplacian(nu, var) == 0.0)
+    solver.solve()
+    assert var.t == pytest.approx(7 * dt)
+
+    xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
+    bcs = [O.FaceBC(f, "dirichlet", 0.0) for f in O.FACES[: 2 * nd]]
+    x = phi0.clone()
+    eq = O.Equation([O.Term("div", 1.0, u, limiter), O.Term("laplacian", -1.0, nu)], dx, xs, bcs).build(x)
+    for _ in range(7):
+        x = O.euler_step(eq, x, None, dt)
+    assert torch.equal(var().cpu(), x), (var().cpu() - x).abs().max().item()
+
+
+def test_cpu_field_fails_loudly():
+    from pyapes_b200._native import NativeError
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import homogeneous_bcs
+
+    mesh = Mesh(Box[0:1, 0:1], None, [8, 8], "cpu")
+    var = Field("p", 1, mesh, {"domain": homogeneous_bcs(2, 0.0, "dirichlet"), "obstacle": None})
+    s = Solver({"fdm": {"method": "cg", "tol": 1e-6, "max_it": 10, "report": False}})
+    s.set_eq(FDM().laplacian(var) == 1.0)
+    with pytest.raises(NativeError):
+        s.solve()
