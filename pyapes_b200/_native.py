@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpyapes_b200.so")
+LIB_PATH = os.environ.get("PA_LIB") or os.path.join(_HERE, "lib", "libpyapes_b200.so")
 
 PA_F32, PA_F64 = 0, 1
 PA_MAX_OPS, PA_MAX_FACES = 4, 6
