@@ -302,10 +302,10 @@ def run_ours(args):
             "algorithmic_bytes_per_lup": B_PER_LUP_CG,
             "step_hbm_frac": (B_PER_LUP_CG * value / world) / hbm,
         },
-        "roofline": {"bound": "hbm", "kernel": "k_cg_phaseB<double>", "achieved": ach_b, "peak": hbm, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kt["kernels"][1], "achieved": ach_b, "peak": hbm, "unit": "GB/s",
                      "frac": ach_b / hbm, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": kt["phaseB_ms"], "algorithmic_bytes_per_launch": B_PER_CELL_PHASE_B * cells,
-                     "other_kernels": {"k_cg_phaseA<double>": {"avg_launch_ms": kt["phaseA_ms"], "achieved": ach_a,
+                     "other_kernels": {kt["kernels"][0]: {"avg_launch_ms": kt["phaseA_ms"], "achieved": ach_a,
                                                                "frac": ach_a / hbm},
                                        "bc_faces+shell_norm_ms_per_iter": kt["small_ms"]},
                      "kernel_share_of_iteration": kt["share"]},

@@ -145,7 +145,8 @@ typedef struct {
   int32_t max_it;
   int32_t check_every; /* iterations between host polls of the device-side done flag (0 = default) */
   int32_t use_graph;   /* capture the iteration in a CUDA graph */
-  int32_t variant;     /* 0 = default (fused tiled kernels when applicable), 1 = generic kernels */
+  int32_t variant;     /* 0 = auto (TMA-staged fused kernels, else register-tiled, else generic),
+                          1 = generic kernels, 2 = register-tiled kernels (no TMA) */
 } pa_solver_cfg;
 
 const char* pa_last_error(void);

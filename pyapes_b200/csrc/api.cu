@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_tma.cuh"
 
 namespace pa {
 
@@ -238,7 +239,8 @@ static int solver_stream(cudaStream_t caller, cudaStream_t* out) {
 template <typename T>
 static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
                          const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt, bool tiled,
-                         const TilePlan& plan, int parity, cudaEvent_t* marks = nullptr) {
+                         const TilePlan& plan, int parity, cudaEvent_t* marks = nullptr,
+                         const TmaPlan* tma = nullptr) {
   auto mark = [&](int i) {
     if (marks) cudaEventRecord(marks[i], L.s);
   };
@@ -246,7 +248,14 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
   T* r = (T*)w.vec[0];
   T* d = (T*)w.vec[1];
   int nb = grid_blocks(g.cells);
-  if (tiled) {
+  if (tma) {
+    T* d_new = (T*)w.vec[2 - parity];
+    launch_cg_phaseA_tma<T>(L.s, *tma, g, eq, parity, d_new, w.st, w.partials);
+    ++L.count;
+    mark(1);
+    launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials);
+    ++L.count;
+  } else if (tiled) {
     // the fused d-update recomputes d_new on tile halos, so d is double-buffered: neighbours
     // must still see d_old there (kernels_tiled.cuh)
     T* d_old = (T*)w.vec[1 + parity];
@@ -264,7 +273,7 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     L.count += 3;
   }
   mark(2);
-  if (!(tiled && plan.fuse_fin)) {
+  if (!((tiled && plan.fuse_fin) || (tma && tma->tile.fuse_fin))) {
     launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
     launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_CG_FIN);
   }
@@ -289,7 +298,11 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
   carve(ws, g.cells, sizeof(T), method_nvec(PA_METHOD_CG), w);
   Launcher L{stream};
   TilePlan plan;
-  bool tiled = variant == 0 && plan_tiles<T>(g, *peq, plan);
+  TmaPlan tmap;
+  bool use_tma = variant == 0 && plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1],
+                                             (T*)w.vec[2], tmap);
+  if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+  bool tiled = !use_tma && (variant == 0 || variant == 2) && plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
   k_state_init<<<1, 1, 0, stream>>>(w.st, 1e-300, iters + 10);
   launch_bcs<T>(L, g, nfaces, faces, x, nullptr);
@@ -302,7 +315,8 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
   for (int it = 0; it < iters; ++it) {
     T* cur = (it & 1) ? x_alt : x;
     T* nxt = (it & 1) ? x : x_alt;
-    cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, it & 1, &ev[4 * (size_t)it]);
+    cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, it & 1, &ev[4 * (size_t)it],
+                    use_tma ? &tmap : nullptr);
   }
   PA_CUDA(cudaStreamSynchronize(stream));
   double a = 0, b = 0, c = 0;
@@ -322,7 +336,7 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
   out_ms[2] = c / iters;
   out_ms[3] = (double)tot / iters;
   out_ms[4] = (double)(L.count - before) / iters;
-  out_ms[5] = tiled ? 1.0 : 0.0;
+  out_ms[5] = use_tma ? 2.0 : (tiled ? 1.0 : 0.0);
   for (auto& e : ev) cudaEventDestroy(e);
   PA_CUDA(cudaGetLastError());
   return PA_OK;
@@ -384,7 +398,14 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
 
   TilePlan plan;
   bool tiled = false;
-  if (method == PA_METHOD_CG && cfg->variant == 0) tiled = plan_tiles<T>(g, *peq, plan);
+  TmaPlan tmap;
+  bool use_tma = false;
+  if (method == PA_METHOD_CG && cfg->variant == 0) {
+    use_tma = plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], tmap);
+    if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+  }
+  if (method == PA_METHOD_CG && !use_tma && (cfg->variant == 0 || cfg->variant == 2))
+    tiled = plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
 
   k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
@@ -422,7 +443,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
 
   auto iteration = [&](T* cur, T* nxt) {
     if (method == PA_METHOD_CG)
-      cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1);
+      cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
+                      use_tma ? &tmap : nullptr);
     else if (method == PA_METHOD_BICGSTAB)
       bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt);
     else

@@ -1,0 +1,687 @@
+// TMA-staged CG kernels (sm_100a): the fastest path for ONE constant-coefficient star
+// operator on 2-D/3-D grids whose axes 1 and 2 are not periodic.
+//
+// Producer/consumer pipeline per CTA (no CTA-wide barrier in the plane loop):
+//   * warp 8 (one elected lane) is the PRODUCER: for every plane of the CTA's chunk it issues
+//     `cp.async.bulk.tensor.3d` (TMA) loads of the tile *with its halo* — box
+//     (TY+2) x (TZ+2*VEC) — into a ring of S shared-memory stages; completion is signalled on
+//     a per-stage `full` mbarrier (expect_tx bytes).  Out-of-bounds halo cells are zero-filled
+//     by the TMA unit, which is exactly what a non-periodic edge needs (those values only
+//     reach cells outside the solver region, which are masked).
+//   * warps 0-7 are CONSUMERS: a thread owns RY consecutive rows x one 16-byte vector and keeps
+//     planes x-1, x, x+1 of its cells in registers (3x unrolled loop: no register rotation);
+//     axis-1/axis-2 neighbours are read straight from the staged halo tile.  When a warp is
+//     done with a stage it arrives on that stage's `empty` mbarrier; the producer refills it.
+//   The pipeline is S-2 planes deep, so DRAM latency is covered by TMA transactions in flight,
+//   not by occupancy or prefetch registers.
+//
+// CG fusion as in kernels_tiled.cuh (SURVEY.md §8d canonical variant, 8 words/cell/iteration):
+//   phase A: d_new = r + beta*d ; dAd = sum d_new*A(d_new)     [R r, R d, W d]
+//            (d_new on the halo is recomputed from the staged raw r, d — bit-identical)
+//   phase B: x_new = x + alpha*d ; r -= alpha*A(d) ; sums      [R x, R d, R r, W x, W r]
+// Per-cell arithmetic order is identical to eval_equation() in common.cuh.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_tiled.cuh"
+
+namespace pa {
+
+template <typename T, int RY_>
+struct TmaCfg {
+  static constexpr int VEC = VecOf<T>::N;
+  static constexpr int RY = RY_;
+  static constexpr int CWARPS = 8;                 // consumer warps
+  static constexpr int THREADS = (CWARPS + 1) * 32;  // + producer warp
+  static constexpr int TY = CWARPS * RY;
+  static constexpr int TZ = 32 * VEC;
+  static constexpr int HZ = VEC;                   // z halo, keeps own cells 16-B aligned
+  static constexpr int BOXZ = TZ + 2 * HZ;
+  static constexpr int BOXY = TY + 2;
+  static constexpr int S = 4;                      // pipeline stages (power of two)
+  static constexpr int HALO_BYTES = BOXY * BOXZ * (int)sizeof(T);
+  static constexpr int OWN_BYTES = TY * TZ * (int)sizeof(T);
+  static constexpr int HALO_SLOT = (HALO_BYTES + 127) / 128 * 128;
+  static constexpr int OWN_SLOT = (OWN_BYTES + 127) / 128 * 128;
+  static constexpr int STAGE_A = 2 * HALO_SLOT;              // r halo, d halo
+  static constexpr int STAGE_B = HALO_SLOT + 2 * OWN_SLOT;   // d halo, x own, r own
+  static constexpr int BAR_BYTES = 128;                      // 2*S mbarriers
+  static constexpr size_t SMEM_A = (size_t)S * STAGE_A + BAR_BYTES + 128;
+  static constexpr size_t SMEM_B = (size_t)S * STAGE_B + BAR_BYTES + 128;
+};
+
+constexpr int kTmaRY = 2;
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+template <typename T>
+static inline bool make_map(CUtensorMap* m, const T* base, const GridDev& g, int boxz, int boxy) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)g.n[2], (cuuint64_t)g.n[1], (cuuint64_t)g.n[0]};
+  cuuint64_t strides[2] = {(cuuint64_t)g.n[2] * sizeof(T), (cuuint64_t)g.n[1] * g.n[2] * sizeof(T)};
+  cuuint32_t box[3] = {(cuuint32_t)boxz, (cuuint32_t)boxy, 1u};
+  cuuint32_t es[3] = {1u, 1u, 1u};
+  CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct TmaPlan {
+  TilePlan tile;            // grid geometry (tiles_y/z, chunks, cx, fuse_fin)
+  CUtensorMap x_own[2];     // x, x_alt  (phase B reads the current iterate)
+  CUtensorMap r_own, r_halo;
+  CUtensorMap d_halo[2];    // the two d buffers
+};
+
+template <typename T>
+inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
+                     const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
+  typedef TmaCfg<T, kTmaRY> C;
+  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR) return false;
+  if (!g.act[1] || !g.act[2]) return false;
+  if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
+  for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
+    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
+  TilePlan& p = tp.tile;
+  p.ry = kTmaRY;
+  p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;
+  p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
+  const int tiles = p.tiles_y * p.tiles_z;
+  const int slots = kNumSMs * 2;
+  int best_c = 1;
+  double best = -1.0;
+  const int maxc = g.n[0] >= 16 ? g.n[0] / 8 : 1;
+  for (int c = 1; c <= maxc; ++c) {
+    const int cx = (g.n[0] + c - 1) / c;
+    const int cc = (g.n[0] + cx - 1) / cx;
+    const long long items = (long long)cc * tiles;
+    if (items > kMaxPartials) break;
+    const long long waves = (items + slots - 1) / slots;
+    const double quant = (double)items / (double)(waves * slots);
+    const double halo = g.act[0] ? (double)cx / (double)(cx + 2) : 1.0;
+    const double score = quant * halo * (items >= slots ? 1.0 : (double)items / slots);
+    if (score > best + 1e-9) {
+      best = score;
+      best_c = cc;
+    }
+  }
+  p.cx = (g.n[0] + best_c - 1) / best_c;
+  p.chunks = (g.n[0] + p.cx - 1) / p.cx;
+  p.vec_ok = 1;
+  p.fuse_fin = 0;
+  bool ok = make_map<T>(&tp.x_own[0], x, g, C::TZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::TZ, C::TY) &&
+            make_map<T>(&tp.r_own, r, g, C::TZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
+            make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) &&
+            make_map<T>(&tp.d_halo[1], d1, g, C::BOXZ, C::BOXY);
+  return ok;
+}
+
+// ---- consumer-side geometry -----------------------------------------------------------------------
+template <typename T, int RY>
+struct ConsCtx {
+  int lane, warp;
+  int hoff;   // element offset of (own row 0, own element 0) inside a halo tile
+  int ooff;   // same inside an own tile
+  long long goff;  // element offset of (own row 0, element 0) inside a global plane
+  unsigned valid, inreg, nonshell;  // bit k*VEC+e   (GENERAL path)
+  int cly[RY], clz[VecOf<T>::N];
+};
+
+template <typename T, int RY>
+__device__ __forceinline__ void cons_setup(const GridDev& g, ConsCtx<T, RY>& c, int y0, int z0) {
+  typedef TmaCfg<T, RY> C;
+  c.lane = threadIdx.x & 31;
+  c.warp = threadIdx.x >> 5;
+  c.hoff = (c.warp * RY + 1) * C::BOXZ + C::HZ + c.lane * C::VEC;
+  c.ooff = (c.warp * RY) * C::TZ + c.lane * C::VEC;
+  const int yb = y0 + c.warp * RY, zg = z0 + c.lane * C::VEC;
+  c.goff = (long long)yb * g.n[2] + zg;
+  c.valid = c.inreg = c.nonshell = 0u;
+#pragma unroll
+  for (int k = 0; k < RY; ++k) {
+    const int y = yb + k;
+    c.cly[k] = (y < g.n[1]) ? coef_class(g, 1, y) : 0;
+#pragma unroll
+    for (int e = 0; e < C::VEC; ++e) {
+      const int z = zg + e;
+      const bool v = (y < g.n[1]) && (z < g.n[2]);
+      const bool rg = v && y >= g.lo[1] && y < g.hi[1] && z >= g.lo[2] && z < g.hi[2];
+      const bool ns = v && y != 0 && y != g.n[1] - 1 && z != 0 && z != g.n[2] - 1;
+      const unsigned bit = 1u << (k * C::VEC + e);
+      if (v) c.valid |= bit;
+      if (rg) c.inreg |= bit;
+      if (ns) c.nonshell |= bit;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < C::VEC; ++e) c.clz[e] = (zg + e < g.n[2]) ? coef_class(g, 2, zg + e) : 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void lds_vec(const T* p, T (&v)[VecOf<T>::N]) {
+  typedef typename VecOf<T>::type V;
+  V q = *reinterpret_cast<const V*>(p);
+  const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+  for (int e = 0; e < VecOf<T>::N; ++e) v[e] = s[e];
+}
+
+template <typename T, int RY, bool LEAN>
+__device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, RY>& c, int k, const T (&v)[VecOf<T>::N]) {
+  typedef typename VecOf<T>::type V;
+  constexpr int N = VecOf<T>::N;
+  const unsigned m = (c.valid >> (k * N)) & ((1u << N) - 1u);
+  if (LEAN || m == ((1u << N) - 1u)) {
+    V q;
+    T* s = reinterpret_cast<T*>(&q);
+#pragma unroll
+    for (int e = 0; e < N; ++e) s[e] = v[e];
+    *reinterpret_cast<V*>(p) = q;
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e)
+      if ((m >> e) & 1u) p[e] = v[e];
+  }
+}
+
+// the star operator on the thread's cells (same arithmetic order as eval_equation)
+template <typename T, int RY, bool LEAN, typename F>
+__device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, RY>& c, const T (&cx)[3],
+                                           bool actx, const T (&vm)[RY][VecOf<T>::N],
+                                           const T (&vc)[RY][VecOf<T>::N], const T (&vp)[RY][VecOf<T>::N],
+                                           const T (&up)[VecOf<T>::N], const T (&dn)[VecOf<T>::N],
+                                           const T (&zl)[RY], const T (&zr)[RY], F emit) {
+  constexpr int VEC = VecOf<T>::N;
+#pragma unroll
+  for (int k = 0; k < RY; ++k) {
+    const int cy = LEAN ? 0 : c.cly[k];
+    const T yap = o.coef[1][cy][0], yac = o.coef[1][cy][1], yam = o.coef[1][cy][2];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int cz = LEAN ? 0 : c.clz[e];
+      const T zap = o.coef[2][cz][0], zac = o.coef[2][cz][1], zam = o.coef[2][cz][2];
+      const T v0 = vc[k][e];
+      const T yp = (k == RY - 1) ? dn[e] : vc[k + 1 < RY ? k + 1 : k][e];
+      const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
+      const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
+      const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
+      T acc = (T)0;
+      if (actx) {
+        T s = cx[0] * vp[k][e];
+        s = s + cx[1] * v0;
+        s = s + cx[2] * vm[k][e];
+        acc = acc + s;
+      }
+      {
+        T s = yap * yp;
+        s = s + yac * v0;
+        s = s + yam * ym;
+        acc = acc + s;
+      }
+      {
+        T s = zap * zp;
+        s = s + zac * v0;
+        s = s + zam * zm;
+        acc = acc + s;
+      }
+      if (o.has_param) acc = acc * o.param;
+      acc = acc * o.sign;
+      const T res = (T)0 + acc;
+      emit(k, e, res);
+    }
+  }
+}
+
+// =========================================================================================
+// phase B
+// =========================================================================================
+template <typename T, int RY, bool LEAN>
+__device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
+                                              T* __restrict__ x_new, T* __restrict__ r, T alpha,
+                                              unsigned char* stages, uint64_t* full, uint64_t* empty,
+                                              int y0, int z0, int x0, int x1, double (&acc_out)[2]) {
+  typedef TmaCfg<T, RY> C;
+  constexpr int VEC = C::VEC;
+  ConsCtx<T, RY> c;
+  cons_setup<T, RY>(g, c, y0, z0);
+  const bool actx = g.act[0] != 0;
+  const long long n12 = (long long)g.n[1] * g.n[2];
+  T* xo = x_new + (long long)x0 * n12 + c.goff;
+  T* ro = r + (long long)x0 * n12 + c.goff;
+
+  auto halo = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B); };
+  auto ownx = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B + C::HALO_SLOT); };
+  auto ownr = [&](int s) {
+    return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B + C::HALO_SLOT + C::OWN_SLOT);
+  };
+  auto load_own = [&](int s, T (&v)[RY][VEC]) {
+    const T* h = halo(s) + c.hoff;
+#pragma unroll
+    for (int k = 0; k < RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
+  };
+  auto release = [&](int s) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&empty[s]);
+  };
+
+  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  double a0 = 0.0, a1 = 0.0;
+
+  // prologue: plane x0-1 (counter 0) -> A ; plane x0 (counter 1) -> B
+  if (actx) {
+    mbar_wait(&full[0], 0);
+    load_own(0, A);
+    release(0);
+  }
+  mbar_wait(&full[1 % C::S], 0);
+  load_own(1 % C::S, B);
+
+  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+    // i = pipeline counter of plane x+1; plane x sits in stage (i-1)%S
+    const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
+    if (actx) {
+      mbar_wait(&full[sn], (i / C::S) & 1);
+      load_own(sn, vp);
+    }
+    const T* h = halo(sc) + c.hoff;
+    const bool xreg = x >= g.lo[0] && x < g.hi[0];
+    const bool xown = x >= g.olo0 && x < g.ohi0;
+    const int gx = x + g.goff0;
+    const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
+    if (xreg) {
+      T ad[RY][VEC];
+      {
+        T up[VEC], dn[VEC], zl[RY], zr[RY];
+        lds_vec<T>(h - C::BOXZ, up);
+        lds_vec<T>(h + RY * C::BOXZ, dn);
+#pragma unroll
+        for (int k = 0; k < RY; ++k) {
+          zl[k] = h[k * C::BOXZ - 1];
+          zr[k] = h[k * C::BOXZ + VEC];
+        }
+        const int clx = actx ? coef_class(g, 0, x) : 0;
+        const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
+        star_cells<T, RY, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr,
+                                [&](int k, int e, T v) { ad[k][e] = v; });
+      }
+      // x and r of this plane are only needed now: keep their live range short
+#pragma unroll
+      for (int k = 0; k < RY; ++k) {
+        T xv[VEC], rv[VEC], xn[VEC], rn[VEC];
+        lds_vec<T>(ownx(sc) + c.ooff + k * C::TZ, xv);
+        lds_vec<T>(ownr(sc) + c.ooff + k * C::TZ, rv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const bool in = LEAN || ((c.inreg >> (k * VEC + e)) & 1u);
+          xn[e] = xv[e] + alpha * vc[k][e];       // linalg.py:122 (d == 0 outside the region)
+          const T t = rv[e] - alpha * ad[k][e];   // linalg.py:131
+          rn[e] = in ? t : rv[e];
+          if (xown) {
+            if (in) {
+              const T q = t * t;
+              a0 += (double)q;
+            }
+            if (!xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
+              const T df = xn[e] - xv[e];
+              const T q2 = df * df;
+              a1 += (double)q2;
+            }
+          }
+        }
+        stg_row<T, RY, LEAN>(xo + (long long)k * g.n[2], c, k, xn);
+        stg_row<T, RY, LEAN>(ro + (long long)k * g.n[2], c, k, rn);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RY; ++k) {
+        T xv[VEC];
+        lds_vec<T>(ownx(sc) + c.ooff + k * C::TZ, xv);
+        stg_row<T, RY, LEAN>(xo + (long long)k * g.n[2], c, k, xv);
+      }
+    }
+    xo += n12;
+    ro += n12;
+    release(sc);
+  };
+
+  int x = x0, i = 2;
+  while (true) {
+    step(A, B, Cc, x, i);
+    if (++x >= x1) break;
+    ++i;
+    step(B, Cc, A, x, i);
+    if (++x >= x1) break;
+    ++i;
+    step(Cc, A, B, x, i);
+    if (++x >= x1) break;
+    ++i;
+  }
+  acc_out[0] = a0;
+  acc_out[1] = a1;
+}
+
+template <typename T, int RY>
+__global__ void __launch_bounds__(TmaCfg<T, RY>::THREADS, 2)
+k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_x,
+                const __grid_constant__ CUtensorMap tm_r, TilePlan p, GridDev g, OpDev<T> o,
+                T* __restrict__ x_new, T* __restrict__ r, SolverState* st, double* partials) {
+  typedef TmaCfg<T, RY> C;
+  extern __shared__ unsigned char smem_dyn[];
+  if (st->done) return;
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  unsigned char* stages = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_B);
+  uint64_t* empty = full + C::S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
+  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const bool actx = g.act[0] != 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], C::CWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  if (warp == C::CWARPS) {
+    if (lane == 0) {
+      // producer: planes x0-1 .. x1 (pipeline counters 0 .. cx+1)
+      const int n = x1 - x0 + 2;
+      for (int i = 0; i < n; ++i) {
+        if (!actx && i != 1) continue;
+        const int pl = x0 - 1 + i;
+        const int s = i & (C::S - 1);
+        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
+        const bool inner = (pl >= x0 && pl < x1);
+        mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? 2 * C::OWN_BYTES : 0)));
+        unsigned char* sb = stages + (size_t)s * C::STAGE_B;
+        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+        tma_load_3d(sb, &tm_d, z0 - C::HZ, y0 - 1, xw, &full[s]);
+        if (inner) {
+          tma_load_3d(sb + C::HALO_SLOT, &tm_x, z0, y0, xw, &full[s]);
+          tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT, &tm_r, z0, y0, xw, &full[s]);
+        }
+      }
+    }
+  } else {
+    const T alpha = (T)st->scal[S_ALPHA];
+    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    if (full_tile && !edge)
+      tmaB_consumer<T, RY, true>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+    else
+      tmaB_consumer<T, RY, false>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+  }
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (p.fuse_fin) {
+    if (threadIdx.x == 0) st->sum[R_SHELL] = 0.0;
+    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_CG_FIN});
+  } else {
+    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_NONE});
+  }
+}
+
+// =========================================================================================
+// phase A
+// =========================================================================================
+template <typename T, int RY, bool LEAN>
+__device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
+                                              T* __restrict__ d_new, T beta, unsigned char* stages,
+                                              uint64_t* full, uint64_t* empty, int y0, int z0, int x0,
+                                              int x1, double& acc_out) {
+  typedef TmaCfg<T, RY> C;
+  constexpr int VEC = C::VEC;
+  ConsCtx<T, RY> c;
+  cons_setup<T, RY>(g, c, y0, z0);
+  const bool actx = g.act[0] != 0;
+  const long long n12 = (long long)g.n[1] * g.n[2];
+  T* dout = d_new + (long long)x0 * n12 + c.goff;
+
+  auto rt = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_A) + c.hoff; };
+  auto dt = [&](int s) {
+    return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_A + C::HALO_SLOT) + c.hoff;
+  };
+  // d_new = r + beta*d on the thread's own cells of the plane in stage s   (linalg.py:141)
+  auto own_dn = [&](int s, T (&v)[RY][VEC]) {
+    const T* rp = rt(s);
+    const T* dp = dt(s);
+#pragma unroll
+    for (int k = 0; k < RY; ++k) {
+      T a[VEC], b[VEC];
+      lds_vec<T>(rp + k * C::BOXZ, a);
+      lds_vec<T>(dp + k * C::BOXZ, b);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[k][e] = a[e] + beta * b[e];
+    }
+  };
+  auto write_d = [&](const T (&v)[RY][VEC]) {
+#pragma unroll
+    for (int k = 0; k < RY; ++k) stg_row<T, RY, LEAN>(dout + (long long)k * g.n[2], c, k, v[k]);
+    dout += n12;
+  };
+  auto release = [&](int s) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&empty[s]);
+  };
+
+  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  double acc = 0.0;
+
+  if (actx) {
+    mbar_wait(&full[0], 0);
+    own_dn(0, A);
+    release(0);
+  }
+  mbar_wait(&full[1 % C::S], 0);
+  own_dn(1 % C::S, B);
+  write_d(B);
+
+  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+    const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
+    if (actx) {
+      mbar_wait(&full[sn], (i / C::S) & 1);
+      own_dn(sn, vp);
+      if (x + 1 < x1) write_d(vp);
+    }
+    const bool xin = x >= g.lo[0] && x < g.hi[0] && x >= g.olo0 && x < g.ohi0;
+    if (xin) {
+      // halo neighbours of the centre plane: recomputed from the staged raw r, d
+      const T* rp = rt(sc);
+      const T* dp = dt(sc);
+      T up[VEC], dn[VEC], zl[RY], zr[RY];
+      {
+        T a[VEC], b[VEC];
+        lds_vec<T>(rp - C::BOXZ, a);
+        lds_vec<T>(dp - C::BOXZ, b);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) up[e] = a[e] + beta * b[e];
+        lds_vec<T>(rp + RY * C::BOXZ, a);
+        lds_vec<T>(dp + RY * C::BOXZ, b);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) dn[e] = a[e] + beta * b[e];
+      }
+#pragma unroll
+      for (int k = 0; k < RY; ++k) {
+        zl[k] = rp[k * C::BOXZ - 1] + beta * dp[k * C::BOXZ - 1];
+        zr[k] = rp[k * C::BOXZ + VEC] + beta * dp[k * C::BOXZ + VEC];
+      }
+      const int clx = actx ? coef_class(g, 0, x) : 0;
+      const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
+      // d == 0 outside the solver region: d*Ad needs no region mask, only array bounds
+      star_cells<T, RY, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T ad) {
+        if (LEAN || ((c.valid >> (k * VEC + e)) & 1u)) {
+          const T q = vc[k][e] * ad;
+          acc += (double)q;
+        }
+      });
+    }
+    release(sc);
+  };
+
+  int x = x0, i = 2;
+  while (true) {
+    step(A, B, Cc, x, i);
+    if (++x >= x1) break;
+    ++i;
+    step(B, Cc, A, x, i);
+    if (++x >= x1) break;
+    ++i;
+    step(Cc, A, B, x, i);
+    if (++x >= x1) break;
+    ++i;
+  }
+  acc_out = acc;
+}
+
+template <typename T, int RY>
+__global__ void __launch_bounds__(TmaCfg<T, RY>::THREADS, 2)
+k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_d,
+                TilePlan p, GridDev g, OpDev<T> o, T* __restrict__ d_new, SolverState* st,
+                double* partials) {
+  typedef TmaCfg<T, RY> C;
+  extern __shared__ unsigned char smem_dyn[];
+  if (st->done) return;
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  unsigned char* stages = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_A);
+  uint64_t* empty = full + C::S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
+  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const bool actx = g.act[0] != 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], C::CWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double acc[1] = {0.0};
+  if (warp == C::CWARPS) {
+    if (lane == 0) {
+      const int n = x1 - x0 + 2;
+      for (int i = 0; i < n; ++i) {
+        if (!actx && i != 1) continue;
+        const int pl = x0 - 1 + i;
+        const int s = i & (C::S - 1);
+        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
+        mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
+        unsigned char* sb = stages + (size_t)s * C::STAGE_A;
+        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+        tma_load_3d(sb, &tm_r, z0 - C::HZ, y0 - 1, xw, &full[s]);
+        tma_load_3d(sb + C::HALO_SLOT, &tm_d, z0 - C::HZ, y0 - 1, xw, &full[s]);
+      }
+    }
+  } else {
+    const T beta = (T)st->scal[S_BETA];
+    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    if (full_tile && !edge)
+      tmaA_consumer<T, RY, true>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+    else
+      tmaA_consumer<T, RY, false>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+  }
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_CG_DAD});
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+template <typename T>
+inline void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                                 int parity, T* d_new, SolverState* st, double* partials) {
+  typedef TmaCfg<T, kTmaRY> C;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_cg_phaseA_tma<T, kTmaRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
+    attr = true;
+  }
+  dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
+  k_cg_phaseA_tma<T, kTmaRY><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tp.tile, g,
+                                                                eq.op[0], d_new, st, partials);
+}
+
+template <typename T>
+inline void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                                 int parity, T* x_new, T* r, SolverState* st, double* partials) {
+  typedef TmaCfg<T, kTmaRY> C;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_cg_phaseB_tma<T, kTmaRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
+    attr = true;
+  }
+  dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
+  // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
+  k_cg_phaseB_tma<T, kTmaRY><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own,
+                                                                tp.tile, g, eq.op[0], x_new, r, st, partials);
+}
+
+}  // namespace pa

@@ -42,5 +42,9 @@ def cg_kernel_times(n: int, iters: int = 20, variant: int = 0, dtype: str = "dou
         N.check(lib.pa_cg_profile(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(), rhs.data_ptr(),
                                   iters, variant, ws.data_ptr(), wsb, out, N.current_stream(x.device)))
     a, b, c, tot, launches, tiled = list(out)
+    names = {2.0: ("k_cg_phaseA_tma<double,2>", "k_cg_phaseB_tma<double,2>"),
+             1.0: ("k_cg_phaseA<double,2>", "k_cg_phaseB<double,2>"),
+             0.0: ("k_cg_dupdate+k_cg_dAd", "k_cg_update")}[tiled]
     return {"phaseA_ms": a, "phaseB_ms": b, "small_ms": c, "iter_ms": tot, "launches_per_iter": launches,
-            "tiled": bool(tiled), "share": {"phaseA": a / tot, "phaseB": b / tot, "bc+shell": c / tot}}
+            "tiled": bool(tiled), "path": {2.0: "tma", 1.0: "register-tiled", 0.0: "generic"}[tiled],
+            "kernels": names, "share": {"phaseA": a / tot, "phaseB": b / tot, "bc+shell": c / tot}}
