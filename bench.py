@@ -189,6 +189,13 @@ def run_ours(args):
 
     n, iters = args.n, args.iters
     cfg = {"method": "cg", "tol": 1e-30, "max_it": iters - 1, "report": False, "check_every": iters + (iters & 1)}
+    if world > 1:
+        from pyapes_b200.parallel import slab_layout
+
+        lay = slab_layout(n * world, rank, world)
+        local_shape, olo, ohi = (1, lay["n0_local"], n, n), lay["olo0"], lay["ohi0"]
+    else:
+        local_shape, olo, ohi = (1, n, n, n), 0, n
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,9 +214,11 @@ def run_ours(args):
         solver.set_eq(FDM().laplacian(1.0, var) == rhs_dev)
         return solver, var
 
-    rhs_h = host_rhs(n, rank)
+    rhs_h = host_rhs(n, rank)  # this rank's OWNED planes (pinned host memory)
     out_h = torch.empty_like(rhs_h).pin_memory()
-    rhs_d = rhs_h.to(dev)
+    rhs_d = torch.zeros(local_shape, dtype=torch.float64, device=dev)
+    rhs_d[:, olo:ohi].copy_(rhs_h)
+    rhs_e2e = torch.zeros(local_shape, dtype=torch.float64, device=dev)
     launches = 0
 
     def step_device():
@@ -223,12 +232,12 @@ def run_ours(args):
         return var
 
     def step_e2e():
-        rd = rhs_h.to(dev, non_blocking=True)
-        solver, var = new_solver(rd)
+        rhs_e2e[:, olo:ohi].copy_(rhs_h, non_blocking=True)  # H2D of this step's input
+        solver, var = new_solver(rhs_e2e)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             solver.solve()
-        out_h.copy_(var(), non_blocking=True)
+        out_h.copy_(var()[:, olo:ohi], non_blocking=True)    # D2H of the result
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):

@@ -198,6 +198,20 @@ int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,
                      const pa_face_bc* faces, int dtype, void* x_host, const void* rhs_host,
                      const pa_solver_cfg* cfg, pa_report* report);
 
+/* --- multi-GPU (one process per GPU, slab decomposition along kernel axis 0).
+ *     The reference has no distributed path; these are new.  NCCL is loaded at run time.
+ *     pa_comm_unique_id: rank 0 creates the 128-byte NCCL id, the host layer broadcasts it.
+ *     pa_cg_solve_dist : same contract as pa_cg_solve on the LOCAL slab described by `g`
+ *     (n[0] includes the ghost planes, goff0/gn0/olo0/ohi0 place it in the global grid); the
+ *     halo exchange of r and the all-reduces of the CG scalars run inside the call. */
+int pa_comm_unique_id(void* out128);
+int pa_comm_create(const void* id128, int rank, int nranks, void** comm_out);
+int pa_comm_destroy(void* comm);
+int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                     int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg, void* ws,
+                     size_t ws_bytes, void* comm, int rank, int nranks, pa_report* report,
+                     void* stream);
+
 /* --- instrumented CG pass (measurement only): `iters` iterations with every section bracketed
  *     by CUDA events on the launching stream.  out_ms[6] = average per iteration of
  *     {phase A (d update + d.Ad), phase B (x,r update), BC faces + shell norm, whole iteration,

@@ -22,8 +22,9 @@ def kernel_axis(mesh_axis: int, ndim: int) -> int:
     return mesh_axis + 3 - ndim
 
 
-def lower_grid(nx, bcs) -> N.Grid:
-    """Grid block + the solver region of mesh/tools.py:7-20 (single GPU)."""
+def lower_grid(nx, bcs, slab=None) -> N.Grid:
+    """Grid block + the solver region of mesh/tools.py:7-20.  `slab` (pyapes_b200.parallel)
+    places a local block with ghost planes inside the global grid along kernel axis 0."""
     nd = len(nx)
     g = N.Grid()
     n = [1] * (3 - nd) + [int(v) for v in nx]
@@ -40,6 +41,13 @@ def lower_grid(nx, bcs) -> N.Grid:
         g.n[a], g.lo[a], g.hi[a] = n[a], lo[a], max(hi[a], lo[a])
     g.gn0, g.goff0, g.olo0, g.ohi0 = n[0], 0, 0, n[0]
     g.ndim = nd
+    if slab is not None:
+        assert nd == 3, "slab decomposition is along axis 0 of a 3-D mesh"
+        g.gn0, g.goff0, g.olo0, g.ohi0 = slab["gn0"], slab["goff0"], slab["olo0"], slab["ohi0"]
+        # region along axis 0: owned planes that are inside the global slicer
+        glo, ghi = (0 if lo[0] == 0 else 1), (slab["gn0"] if hi[0] == n[0] else slab["gn0"] - 1)
+        g.lo[0] = max(slab["olo0"], glo - slab["goff0"])
+        g.hi[0] = max(g.lo[0], min(slab["ohi0"], ghi - slab["goff0"]))
     return g
 
 

@@ -8,6 +8,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
+#include "dist.cuh"
 
 namespace pa {
 
@@ -106,12 +107,9 @@ static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_
       int gi = fd.side < 0 ? 0 : g.gn0 - 1;
       int pl = gi - g.goff0;
       if (pl < g.olo0 || pl >= g.ohi0) continue;
-      if (g.goff0 != 0 || g.gn0 != g.n[0]) {
-        // slab-decomposed: face plane indices are local; handled by k_bc_face via n[0]
-        // only when the block spans the whole axis.  Multi-rank x faces go through
-        // launch_bcs_slab (dist.cu).
-        continue;
-      }
+      // slab-decomposed: the rank that owns a global x face has no ghost plane on that side,
+      // so the face plane is local plane 0 / n[0]-1 and k_bc_face's local indexing holds
+      if (pl != (fd.side < 0 ? 0 : g.n[0] - 1)) continue;
     }
     int b = (fd.axis == 0) ? 1 : 0, c = (fd.axis == 2) ? 1 : 2;
     long long ncell = (long long)g.n[b] * g.n[c];
@@ -240,7 +238,7 @@ template <typename T>
 static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
                          const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt, bool tiled,
                          const TilePlan& plan, int parity, cudaEvent_t* marks = nullptr,
-                         const TmaPlan* tma = nullptr) {
+                         const TmaPlan* tma = nullptr, const Dist* dist = nullptr) {
   auto mark = [&](int i) {
     if (marks) cudaEventRecord(marks[i], L.s);
   };
@@ -252,6 +250,11 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     T* d_new = (T*)w.vec[2 - parity];
     launch_cg_phaseA_tma<T>(L.s, *tma, g, eq, parity, d_new, w.st, w.partials);
     ++L.count;
+    if (dist) {
+      dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
+      k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_DAD, w.st);
+      L.count += 2;
+    }
     mark(1);
     launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials);
     ++L.count;
@@ -262,20 +265,44 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     T* d_new = (T*)w.vec[2 - parity];
     launch_cg_phaseA<T>(L.s, plan, g, eq, r, d_old, d_new, w.st, w.partials);
     ++L.count;
+    if (dist) {
+      dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
+      k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_DAD, w.st);
+      L.count += 2;
+    }
     mark(1);
     launch_cg_phaseB<T>(L.s, plan, g, eq, cur, nxt, d_new, r, w.st, w.partials);
     ++L.count;
   } else {
     k_cg_dupdate<T><<<nb, kBlock, 0, L.s>>>(g, r, d, w.st);
-    k_cg_dAd<T><<<nb, kBlock, 0, L.s>>>(g, eq, d, w.st, w.partials, ST_CG_DAD);
+    k_cg_dAd<T><<<nb, kBlock, 0, L.s>>>(g, eq, d, w.st, w.partials, dist ? ST_NONE : ST_CG_DAD);
+    if (dist) {
+      dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
+      k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_DAD, w.st);
+      L.count += 2;
+    }
     mark(1);
     k_cg_update<T><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, d, r, w.st, w.partials);
     L.count += 3;
   }
   mark(2);
-  if (!((tiled && plan.fuse_fin) || (tma && tma->tile.fuse_fin))) {
-    launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
-    launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_CG_FIN);
+  if (!dist) {
+    if (!((tiled && plan.fuse_fin) || (tma && tma->tile.fuse_fin))) {
+      launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+      launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_CG_FIN);
+    }
+  } else {
+    // multi-GPU: boundary planes of the new r to the neighbours' ghosts, then the three sums
+    if (static_shell(nfaces, faces)) {
+      cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
+    } else {
+      launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+      launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_NONE);
+    }
+    dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
+    dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
+    k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_FIN, w.st);
+    L.count += 3;
   }
   mark(3);
 }
@@ -381,7 +408,7 @@ template <typename T>
 static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int nfaces,
                       const pa_face_bc* faces, T* x, T* x_alt, const T* rhs,
                       const pa_solver_cfg* cfg, void* ws, size_t ws_size, pa_report* rep,
-                      cudaStream_t caller_stream) {
+                      cudaStream_t caller_stream, const Dist* dist = nullptr) {
   cudaStream_t stream;
   {
     int rcs = solver_stream(caller_stream, &stream);
@@ -407,6 +434,12 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (method == PA_METHOD_CG && !use_tma && (cfg->variant == 0 || cfg->variant == 2))
     tiled = plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
+  if (dist) {
+    if (method != PA_METHOD_CG) return fail(PA_ERR_UNSUPPORTED, "multi-GPU: only CG is slab-decomposed so far");
+    if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+    plan.dist = tmap.tile.dist = 1;
+    plan.fuse_fin = tmap.tile.fuse_fin = 0;
+  }
 
   k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
   ++L.count;
@@ -417,9 +450,23 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (method == PA_METHOD_CG) {
     T* r = (T*)w.vec[0];
     T* d = (T*)w.vec[1];
+    const long long plane = (long long)g.n[1] * g.n[2];
+    if (dist) dist_halo_exchange<T>(*dist, x, plane, g.olo0, g.ohi0, stream);  // x ghosts for r0
     k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r, d, w.st, w.partials,
-                                                  ST_CG_INIT);
+                                                  dist ? ST_NONE : ST_CG_INIT);
     ++L.count;
+    if (dist) {
+      dist_halo_exchange<T>(*dist, r, plane, g.olo0, g.ohi0, stream);
+      if (g.olo0 > 0)
+        PA_CUDA(cudaMemcpyAsync(d, r, (size_t)g.olo0 * plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      if (g.ohi0 < g.n[0])
+        PA_CUDA(cudaMemcpyAsync(d + (long long)g.ohi0 * plane, r + (long long)g.ohi0 * plane,
+                                (size_t)(g.n[0] - g.ohi0) * plane * sizeof(T), cudaMemcpyDeviceToDevice,
+                                stream));
+      dist_allreduce(*dist, &w.st->sum[R_A], 1, stream);
+      k_finalize<T><<<1, 1, 0, stream>>>(ST_CG_INIT, w.st);
+      L.count += 4;
+    }
   } else if (method == PA_METHOD_BICGSTAB) {
     T* r0 = (T*)w.vec[0];
     T* r = (T*)w.vec[1];
@@ -444,7 +491,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   auto iteration = [&](T* cur, T* nxt) {
     if (method == PA_METHOD_CG)
       cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
-                      use_tma ? &tmap : nullptr);
+                      use_tma ? &tmap : nullptr, dist);
     else if (method == PA_METHOD_BICGSTAB)
       bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt);
     else
@@ -639,6 +686,53 @@ int pa_cg_solve(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_fa
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
                                    (const T*)rhs, cfg, ws, ws_bytes_, report,
                                    (cudaStream_t)stream));
+}
+
+int pa_comm_unique_id(void* out128) {
+  NcclApi& a = nccl_api();
+  if (!a.ok) return fail(PA_ERR_NCCL, a.error);
+  ncclUniqueId id;
+  ncclResult_t rc = a.GetUniqueId(&id);
+  if (rc != ncclSuccess) return fail(PA_ERR_NCCL, a.GetErrorString(rc));
+  memcpy(out128, &id, sizeof(id));
+  return PA_OK;
+}
+
+int pa_comm_create(const void* id128, int rank, int nranks, void** comm_out) {
+  PA_REQUIRE_DEVICE();
+  NcclApi& a = nccl_api();
+  if (!a.ok) return fail(PA_ERR_NCCL, a.error);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t c;
+  ncclResult_t rc = a.CommInitRank(&c, nranks, id, rank);
+  if (rc != ncclSuccess) return fail(PA_ERR_NCCL, a.GetErrorString(rc));
+  *comm_out = (void*)c;
+  return PA_OK;
+}
+
+int pa_comm_destroy(void* comm) {
+  NcclApi& a = nccl_api();
+  if (!a.ok || !comm) return PA_OK;
+  a.CommDestroy((ncclComm_t)comm);
+  return PA_OK;
+}
+
+int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                     int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg, void* ws,
+                     size_t ws_bytes_, void* comm, int rank, int nranks, pa_report* report,
+                     void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
+  if (rc) return rc;
+  if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
+  for (int f = 0; f < nfaces; ++f)
+    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
+      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
+  Dist d{(ncclComm_t)comm, rank, nranks};
+  PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
+                                   (const T*)rhs, cfg, ws, ws_bytes_, report, (cudaStream_t)stream,
+                                   nranks > 1 ? &d : nullptr));
 }
 
 int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,

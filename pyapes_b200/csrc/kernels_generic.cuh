@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kBlock) k_cg_dupdate(GridDev g, const T* __res
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.cells;
        idx += (long long)gridDim.x * blockDim.x) {
     Cell c = decode(g, idx);
-    if (in_region(g, c)) d[idx] = r[idx] + beta * d[idx];
+    // ghost planes of a slab too: r's ghosts are exchanged, so d's ghosts follow bit for bit
+    if (in_region(g, c) || !owned(g, c)) d[idx] = r[idx] + beta * d[idx];
   }
 }
 

@@ -42,6 +42,7 @@ struct TilePlan {
   int vec_ok;                        // 16-byte vector access legal (n2 % VEC == 0)
   int fuse_fin;                      // phase B also finalizes the iteration (static shell)
   int ry;                            // rows per thread of the instantiation to launch (2 or 4)
+  int dist;                          // multi-GPU: leave raw sums for the NCCL all-reduce
 };
 
 template <typename T>
@@ -126,6 +127,7 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.chunks = (g.n[0] + p.cx - 1) / p.cx;
   p.vec_ok = (g.n[2] % C::VEC == 0) ? 1 : 0;
   p.fuse_fin = 0;
+  p.dist = 0;
   return true;
 }
 
@@ -494,7 +496,7 @@ k_cg_phaseA(TilePlan p, GridDev g, OpDev<T> o, const T* __restrict__ r, const T*
     phaseA_body<T, RY, false>(p, g, o, r, d_old, d_new, beta, smem, y0, z0, acc[0]);
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_CG_DAD});
+  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, p.dist ? ST_NONE : ST_CG_DAD});
 }
 
 // =========================================================================================

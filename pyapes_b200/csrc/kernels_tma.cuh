@@ -173,6 +173,7 @@ inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const 
   p.chunks = (g.n[0] + p.cx - 1) / p.cx;
   p.vec_ok = 1;
   p.fuse_fin = 0;
+  p.dist = 0;
   bool ok = make_map<T>(&tp.x_own[0], x, g, C::TZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::TZ, C::TY) &&
             make_map<T>(&tp.r_own, r, g, C::TZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
             make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) &&
@@ -651,7 +652,7 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_CG_DAD});
+  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, p.dist ? ST_NONE : ST_CG_DAD});
 }
 
 // ---- launchers -----------------------------------------------------------------------------------

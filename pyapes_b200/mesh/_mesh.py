@@ -110,10 +110,15 @@ class Mesh:
         self._x_host = [
             torch.linspace(lo_h[i].item(), up_h[i].item(), self._nx[i], dtype=ft) for i in range(self.dim)
         ]
+        self.slab = None
+        self._localize()  # hook: a slab-decomposed mesh narrows axis 0 to its own planes here
         self.x = [x.to(self.device) for x in self._x_host]
         # meshgrid returns stride-0 views: no memory is spent here
         self.grid = torch.meshgrid(self.x, indexing="ij")
         self.o_mask: dict = {}
+
+    def _localize(self) -> None:
+        """Single-GPU mesh: the local block is the whole grid."""
 
     # ---- lazily materialised masks ---------------------------------------------------
     @cached_property

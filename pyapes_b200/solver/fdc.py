@@ -54,6 +54,14 @@ def _return_bc_val(bc, var: Field, dim: int, shape) -> Tensor | float:
     raise ValueError(f"Unknown boundary condition value: {v}")
 
 
+def _owns_face(var: Field, bc) -> bool:
+    """Slab-decomposed meshes: the two faces normal to axis 0 exist on the edge ranks only."""
+    slab = getattr(var.mesh, "slab", None)
+    if slab is None or bc.bc_face_dim != 0:
+        return True
+    return slab["rank"] == (0 if bc.bc_n_dir < 0 else slab["world"] - 1)
+
+
 def _grad_like_rhs(var: Field, gamma_min: Tensor, gamma_max: Tensor) -> Tensor:
     """fdc.py:505-540: Neumann faces only; lower faces take gamma_max, upper gamma_min."""
     out = torch.zeros_like(var())
@@ -61,7 +69,7 @@ def _grad_like_rhs(var: Field, gamma_min: Tensor, gamma_max: Tensor) -> Tensor:
         return out
     for j in range(var.mesh.dim):
         for bc in var.bcs:
-            if bc.bc_type != "neumann":
+            if bc.bc_type != "neumann" or not _owns_face(var, bc):
                 continue
             pl = _plane(var, bc, 1)
             at_bc = _return_bc_val(bc, var, 0, out[0][pl].shape)
@@ -97,6 +105,8 @@ class Discretizer:
         phi = var()
         N.require_cuda(phi, "field")
         nd = var.mesh.dim
+        if getattr(var.mesh, "slab", None) is not None:
+            raise NotImplementedError("pyapes_b200: explicit FDC operators on a slab-decomposed mesh are not built yet")
         grid = L.lower_grid(var.nx, var.bcs)
         op, keep = L.lower_op(A_coeffs, nd, phi.dtype)
         code, stream = N.dtype_code(phi.dtype), N.current_stream(phi.device)
@@ -152,7 +162,7 @@ class Laplacian(Discretizer):
         dx = var.dx
         for j in range(var.mesh.dim):
             for bc in var.bcs:
-                if bc.bc_type != "neumann":
+                if bc.bc_type != "neumann" or not _owns_face(var, bc):
                     continue
                 pl = _plane(var, bc, 1)
                 alpha = torch.zeros_like(out[0][pl])

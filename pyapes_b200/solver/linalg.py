@@ -66,7 +66,8 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     if min(mesh.nx) < 3:
         raise ValueError("Linalg: min(mesh.nx) >= 3 is required (linalg.py:44-45)")
     code = N.dtype_code(x.dtype)
-    grid = L.lower_grid(mesh.nx, var.bcs)
+    slab = getattr(mesh, "slab", None)
+    grid = L.lower_grid(mesh.nx, var.bcs, slab)
     faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd)
     eq, keep_e = L_lower_equation(eqs, var)
     lib = N.lib()
@@ -80,9 +81,18 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     cfg.use_graph = 1 if config.get("use_graph", True) else 0
     cfg.variant = int(config.get("variant", 0))
     rep = N.Report()
-    N.check(getattr(lib, _SOLVERS[method])(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
-                                           rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, rep,
-                                           N.current_stream(x.device)))
+    if slab is not None and slab["world"] > 1:
+        from pyapes_b200 import parallel
+
+        if method != "cg":
+            raise NotImplementedError("pyapes_b200: only CG runs on slab-decomposed meshes so far")
+        N.check(lib.pa_cg_solve_dist(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
+                                     rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, parallel.get_comm(x.device),
+                                     slab["rank"], slab["world"], rep, N.current_stream(x.device)))
+    else:
+        N.check(getattr(lib, _SOLVERS[method])(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
+                                               rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, rep,
+                                               N.current_stream(x.device)))
     del keep_f, keep_e, ws
     var._last_launches = rep.launches
     if rep.itr > 0 or rep.status == N.BAD_TOL:
