@@ -121,6 +121,10 @@ def cpu_baseline(n_cpu=128, iters=20):
     from oracle import fd_oracle as O
 
     torch.set_default_dtype(torch.float64)
+    try:  # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     xs, dx = O.make_axes([0, 0, 0], [1, 1, 1], [n_cpu] * 3)
     bcs = [O.FaceBC(f, "dirichlet", 0.0) for f in O.FACES]
     x0 = torch.zeros(1, n_cpu, n_cpu, n_cpu, dtype=torch.float64)

@@ -47,7 +47,7 @@ class TorchDevice:
     operator/solver call on them raises: there is no CPU compute path in this package."""
 
     def __init__(self, device_type: str = "cpu"):
-        assert device_type in TORCH_DEVICE
+        assert device_type.split(":")[0] in TORCH_DEVICE
         self.device_type = device_type
         self._device = torch.device(device_type.lower())
 

@@ -73,7 +73,8 @@ class Mesh:
         device: str = "cpu",
         dtype: str | int = "double",
     ):
-        assert device in TORCH_DEVICE, "Mesh: device only accept cpu or cuda"
+        # "cuda:N" is accepted as well (one process per GPU in the slab-decomposed runs)
+        assert device.split(":")[0] in TORCH_DEVICE, "Mesh: device only accept cpu or cuda"
         self.device = TorchDevice(device).device
         assert dtype in DTYPE_DOUBLE or dtype in DTYPE_SINGLE, "Mesh: dtype only accept double or single"
         self.dtype = DType(dtype)

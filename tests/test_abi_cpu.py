@@ -1,0 +1,107 @@
+"""CPU checks of the drop-in boundary: the library loads without a GPU, exports every symbol
+that include/pyapes_b200.h declares, the ctypes structs match the header's layout, and compute
+entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "pyapes_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as G
+
+    G.build()
+    from pyapes_b200 import _native as N
+
+    lib = N.lib()
+    names = _header_functions()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/pyapes_b200.h but not exported"
+        assert name in N.SYMBOLS, f"{name} has no ctypes prototype in pyapes_b200/_native.py"
+    assert lib.pa_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    from pyapes_b200 import _native as N
+
+    assert C.sizeof(N.FaceBC) == 32
+    assert C.sizeof(N.Grid) == 60
+    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12
+    assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
+    assert C.sizeof(N.Report) == 24 and C.sizeof(N.SolverCfg) == 24
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    from pyapes_b200 import _native as N
+
+    lib = N.lib()
+    assert lib.pa_device_count() == 0
+    g, eq = N.Grid(), N.Equation()
+    rc = lib.pa_stencil_apply(g, eq, N.PA_F64, None, None, None)
+    assert rc == -2 and b"no CPU path" in lib.pa_last_error()
+    with pytest.raises(N.NativeError):
+        N.check(rc)
+
+
+def test_host_layer_rejects_cpu_fields():
+    from pyapes_b200._native import NativeError
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdc import FDC
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import homogeneous_bcs
+
+    mesh = Mesh(Box[0:1, 0:1], None, [8, 8], "cpu")
+    var = Field("p", 1, mesh, {"domain": homogeneous_bcs(2, 0.0, "dirichlet"), "obstacle": None})
+    s = Solver({"fdm": {"method": "cg", "tol": 1e-6, "max_it": 10, "report": False}})
+    s.set_eq(FDM().laplacian(var) == 1.0)
+    for call in (s.solve, lambda: s.Aop(var), lambda: FDC({"grad": {"edge": False}}).grad(var),
+                 lambda: var.bcs[0].apply(var(), mesh.grid, 0)):
+        with pytest.raises(NativeError):
+            call()
+
+
+def test_dsl_semantics_match_reference():
+    """Equation algebra (fdm.py:75-105) and set_eq's in-place RHS mutation (ops.py:74-81)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    mesh = Mesh(Box[0:1, 0:1], None, [9, 7], "cpu")
+    bcs = mixed_bcs([0.5, 0.0, 1.0, 0.0], ["neumann", "dirichlet", "neumann", "dirichlet"])
+    var = Field("p", 1, mesh, {"domain": bcs, "obstacle": None})
+    fdm = FDM({"div": {"limiter": "upwind", "edge": False}})
+    rhs = torch.zeros_like(var())
+    s = Solver({"fdm": {"method": "bicgstab", "tol": 1e-6, "max_it": 10, "report": False}})
+    eq = fdm.div(0.5, var) - fdm.laplacian(0.1, var)
+    s.set_eq(eq == rhs)
+    assert [s.eqs[k]["name"] for k in s.eqs] == ["Div", "Laplacian"]
+    assert s.eqs[0]["sign"] == 1.0 and s.eqs[1]["sign"] == -1
+    assert s.rhs is rhs and rhs.abs().sum() > 0  # Neumann adjustment added in place
+    assert fdm.div.ops == {} and fdm.div.rhs is None  # singletons reset
+    with pytest.raises(RuntimeError):
+        s.config["fdm"]["method"] = "gmres"
+        from pyapes_b200.solver.linalg import solve
+
+        solve(var, rhs, None, s.eqs, s.config["fdm"], mesh)
+    with pytest.raises(NotImplementedError):
+        from pyapes_b200.geometry import Cylinder
+
+        Mesh(Cylinder[0:1, 0:1], None, [5, 5], "cpu")
