@@ -8,6 +8,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
+#include "kernels_tma_pw.cuh"
 #include "dist.cuh"
 
 namespace pa {
@@ -371,7 +372,8 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
 
 template <typename T>
 static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
-                               const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt) {
+                               const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt,
+                               const TilePlan* pw = nullptr) {
   T* r0 = (T*)w.vec[0];
   T* r = (T*)w.vec[1];
   T* p = (T*)w.vec[2];
@@ -379,11 +381,31 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   T* s = (T*)w.vec[4];
   T* t = (T*)w.vec[5];
   int nb = grid_blocks(g.cells);
-  k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
-  k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_BI_V);
-  k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_BI_S);
-  k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_BI_T);
-  k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
+  // streaming axpy stages: legal when every cell is owned and the cell count is a multiple of
+  // the 16-byte vector width (the region test is unnecessary: everything is 0 outside it)
+  constexpr int SV = StreamVec<T>::N;
+  const bool stream_ok = (g.cells % SV == 0) && g.olo0 == 0 && g.ohi0 == g.n[0];
+  const long long nvec = g.cells / SV;
+  if (stream_ok)
+    k_bi_p_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r, p, v, w.st);
+  else
+    k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
+  if (pw)
+    launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_BI_V);
+  else
+    k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_BI_V);
+  if (stream_ok)
+    k_bi_s_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r, v, s, w.st, w.partials, ST_BI_S);
+  else
+    k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_BI_S);
+  if (pw)
+    launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_BI_T);
+  else
+    k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_BI_T);
+  if (stream_ok)
+    k_bi_x_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, cur, nxt, p, s, t, r, w.st, w.partials);
+  else
+    k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
   L.count += 5;
   launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
   k_finalize<T><<<1, 1, 0, L.s>>>(ST_BI_FIN, w.st);
@@ -393,10 +415,19 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
 template <typename T>
 static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
                              const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt,
-                             const T* rhs) {
+                             const T* rhs, const TilePlan* pw = nullptr) {
   int nb = grid_blocks(g.cells);
-  k_pointwise_update<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, rhs, (T)0, w.st, w.partials);
-  ++L.count;
+  if (pw) {
+    // static shell: the sweep also finalizes the iteration (shell part of the norm is 0)
+    const bool fuse = static_shell(nfaces, faces) != 0;
+    launch_star_tma<T, PW_JACOBI>(L.s, g, eq, *pw, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
+                                  fuse ? ST_JA_FIN : ST_NONE);
+    ++L.count;
+    if (fuse) return;
+  } else {
+    k_pointwise_update<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, rhs, (T)0, w.st, w.partials);
+    ++L.count;
+  }
   launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
   launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_JA_FIN);
 }
@@ -441,6 +472,11 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     plan.fuse_fin = tmap.tile.fuse_fin = 0;
   }
 
+  TilePlan pwtile;
+  const bool pw_ok = cfg->variant != 1 && pw_eligible<T>(g, *peq, nfaces, faces);
+  if (pw_ok) pw_tile_plan<T>(g, pwtile);
+  const TilePlan* pw = pw_ok ? &pwtile : nullptr;
+
   k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
   ++L.count;
   launch_bcs<T>(L, g, nfaces, faces, x, nullptr);
@@ -452,8 +488,12 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     T* d = (T*)w.vec[1];
     const long long plane = (long long)g.n[1] * g.n[2];
     if (dist) dist_halo_exchange<T>(*dist, x, plane, g.olo0, g.ohi0, stream);  // x ghosts for r0
-    k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r, d, w.st, w.partials,
-                                                  dist ? ST_NONE : ST_CG_INIT);
+    if (pw)
+      launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r, d, (T)0, w.st, w.partials,
+                                   dist ? ST_NONE : ST_CG_INIT);
+    else
+      k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r, d, w.st, w.partials,
+                                                    dist ? ST_NONE : ST_CG_INIT);
     ++L.count;
     if (dist) {
       dist_halo_exchange<T>(*dist, r, plane, g.olo0, g.ohi0, stream);
@@ -471,8 +511,11 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     T* r0 = (T*)w.vec[0];
     T* r = (T*)w.vec[1];
     for (int i = 2; i < 6; ++i) PA_CUDA(cudaMemsetAsync(w.vec[i], 0, vbytes, stream));
-    k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials,
-                                                  ST_BI_INIT);
+    if (pw)
+      launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r0, r, (T)0, w.st, w.partials, ST_BI_INIT);
+    else
+      k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials,
+                                                    ST_BI_INIT);
     ++L.count;
   }
   PA_CUDA(cudaGetLastError());
@@ -493,9 +536,9 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
                       use_tma ? &tmap : nullptr, dist);
     else if (method == PA_METHOD_BICGSTAB)
-      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt);
+      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, pw);
     else
-      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs);
+      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs, pw);
   };
 
   const long long max_iters = (method == PA_METHOD_BICGSTAB)
@@ -778,8 +821,16 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   GridDev g = make_grid(*pg);
   EqDev<T> eq = make_eq<T>(*peq);
   Launcher L{s};
-  k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, phi_new, rhs,
-                                                                   (T)dt, nullptr, nullptr);
+  bool done = false;
+  if (pw_eligible<T>(g, *peq, nfaces, faces)) {
+    TilePlan tile;
+    pw_tile_plan<T>(g, tile);
+    done = launch_star_tma<T, PW_EULER>(s, g, eq, tile, phi, rhs, phi_new, nullptr, (T)dt, nullptr, nullptr,
+                                        ST_NONE);
+  }
+  if (!done)
+    k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, phi_new, rhs,
+                                                                     (T)dt, nullptr, nullptr);
   launch_bcs<T>(L, g, nfaces, faces, phi_new, nullptr);
   PA_CUDA(cudaGetLastError());
   return PA_OK;

@@ -526,6 +526,96 @@ __global__ void __launch_bounds__(kBlock) k_bi_x(GridDev g, const T* __restrict_
                  StoreSums<T, 1>{st, R_A, ST_NONE});
 }
 
+// Streaming (index-free) versions of the three axpy stages.  Outside the solver region r, p, v,
+// s, t are identically 0, so the updates can run over every cell: 0 + beta*(0 - omega*0) == 0 and
+// x + alpha*0 == x exactly.  16-byte vector accesses, grid-stride.  Single-GPU only (all cells
+// owned).  `n` must be a multiple of the vector width; the caller falls back otherwise.
+template <typename T>
+struct StreamVec {
+  static constexpr int N = 16 / sizeof(T);
+  struct alignas(16) type {
+    T v[16 / sizeof(T)];
+  };
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_bi_p_stream(long long nvec, const T* __restrict__ r,
+                                                        T* __restrict__ p, const T* __restrict__ v,
+                                                        const SolverState* st) {
+  typedef typename StreamVec<T>::type V;
+  if (st->done) return;
+  const T beta = (T)st->scal[S_BETA], omega = (T)st->scal[S_OMEGA];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    V a = reinterpret_cast<const V*>(r)[i], b = reinterpret_cast<const V*>(p)[i],
+      c = reinterpret_cast<const V*>(v)[i], o;
+#pragma unroll
+    for (int e = 0; e < StreamVec<T>::N; ++e) {
+      T t = b.v[e] - omega * c.v[e];
+      o.v[e] = a.v[e] + beta * t;
+    }
+    reinterpret_cast<V*>(p)[i] = o;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_bi_s_stream(long long nvec, const T* __restrict__ r,
+                                                        const T* __restrict__ v, T* __restrict__ s,
+                                                        SolverState* st, double* partials, int stage) {
+  typedef typename StreamVec<T>::type V;
+  if (st->done) return;
+  const T alpha = (T)st->scal[S_ALPHA];
+  double acc[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    V a = reinterpret_cast<const V*>(r)[i], c = reinterpret_cast<const V*>(v)[i], o;
+#pragma unroll
+    for (int e = 0; e < StreamVec<T>::N; ++e) {
+      T sv = a.v[e] - alpha * c.v[e];
+      o.v[e] = sv;
+      T q = sv * sv;
+      acc[0] += (double)q;
+    }
+    reinterpret_cast<V*>(s)[i] = o;
+  }
+  grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, stage});
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T* __restrict__ x,
+                                                        T* __restrict__ x_new, const T* __restrict__ p,
+                                                        const T* __restrict__ s, const T* __restrict__ t,
+                                                        T* __restrict__ r, SolverState* st,
+                                                        double* partials) {
+  typedef typename StreamVec<T>::type V;
+  if (st->done) return;
+  const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA];
+  const bool early = st->finished_flag != 0;
+  double acc[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    V xv = reinterpret_cast<const V*>(x)[i], pv = reinterpret_cast<const V*>(p)[i], xo;
+    if (early) {
+#pragma unroll
+      for (int e = 0; e < StreamVec<T>::N; ++e) xo.v[e] = xv.v[e] + alpha * pv.v[e];
+    } else {
+      V sv = reinterpret_cast<const V*>(s)[i], tv = reinterpret_cast<const V*>(t)[i], ro;
+#pragma unroll
+      for (int e = 0; e < StreamVec<T>::N; ++e) {
+        T xn = xv.v[e] + alpha * pv.v[e];
+        xo.v[e] = xn + sv.v[e] * omega;
+        T rn = sv.v[e] - omega * tv.v[e];
+        ro.v[e] = rn;
+        T q = rn * rn;
+        acc[0] += (double)q;
+      }
+      reinterpret_cast<V*>(r)[i] = ro;
+    }
+    reinterpret_cast<V*>(x_new)[i] = xo;
+  }
+  grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_NONE});
+}
+
 // ---------------------------------------------------------------------------------------
 // Jacobi and explicit Euler (not in the reference)
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,391 @@
+// TMA-staged star engine for everything that is "one stencil application + a pointwise
+// epilogue": residual init, Jacobi sweep, explicit Euler step, BiCGSTAB's two operator
+// applications.  Same producer/consumer mbarrier pipeline as kernels_tma.cuh, but
+//   * the equation may have up to PA_MAX_OPS constant-coefficient STAR operators (e.g. upwind
+//     Div + Laplacian of the advection-diffusion problems), summed in the reference's order;
+//   * one optional auxiliary own-tile input (rhs or r0) rides in the same pipeline stage.
+// Algorithmic traffic: R in (+halo), [R aux], W out  = 2-3 words per cell.
+#pragma once
+#include "kernels_tma.cuh"
+
+namespace pa {
+
+enum PwMode {
+  PW_RESID = 0,    // out = rhs - A(in) on the region, 0 elsewhere; out2 = out; sum out^2
+  PW_JACOBI = 1,   // out = in + (rhs - A(in)) / diag   on the region, in elsewhere; sum |d|^2
+  PW_EULER = 2,    // out = in + dt*(rhs - A(in))       on the region, in elsewhere
+  PW_APPLY_V = 3,  // out = A(in) on the region, 0 elsewhere; sum r0*out
+  PW_APPLY_T = 4,  // out = A(in) ...; sums out*in, out*out, r0*out; skipped when finished_flag
+};
+
+template <typename T, int RY_>
+struct PwCfg : TmaCfg<T, RY_> {
+  typedef TmaCfg<T, RY_> B;
+  static constexpr int STAGE = B::HALO_SLOT + B::OWN_SLOT;  // in halo, aux own
+  static constexpr size_t SMEM = (size_t)B::S * STAGE + B::BAR_BYTES + 128;
+};
+
+struct PwPlan {
+  TilePlan tile;
+  CUtensorMap in_halo[2];  // the two ping-pong buffers of the stencilled field (or one)
+  CUtensorMap aux_own;     // rhs / r0
+  int has_aux;
+};
+
+// sum over operators of sign*param*(star), reference order (ops.py:130-149, fdc.py:103-108)
+template <typename T, int RY, bool LEAN, int NOPS, typename F>
+__device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<T, RY>& c, int clx,
+                                              bool actx, const T (&vm)[RY][VecOf<T>::N],
+                                              const T (&vc)[RY][VecOf<T>::N],
+                                              const T (&vp)[RY][VecOf<T>::N], const T (&up)[VecOf<T>::N],
+                                              const T (&dn)[VecOf<T>::N], const T (&zl)[RY],
+                                              const T (&zr)[RY], F emit) {
+  constexpr int VEC = VecOf<T>::N;
+#pragma unroll
+  for (int k = 0; k < RY; ++k) {
+    const int cy = LEAN ? 0 : c.cly[k];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int cz = LEAN ? 0 : c.clz[e];
+      const T v0 = vc[k][e];
+      const T yp = (k == RY - 1) ? dn[e] : vc[k + 1 < RY ? k + 1 : k][e];
+      const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
+      const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
+      const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
+      T res = (T)0, diag = (T)0;
+      const int nops = NOPS > 0 ? NOPS : eq.nops;  // compile-time count: unrolled, constant operands
+#pragma unroll
+      for (int q = 0; q < nops; ++q) {
+        const OpDev<T>& o = eq.op[q];
+        T acc = (T)0, dacc = (T)0;
+        if (actx) {
+          T s = o.coef[0][clx][0] * vp[k][e];
+          s = s + o.coef[0][clx][1] * v0;
+          s = s + o.coef[0][clx][2] * vm[k][e];
+          acc = acc + s;
+          dacc = dacc + o.coef[0][clx][1];
+        }
+        {
+          T s = o.coef[1][cy][0] * yp;
+          s = s + o.coef[1][cy][1] * v0;
+          s = s + o.coef[1][cy][2] * ym;
+          acc = acc + s;
+          dacc = dacc + o.coef[1][cy][1];
+        }
+        {
+          T s = o.coef[2][cz][0] * zp;
+          s = s + o.coef[2][cz][1] * v0;
+          s = s + o.coef[2][cz][2] * zm;
+          acc = acc + s;
+          dacc = dacc + o.coef[2][cz][1];
+        }
+        if (o.has_param) {
+          acc = acc * o.param;
+          dacc = dacc * o.param;
+        }
+        acc = acc * o.sign;
+        dacc = dacc * o.sign;
+        res = res + acc;
+        diag = diag + dacc;
+      }
+      emit(k, e, res, diag);
+    }
+  }
+}
+
+template <typename T, int RY, int MODE, bool LEAN, int NOPS>
+__device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
+                                            T* __restrict__ out, T* __restrict__ out2, T dt, bool has_aux,
+                                            unsigned char* stages, uint64_t* full, uint64_t* empty,
+                                            int y0, int z0, int x0, int x1, double (&acc_out)[3]) {
+  typedef PwCfg<T, RY> C;
+  constexpr int VEC = C::VEC;
+  ConsCtx<T, RY> c;
+  cons_setup<T, RY>(g, c, y0, z0);
+  const bool actx = g.act[0] != 0;
+  const long long n12 = (long long)g.n[1] * g.n[2];
+  T* op_ = out + (long long)x0 * n12 + c.goff;
+  T* op2_ = out2 ? out2 + (long long)x0 * n12 + c.goff : nullptr;
+
+  auto halo = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE); };
+  auto aux = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE + C::HALO_SLOT); };
+  auto load_own = [&](int s, T (&v)[RY][VEC]) {
+    const T* h = halo(s) + c.hoff;
+#pragma unroll
+    for (int k = 0; k < RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
+  };
+  auto release = [&](int s) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&empty[s]);
+  };
+
+  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (actx) {
+    mbar_wait(&full[0], 0);
+    load_own(0, A);
+    release(0);
+  }
+  mbar_wait(&full[1 % C::S], 0);
+  load_own(1 % C::S, B);
+
+  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+    const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
+    if (actx) {
+      mbar_wait(&full[sn], (i / C::S) & 1);
+      load_own(sn, vp);
+    }
+    const T* h = halo(sc) + c.hoff;
+    const bool xreg = x >= g.lo[0] && x < g.hi[0];
+    const bool xown = x >= g.olo0 && x < g.ohi0;
+    const int gx = x + g.goff0;
+    const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
+    T ax[RY][VEC], dg[RY][VEC];
+    if (xreg) {
+      T up[VEC], dn[VEC], zl[RY], zr[RY];
+      lds_vec<T>(h - C::BOXZ, up);
+      lds_vec<T>(h + RY * C::BOXZ, dn);
+#pragma unroll
+      for (int k = 0; k < RY; ++k) {
+        zl[k] = h[k * C::BOXZ - 1];
+        zr[k] = h[k * C::BOXZ + VEC];
+      }
+      const int clx = actx ? coef_class(g, 0, x) : 0;
+      star_cells_eq<T, RY, LEAN, NOPS>(eq, c, clx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T v, T d) {
+        ax[k][e] = v;
+        dg[k][e] = d;
+      });
+    }
+#pragma unroll
+    for (int k = 0; k < RY; ++k) {
+      T av[VEC], o[VEC];
+      if (has_aux) {
+        lds_vec<T>(aux(sc) + c.ooff + k * C::TZ, av);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) av[e] = (T)0;
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const bool in = xreg && (LEAN || ((c.inreg >> (k * VEC + e)) & 1u));
+        const T xc = vc[k][e];
+        if (MODE == PW_RESID) {
+          const T res = in ? av[e] - ax[k][e] : (T)0;
+          o[e] = res;
+          if (in && xown) {
+            const T q = res * res;
+            a0 += (double)q;
+          }
+        } else if (MODE == PW_JACOBI) {
+          T xn = xc;
+          if (in) {
+            const T res = av[e] - ax[k][e];
+            xn = xc + res / dg[k][e];
+          }
+          o[e] = xn;
+          if (xown && !xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
+            const T df = xn - xc;
+            const T q = df * df;
+            a1 += (double)q;
+          }
+        } else if (MODE == PW_EULER) {
+          T xn = xc;
+          if (in) {
+            const T res = av[e] - ax[k][e];
+            xn = xc + dt * res;
+          }
+          o[e] = xn;
+        } else {  // PW_APPLY_V / PW_APPLY_T
+          const T a = in ? ax[k][e] : (T)0;
+          o[e] = a;
+          if (in && xown) {
+            if (MODE == PW_APPLY_V) {
+              const T q = av[e] * a;
+              a0 += (double)q;
+            } else {
+              const T q0 = a * xc, q1 = a * a, q2 = av[e] * a;
+              a0 += (double)q0;
+              a1 += (double)q1;
+              a2 += (double)q2;
+            }
+          }
+        }
+      }
+      stg_row<T, RY, LEAN>(op_ + (long long)k * g.n[2], c, k, o);
+      if (MODE == PW_RESID && op2_) stg_row<T, RY, LEAN>(op2_ + (long long)k * g.n[2], c, k, o);
+    }
+    op_ += n12;
+    if (op2_) op2_ += n12;
+    release(sc);
+  };
+
+  int x = x0, i = 2;
+  if (LEAN) {  // 3x unrolled: no register rotation
+    while (true) {
+      step(A, B, Cc, x, i);
+      if (++x >= x1) break;
+      ++i;
+      step(B, Cc, A, x, i);
+      if (++x >= x1) break;
+      ++i;
+      step(Cc, A, B, x, i);
+      if (++x >= x1) break;
+      ++i;
+    }
+  } else {  // boundary tiles: one copy of the body (instruction-cache footprint), rotate registers
+    for (; x < x1; ++x, ++i) {
+      step(A, B, Cc, x, i);
+#pragma unroll
+      for (int k = 0; k < RY; ++k)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          A[k][e] = B[k][e];
+          B[k][e] = Cc[k][e];
+        }
+    }
+  }
+  acc_out[0] = a0;
+  acc_out[1] = a1;
+  acc_out[2] = a2;
+}
+
+template <typename T, int RY, int MODE, int NOPS>
+__global__ void __launch_bounds__(PwCfg<T, RY>::THREADS, 2)
+k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_aux,
+           TilePlan p, GridDev g, EqDev<T> eq, T* __restrict__ out, T* __restrict__ out2, T dt,
+           int has_aux, SolverState* st, double* partials, int stage) {
+  typedef PwCfg<T, RY> C;
+  extern __shared__ unsigned char smem_dyn[];
+  if (st != nullptr && st->done) return;
+  if (MODE == PW_APPLY_T && st->finished_flag) return;
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  unsigned char* stages = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE);
+  uint64_t* empty = full + C::S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
+  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const bool actx = g.act[0] != 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], C::CWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double acc[3] = {0.0, 0.0, 0.0};
+  if (warp == C::CWARPS) {
+    if (lane == 0) {
+      const int n = x1 - x0 + 2;
+      for (int i = 0; i < n; ++i) {
+        if (!actx && i != 1) continue;
+        const int pl = x0 - 1 + i;
+        const int s = i & (C::S - 1);
+        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
+        const bool inner = has_aux && (pl >= x0 && pl < x1);
+        mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? C::OWN_BYTES : 0)));
+        unsigned char* sb = stages + (size_t)s * C::STAGE;
+        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+        tma_load_3d(sb, &tm_in, z0 - C::HZ, y0 - 1, xw, &full[s]);
+        if (inner) tma_load_3d(sb + C::HALO_SLOT, &tm_aux, z0, y0, xw, &full[s]);
+      }
+    }
+  } else {
+    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    if (full_tile && !edge)
+      pw_consumer<T, RY, MODE, true, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
+                                           x1, acc);
+    else
+      pw_consumer<T, RY, MODE, false, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
+                                            x1, acc);
+  }
+  if (MODE == PW_EULER) return;  // no reductions
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  grid_reduce<3>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 3>{st, R_A, stage});
+}
+
+// ---- host ------------------------------------------------------------------------------------
+template <typename T>
+inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces) {
+  typedef PwCfg<T, kTmaRY> C;
+  if (eq.nops < 1 || eq.nops > PA_MAX_OPS) return false;
+  for (int k = 0; k < eq.nops; ++k)
+    if (eq.ops[k].kind != PA_OP_STAR) return false;
+  if (!g.act[1] || !g.act[2]) return false;
+  if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
+  for (int f = 0; f < nfaces; ++f)
+    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+template <typename T>
+inline void pw_tile_plan(const GridDev& g, TilePlan& p) {
+  typedef PwCfg<T, kTmaRY> C;
+  p.ry = kTmaRY;
+  p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;
+  p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
+  const int tiles = p.tiles_y * p.tiles_z;
+  const int slots = kNumSMs * 2;
+  int best_c = 1;
+  double best = -1.0;
+  const int maxc = g.n[0] >= 16 ? g.n[0] / 8 : 1;
+  for (int c = 1; c <= maxc; ++c) {
+    const int cx = (g.n[0] + c - 1) / c;
+    const int cc = (g.n[0] + cx - 1) / cx;
+    const long long items = (long long)cc * tiles;
+    if (items > kMaxPartials) break;
+    const long long waves = (items + slots - 1) / slots;
+    const double quant = (double)items / (double)(waves * slots);
+    const double halo = g.act[0] ? (double)cx / (double)(cx + 2) : 1.0;
+    const double score = quant * halo * (items >= slots ? 1.0 : (double)items / slots);
+    if (score > best + 1e-9) {
+      best = score;
+      best_c = cc;
+    }
+  }
+  p.cx = (g.n[0] + best_c - 1) / best_c;
+  p.chunks = (g.n[0] + p.cx - 1) / p.cx;
+  p.vec_ok = 1;
+  p.fuse_fin = 0;
+  p.dist = 0;
+}
+
+// One launch of the engine.  `in` is the stencilled field, `aux` rhs / r0 (may be null).
+template <typename T, int MODE, int NOPS>
+inline void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CUtensorMap& tm_aux,
+                              const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, bool has_aux, T* out,
+                              T* out2, T dt, SolverState* st, double* partials, int stage) {
+  typedef PwCfg<T, kTmaRY> C;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_star_tma<T, kTmaRY, MODE, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)C::SMEM);
+    attr = true;
+  }
+  dim3 grid(tile.tiles_z, tile.tiles_y, tile.chunks);
+  k_star_tma<T, kTmaRY, MODE, NOPS><<<grid, C::THREADS, C::SMEM, s>>>(tm_in, tm_aux, tile, g, eq, out, out2, dt,
+                                                                     has_aux ? 1 : 0, st, partials, stage);
+}
+
+template <typename T, int MODE>
+inline bool launch_star_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
+                            const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
+                            double* partials, int stage) {
+  typedef PwCfg<T, kTmaRY> C;
+  CUtensorMap tm_in, tm_aux;
+  if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
+  if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::TZ, C::TY)) return false;
+  // operator count known at compile time for the common equations (1: Poisson, 2: adv-diff)
+  if (eq.nops == 1)
+    launch_star_tma_n<T, MODE, 1>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  else if (eq.nops == 2)
+    launch_star_tma_n<T, MODE, 2>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  else
+    launch_star_tma_n<T, MODE, 0>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  return true;
+}
+
+}  // namespace pa
