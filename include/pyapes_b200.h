@@ -191,6 +191,12 @@ int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_
                   int dtype, const void* phi, void* phi_new, const void* rhs, double dt,
                   void* stream);
 
+/* --- `nsteps` explicit Euler steps ping-ponging between phi (input) and phi_alt; the step pair is
+ *     replayed as a CUDA graph.  *result_in_alt = 1 if the final field is in phi_alt. */
+int pa_euler_steps(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                   int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
+                   int* result_in_alt, void* stream);
+
 /* --- end-to-end entry with HOST buffers: copies x and rhs to the device, solves with CG,
  *     copies the solution back.  x_host, rhs_host: n0*n1*n2 elements of dtype (pinned
  *     memory recommended).  Device scratch is allocated and freed inside the call. */

@@ -110,6 +110,8 @@ SYMBOLS = {
                                   _P, _P, _P, C.POINTER(SolverCfg), _P, C.c_size_t, C.POINTER(Report), _P]),
     "pa_euler_step": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                 _P, _P, _P, C.c_double, _P]),
+    "pa_euler_steps": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
+                                 _P, _P, _P, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "pa_cg_solve_host": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                    _P, _P, C.POINTER(SolverCfg), C.POINTER(Report)]),
 }

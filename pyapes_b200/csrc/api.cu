@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -814,27 +815,69 @@ int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
 }
 
 }  // extern "C"
+// n explicit Euler steps, ping-ponging between `a` (holds phi on entry) and `b`.  A pair of
+// steps is captured once as a CUDA graph and replayed.  Static shell (all faces Dirichlet):
+// after the first step the shell already holds the BC values and later steps copy it, so BC
+// launches are only needed in the first step.
 template <typename T>
 static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
-                      const pa_face_bc* faces, const T* phi, T* phi_new, const T* rhs, double dt,
-                      cudaStream_t s) {
+                      const pa_face_bc* faces, T* a, T* b, const T* rhs, double dt, int nsteps,
+                      int* result_in_b, cudaStream_t caller) {
+  cudaStream_t s;
+  int rcs = solver_stream(caller, &s);
+  if (rcs != PA_OK) return rcs;
   GridDev g = make_grid(*pg);
   EqDev<T> eq = make_eq<T>(*peq);
   Launcher L{s};
-  bool done = false;
-  if (pw_eligible<T>(g, *peq, nfaces, faces)) {
-    TilePlan tile;
-    pw_tile_plan<T>(g, tile);
-    done = launch_star_tma<T, PW_EULER>(s, g, eq, tile, phi, rhs, phi_new, nullptr, (T)dt, nullptr, nullptr,
-                                        ST_NONE);
+  const bool tma = pw_eligible<T>(g, *peq, nfaces, faces);
+  TilePlan tile;
+  if (tma) pw_tile_plan<T>(g, tile);
+  const bool stat = static_shell(nfaces, faces) != 0;
+  auto one = [&](T* cur, T* nxt, bool bcs) {
+    bool done = false;
+    if (tma)
+      done = launch_star_tma<T, PW_EULER>(s, g, eq, tile, cur, rhs, nxt, nullptr, (T)dt, nullptr, nullptr, ST_NONE);
+    if (!done)
+      k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, cur, nxt, rhs, (T)dt, nullptr,
+                                                                       nullptr);
+    if (bcs) launch_bcs<T>(L, g, nfaces, faces, nxt, nullptr);
+  };
+  int done_steps = 0;
+  T* cur = a;
+  T* nxt = b;
+  if (nsteps > 0) {  // the first step always applies the BCs
+    one(cur, nxt, true);
+    std::swap(cur, nxt);
+    ++done_steps;
   }
-  if (!done)
-    k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, phi_new, rhs,
-                                                                     (T)dt, nullptr, nullptr);
-  launch_bcs<T>(L, g, nfaces, faces, phi_new, nullptr);
+  const int remaining = nsteps - done_steps;
+  if (remaining >= 4) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    PA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    one(cur, nxt, !stat);
+    one(nxt, cur, !stat);
+    if (cudaStreamEndCapture(s, &graph) != cudaSuccess) return fail(PA_ERR_CUDA, "graph capture failed");
+    PA_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    for (int k = 0; k + 1 < remaining; k += 2) {
+      PA_CUDA(cudaGraphLaunch(gexec, s));
+      done_steps += 2;
+    }
+    PA_CUDA(cudaStreamSynchronize(s));
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
+  }
+  while (done_steps < nsteps) {
+    one(cur, nxt, !stat);
+    std::swap(cur, nxt);
+    ++done_steps;
+  }
+  PA_CUDA(cudaStreamSynchronize(s));
   PA_CUDA(cudaGetLastError());
+  *result_in_b = (cur == b) ? 1 : 0;
   return PA_OK;
 }
+
 extern "C" {
 
 int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
@@ -844,8 +887,21 @@ int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!phi || !phi_new || phi == phi_new) return fail(PA_ERR_ARG, "phi/phi_new null or aliased");
-  PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (const T*)phi, (T*)phi_new,
-                                   (const T*)rhs, dt, (cudaStream_t)stream));
+  int in_b = 0;
+  PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (T*)phi, (T*)phi_new, (const T*)rhs, dt, 1, &in_b,
+                                   (cudaStream_t)stream));
+}
+
+int pa_euler_steps(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                   int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
+                   int* result_in_alt, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!phi || !phi_alt || phi == phi_alt || !result_in_alt || nsteps < 0)
+    return fail(PA_ERR_ARG, "bad argument");
+  PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (T*)phi, (T*)phi_alt, (const T*)rhs, dt, nsteps,
+                                   result_in_alt, (cudaStream_t)stream));
 }
 
 int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,

@@ -151,13 +151,16 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
     if rhs is not None:
         rhs_c = rhs if rhs.is_contiguous() else rhs.contiguous()
         rhs_ptr = rhs_c.data_ptr()
-    cur, nxt = x, torch.empty_like(x)
-    lib, stream = N.lib(), N.current_stream(x.device)
+    import ctypes as C
+
+    alt = torch.empty_like(x)
+    in_alt = C.c_int(0)
+    N.check(N.lib().pa_euler_steps(grid, eq, nfaces, faces, code, x.data_ptr(), alt.data_ptr(), rhs_ptr, dt, n_steps,
+                                   C.byref(in_alt), N.current_stream(x.device)))
     for _ in range(n_steps):
-        N.check(lib.pa_euler_step(grid, eq, nfaces, faces, code, cur.data_ptr(), nxt.data_ptr(), rhs_ptr, dt, stream))
-        cur, nxt = nxt, cur
         var.update_time()
-    var.VAR, var.VARo = cur, nxt
+    if n_steps > 0:
+        var.VAR, var.VARo = (alt, x) if in_alt.value else (x, alt)
     del keep_f, keep_e
     return _write_report(n_steps, 0.0, True)
 
