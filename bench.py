@@ -35,6 +35,11 @@ B_PER_CELL_PHASE_B = 40.0  # R x, R d, R r, W x, W r
 B_PER_CELL_PHASE_A = 24.0  # R r, R d, W d
 
 
+def workload_name(n, iters):
+    return (f"3D Poisson {n}^3 per GPU fp64 matrix-free CG, Dirichlet BCs, {iters} iterations per step "
+            f"(tol=1e-30, max_it={iters - 1}); RHS torch.rand seed 1234+rank")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +168,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GLUP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D Poisson {args.n}^3 fp64 matrix-free CG, Dirichlet BCs (timed on a bounded CPU sample: {sample})"},
+        "config": {"workload": workload_name(args.n, args.iters), "timed_on": f"bounded CPU sample: {sample}"},
         "cpu_baseline": {"value": value, "unit": "GLUP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -222,7 +227,6 @@ def run_ours(args):
     out_h = torch.empty_like(rhs_h).pin_memory()
     rhs_d = torch.zeros(local_shape, dtype=torch.float64, device=dev)
     rhs_d[:, olo:ohi].copy_(rhs_h)
-    rhs_e2e = torch.zeros(local_shape, dtype=torch.float64, device=dev)
     launches = 0
 
     def step_device():
@@ -235,13 +239,46 @@ def run_ours(args):
         launches += solver.var._last_launches if hasattr(solver.var, "_last_launches") else 0
         return var
 
-    def step_e2e():
-        rhs_e2e[:, olo:ohi].copy_(rhs_h, non_blocking=True)  # H2D of this step's input
-        solver, var = new_solver(rhs_e2e)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            solver.solve()
-        out_h.copy_(var()[:, olo:ohi], non_blocking=True)    # D2H of the result
+    # End-to-end: every step's RHS starts in pinned host memory and its solution ends there.  The
+    # copies run on two copy streams so that step k+1's H2D and step k-1's D2H overlap step k's
+    # solve (double-buffered device RHS); all of them are inside the timed region.
+    # (compute runs on its own stream too: torch's default stream is the legacy stream, which
+    # implicitly synchronises with every blocking stream and would serialise the copies.)
+    h2d_s, d2h_s, main_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    rhs_buf = [torch.zeros(local_shape, dtype=torch.float64, device=dev) for _ in range(2)]
+
+    def run_e2e(k_steps):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main_s):
+            _run_e2e(k_steps)
+        torch.cuda.synchronize()
+
+    def _run_e2e(k_steps):
+        keep = []
+        ev_in = [None, None]
+
+        def upload(k):
+            with torch.cuda.stream(h2d_s):
+                rhs_buf[k % 2][:, olo:ohi].copy_(rhs_h, non_blocking=True)
+                ev_in[k % 2] = torch.cuda.Event()
+                ev_in[k % 2].record(h2d_s)
+
+        upload(0)
+        for k in range(k_steps):
+            torch.cuda.current_stream().wait_event(ev_in[k % 2])
+            if k + 1 < k_steps:
+                upload(k + 1)  # overlaps this step's solve
+            solver, var = new_solver(rhs_buf[k % 2])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                solver.solve()  # returns when the device has finished this solve
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(done)
+                out_h.copy_(var()[:, olo:ohi], non_blocking=True)  # overlaps the next solve
+            keep.append(var)
+        torch.cuda.current_stream().wait_stream(d2h_s)
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
@@ -269,12 +306,10 @@ def run_ours(args):
     value = lup_total / (ms * 1e-3) / 1e9
 
     # --- end to end (host buffers) ------------------------------------------------------------
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -307,8 +342,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"3D Poisson {n}^3 per GPU fp64 matrix-free CG, Dirichlet BCs, {iters} iterations per step "
-                        f"(tol=1e-30, max_it={iters - 1}); RHS torch.rand seed 1234+rank",
+            "workload": workload_name(n, iters),
             "global_grid": [n * world, n, n], "decomposition": f"slab x{world} along axis 0",
             "l2_policy": f"working set {8 * 7 * cells / 2**30:.1f} GiB per GPU >> 126 MB L2 (inputs larger than L2)",
             "lup_definition": "grid points x CG iterations",

@@ -29,7 +29,10 @@ class Solver:
         self.var = eq.var
         self.eqs = eq.ops
         self.rhs = eq.rhs
-        if self.rhs is not None:
+        # The adjustment is non-zero only next to Neumann faces (fdc.py:438,523); without any the
+        # reference adds an all-zero tensor, which is skipped here (saves two full passes).
+        has_neumann = any(bc.bc_type == "neumann" for bc in (self.var.bcs or []))
+        if self.rhs is not None and has_neumann:
             for e in self.eqs:
                 fn = self.eqs[e]["adjust_rhs"]
                 if self.eqs[e]["name"] == "Div":
