@@ -115,6 +115,10 @@ typedef struct {
   double dx[3];       /* upwind_fd field div */
   int32_t zero_am_lo[3]; /* periodic edits of the central scheme (fdc.py:596-602) */
   int32_t zero_ap_hi[3];
+  /* optional per-cell coefficient (Laplacian/Grad called with a Tensor, fdm.py:130,169): the
+   * stencil result is multiplied by param_field[cell] instead of `param`.  Same shape/dtype as
+   * the field; NULL = use the scalar. */
+  const void* param_field;
 } pa_op;
 
 /* sum_k sign_k * param_k * Op_k(phi), accumulated in list order (ops.py:130-149) */

@@ -292,14 +292,25 @@ def div_field(adv: Tensor, nx, dx, bcs, limiter: str) -> FieldCoeffs:
     return FieldCoeffs(kind, adv, dx, zl, zh, "Div")
 
 
-def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param: float | None = None) -> tuple[N.Op, Any]:
-    """StarCoeffs / FieldCoeffs -> pa_op."""
+def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=None) -> tuple[N.Op, Any]:
+    """StarCoeffs / FieldCoeffs -> pa_op.  `param` is None, a float, or a Tensor broadcastable to
+    the field (the reference multiplies the stencil result by it elementwise, fdm.py:169)."""
     op = N.Op()
     op.kind = coeffs.kind
     op.sign = float(sign)
+    keep = None
+    pkeep = None
+    if isinstance(param, Tensor):
+        if param.numel() == 1:
+            param = float(param)
+        else:
+            assert field_shape is not None
+            pkeep = torch.broadcast_to(param, field_shape).to(dtype).contiguous()
+            N.require_cuda(pkeep, "operator coefficient tensor")
+            op.param_field = pkeep.data_ptr()
+            param = 1.0
     op.has_param = 0 if param is None else 1
     op.param = 1.0 if param is None else float(param)
-    keep = None
     if isinstance(coeffs, StarCoeffs):
         for j in range(nd):
             a = kernel_axis(j, nd)
@@ -320,4 +331,4 @@ def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param: float | None = No
         for a in range(3):
             op.zero_am_lo[a] = coeffs.zero_am_lo[a]
             op.zero_ap_hi[a] = coeffs.zero_ap_hi[a]
-    return op, keep
+    return op, (keep, pkeep)

@@ -57,6 +57,7 @@ class Op(C.Structure):
         ("dx", C.c_double * 3),
         ("zero_am_lo", C.c_int32 * 3),
         ("zero_ap_hi", C.c_int32 * 3),
+        ("param_field", C.c_void_p),
     ]
 
 

@@ -55,6 +55,7 @@ struct OpDev {
   T dx[3];
   int zero_am_lo[3];
   int zero_ap_hi[3];
+  const T* param_field;
 };
 
 template <typename T>
@@ -83,6 +84,7 @@ inline EqDev<T> make_eq(const pa_equation& e) {
       o.zero_ap_hi[a] = s.zero_ap_hi[a];
     }
     o.adv = (const T*)s.adv;
+    o.param_field = (const T*)s.param_field;
   }
   return d;
 }
@@ -201,7 +203,10 @@ __device__ __forceinline__ T eval_equation(const GridDev& g, const EqDev<T>& eq,
       s = s + Am * vm[a];
       acc = acc + s;  // axes accumulate into zeros (fdc.py:103-108)
     }
-    if (o.has_param) acc = acc * o.param;  // fdm.py:169
+    if (o.param_field != nullptr)
+      acc = acc * o.param_field[c.idx];  // Tensor coefficient (fdm.py:130,169)
+    else if (o.has_param)
+      acc = acc * o.param;  // fdm.py:169
     acc = acc * o.sign;                    // ops.py:140-143
     res = res + acc;                       // ops.py:149
   }

@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(kBlock) k_grad(GridDev g, OpDev<T> o, const T*
       T s = o.coef[a][cls][0] * vp;
       s = s + o.coef[a][cls][1] * vc;
       s = s + o.coef[a][cls][2] * vm;
-      if (o.has_param) s = s * o.param;
+      if (o.param_field != nullptr)
+        s = s * o.param_field[idx];
+      else if (o.has_param)
+        s = s * o.param;
       out[(long long)comp * g.cells + idx] = s;
       ++comp;
     }
@@ -640,7 +643,10 @@ __device__ __forceinline__ T eq_diag(const GridDev& g, const EqDev<T>& eq, const
       }
       acc = acc + Ac;
     }
-    if (o.has_param) acc = acc * o.param;
+    if (o.param_field != nullptr)
+      acc = acc * o.param_field[c.idx];
+    else if (o.has_param)
+      acc = acc * o.param;
     acc = acc * o.sign;
     res = res + acc;
   }

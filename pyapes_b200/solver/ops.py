@@ -104,11 +104,6 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field):
         param = None
         if name in ("laplacian", "grad"):
             param = e["param"][0]
-            if isinstance(param, Tensor):
-                raise NotImplementedError(
-                    "pyapes_b200: a Tensor-valued operator coefficient is not on the CUDA path "
-                    "(SURVEY.md §8(b) fallback rule)"
-                )
             if name == "grad" and nd != 1:
                 # the reference's `Ax.view(target.size)` fails for mesh.dim > 1 (ops.py:145-147)
                 raise RuntimeError(
@@ -124,7 +119,7 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field):
                 from pyapes_b200.solver.fdc import FDC
 
                 coeffs = FDC(cfg).div.build_A_coeffs(var_j, target, cfg)  # live field (fdm.py:309-312)
-        op, kp = L.lower_op(coeffs, nd, dtype, sign=float(e["sign"]), param=param)
+        op, kp = L.lower_op(coeffs, nd, dtype, sign=float(e["sign"]), param=param, field_shape=target().shape)
         eq.ops[k] = op
         keep.append(kp)
         k += 1

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
 
     assert C.sizeof(N.FaceBC) == 32
     assert C.sizeof(N.Grid) == 60
-    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12
+    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8
     assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
     assert C.sizeof(N.Report) == 24 and C.sizeof(N.SolverCfg) == 24
 

@@ -28,12 +28,13 @@ def timed(fn, reps=3):
     return best
 
 
-def solver_case(name, shape, method, bcs, iters, words, variant=0):
+def solver_case(name, shape, method, bcs, iters, words, variant=0, dtype="double"):
     nd = len(shape)
-    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, "cuda")
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, "cuda", dtype)
+    esz = 8 if dtype == "double" else 4
     kinds, vals = bcs
     g = torch.Generator().manual_seed(1234)
-    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64).cuda()
+    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64).to(mesh.dtype.float).cuda()
     max_it = iters - 1 if method in ("cg", "jacobi") else iters
 
     def run():
@@ -48,7 +49,7 @@ def solver_case(name, shape, method, bcs, iters, words, variant=0):
     for v in shape: n *= v
     glups = n * iters / (ms * 1e-3) / 1e9
     return {"case": name, "shape": shape, "method": method, "iters": iters, "ms": ms, "GLUP/s": round(glups, 2),
-            "words_per_LUP": words, "hbm_frac": round(glups * 1e9 * words * 8 / HBM, 3), "variant": variant}
+            "dtype": dtype, "words_per_LUP": words, "hbm_frac": round(glups * 1e9 * words * esz / HBM, 3), "variant": variant}
 
 
 def euler_case(name, shape, limiter, steps):
@@ -79,6 +80,9 @@ out.append(solver_case(f"config4 Jacobi {N3}^3 mixed", [N3] * 3, "jacobi", MIXED
 out.append(solver_case(f"Jacobi {N3}^3 Dirichlet", [N3] * 3, "jacobi", D6, 50, 3))
 out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet", [N3] * 3, "bicgstab", D6, 20, 17))
 out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet generic", [N3] * 3, "bicgstab", D6, 20, 17, variant=1))
+out.append(solver_case("CG 512^3 Dirichlet fp32", [512] * 3, "cg", D6, 50, 8, dtype="single"))
+out.append(solver_case("CG 1024^2 Dirichlet (2-D)", [1024, 1024], "cg", (["dirichlet"] * 4, [0.0] * 4), 200, 8))
+torch.set_default_dtype(torch.float64)
 out.append(euler_case("config3 Euler 256^3 upwind", [256] * 3, "upwind", 100))
 out.append(euler_case("config3 Euler 256^3 upwind_fd", [256] * 3, "upwind_fd", 100))
 out.append(euler_case("config3 Euler 1024^2 upwind", [1024, 1024], "upwind", 100))
