@@ -119,6 +119,14 @@ typedef struct {
    * stencil result is multiplied by param_field[cell] instead of `param`.  Same shape/dtype as
    * the field; NULL = use the scalar. */
   const void* param_field;
+  /* edge=True of the explicit FDC operators (fdc.py:203-366): one-sided differences on the domain
+   * faces.  0 none; 1 Laplacian (the face cell's value is REPLACED by the one-sided second
+   * derivative along the face's axis, later axes win); 2 Div on a 1-D mesh (the reference raises
+   * IndexError for dim > 1), scaled by adv_const; for pa_grad_apply any non-zero value replaces
+   * component a on the faces normal to axis a.  Uses dx[]. */
+  int32_t edge;
+  int32_t reserved;
+  double adv_const;
 } pa_op;
 
 /* sum_k sign_k * param_k * Op_k(phi), accumulated in list order (ops.py:130-149) */

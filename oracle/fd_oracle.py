@@ -289,6 +289,75 @@ def apply_grad(coeffs, phi: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------------------------
+# edge=True: one-sided differences on the domain faces (fdc.py:203-366, xyz branches)
+# ---------------------------------------------------------------------------------------
+def _edge_planes(nd: int, axis: int, lower: bool):
+    idx = (0, 1, 2, 3) if lower else (-1, -2, -3, -4)
+    return [_plane(nd, axis, i) for i in idx]
+
+
+def edge_laplacian(out: Tensor, phi: Tensor, dx: list[float]) -> Tensor:
+    """fdc.py:223-258.  NOTE the reference REPLACES the whole Laplacian on a face cell by the
+    one-sided second derivative along that face's axis; later axes overwrite shared edges."""
+    nd = phi.dim() - 1
+    dxt = torch.tensor(dx, dtype=phi.dtype)
+    v = phi[0]
+    for a in range(nd):
+        for lower in (True, False):
+            p0, p1, p2, p3 = _edge_planes(nd, a, lower)
+            out[0][p0] = (2.0 * v[p0] - 5.0 * v[p1] + 4.0 * v[p2] - v[p3]) / (dxt[a] ** 2)
+    return out
+
+
+def edge_grad(out: Tensor, phi: Tensor, dx: list[float]) -> Tensor:
+    """fdc.py:260-288: component `a` on the faces normal to axis `a`."""
+    nd = phi.dim() - 1
+    dxt = torch.tensor(dx, dtype=phi.dtype)
+    v = phi[0]
+    for a in range(nd):
+        p0, p1, p2, _ = _edge_planes(nd, a, True)
+        out[0][a][p0] = -(3 / 2 * v[p0] - 2.0 * v[p1] + 1 / 2 * v[p2]) / (dxt[a])
+        p0, p1, p2, _ = _edge_planes(nd, a, False)
+        out[0][a][p0] = (3 / 2 * v[p0] - 2.0 * v[p1] + 1 / 2 * v[p2]) / (dxt[a])
+    return out
+
+
+def apply_div_edge(coeffs, phi: Tensor, dx: list[float], u: float) -> Tensor:
+    """fdc.py:93-102 with 290-348: each axis' term is replaced on that axis' faces before the
+    axes are summed (constant advection speed)."""
+    nd = phi.dim() - 1
+    dxt = torch.tensor(dx, dtype=phi.dtype)
+    v = phi[0]
+    adv = torch.ones_like(v) * u
+    out = torch.zeros_like(phi)
+    for a in range(nd):
+        disc = _axis_sum(coeffs, phi, a)
+        p0, p1, p2, _ = _edge_planes(nd, a, True)
+        disc[p0] = -(3 / 2 * v[p0] - 2.0 * v[p1] + 1 / 2 * v[p2]) / (dxt[a]) * adv[p0]
+        p0, p1, p2, _ = _edge_planes(nd, a, False)
+        disc[p0] = (3 / 2 * v[p0] - 2.0 * v[p1] + 1 / 2 * v[p2]) / (dxt[a]) * adv[p0]
+        out[0] += disc
+    return out
+
+
+def jacobian(phi: Tensor, dx: list[float]) -> list[Tensor]:
+    """fdc.py:896-914: edge=True central gradient of a BC-less container field."""
+    return list(edge_grad(apply_grad(grad_coeffs(phi, dx, []), phi), phi, dx)[0])
+
+
+def hessian(phi: Tensor, dx: list[float]) -> dict[tuple[int, int], Tensor]:
+    """fdc.py:917-944: gradient of every Jacobian component, upper triangle kept."""
+    jac = jacobian(phi, dx)
+    out = {}
+    for i, j in enumerate(jac):
+        hi = jacobian(j.unsqueeze(0).clone(), dx)
+        for k, h in enumerate(hi):
+            if i <= k:
+                out[(i, k)] = h
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # rhs adjustment (fdc.py:425-458, 505-540, 666-694)
 # ---------------------------------------------------------------------------------------
 def laplacian_rhs_adjust(phi, dx, bcs):

@@ -13,7 +13,7 @@ def install_as_pyapes() -> None:
     import sys
 
     names = ["", ".backend", ".geometry", ".geometry.basis", ".geometry.box", ".geometry.cylinder",
-             ".mesh", ".mesh._mesh", ".mesh.tools", ".variables", ".variables.bcs", ".variables.fields",
+             ".mesh", ".mesh._mesh", ".mesh.tools", ".variables", ".variables.bcs", ".variables.fields", ".variables.container",
              ".solver", ".solver.tools", ".solver.types", ".solver.fdc", ".solver.fdm", ".solver.linalg",
              ".solver.ops", ".testing", ".testing.poisson"]
     for n in names:

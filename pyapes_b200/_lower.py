@@ -292,7 +292,8 @@ def div_field(adv: Tensor, nx, dx, bcs, limiter: str) -> FieldCoeffs:
     return FieldCoeffs(kind, adv, dx, zl, zh, "Div")
 
 
-def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=None) -> tuple[N.Op, Any]:
+def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=None, edge: int = 0,
+             dx=None, adv_const: float = 0.0) -> tuple[N.Op, Any]:
     """StarCoeffs / FieldCoeffs -> pa_op.  `param` is None, a float, or a Tensor broadcastable to
     the field (the reference multiplies the stencil result by it elementwise, fdm.py:169)."""
     op = N.Op()
@@ -311,6 +312,12 @@ def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=
             param = 1.0
     op.has_param = 0 if param is None else 1
     op.param = 1.0 if param is None else float(param)
+    op.edge = int(edge)
+    op.adv_const = float(torch.ones(1, dtype=dtype)[0] * adv_const)
+    if dx is not None:
+        dxt0 = torch.tensor(dx, dtype=dtype)
+        for j in range(nd):
+            op.dx[kernel_axis(j, nd)] = float(dxt0[j])
     if isinstance(coeffs, StarCoeffs):
         for j in range(nd):
             a = kernel_axis(j, nd)

@@ -58,6 +58,9 @@ class Op(C.Structure):
         ("zero_am_lo", C.c_int32 * 3),
         ("zero_ap_hi", C.c_int32 * 3),
         ("param_field", C.c_void_p),
+        ("edge", C.c_int32),
+        ("reserved", C.c_int32),
+        ("adv_const", C.c_double),
     ]
 
 

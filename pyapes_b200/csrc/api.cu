@@ -55,6 +55,8 @@ static int check_eq(const pa_equation* eq) {
       return fail(PA_ERR_ARG, "unknown operator kind");
     if (kind != PA_OP_STAR && eq->ops[k].adv == nullptr)
       return fail(PA_ERR_ARG, "field-advection operator without adv pointer");
+    if (eq->ops[k].edge != 0 && eq->nops != 1)
+      return fail(PA_ERR_ARG, "edge=True is an option of the explicit single-operator calls");
   }
   return PA_OK;
 }

@@ -56,6 +56,8 @@ struct OpDev {
   int zero_am_lo[3];
   int zero_ap_hi[3];
   const T* param_field;
+  int edge;
+  T adv_const;
 };
 
 template <typename T>
@@ -85,6 +87,8 @@ inline EqDev<T> make_eq(const pa_equation& e) {
     }
     o.adv = (const T*)s.adv;
     o.param_field = (const T*)s.param_field;
+    o.edge = s.edge;
+    o.adv_const = (T)s.adv_const;
   }
   return d;
 }

@@ -174,13 +174,51 @@ struct StoreSums {
 // ---------------------------------------------------------------------------------------
 // operator application on every cell (roll semantics) — ops._Aop
 // ---------------------------------------------------------------------------------------
+// one-sided first difference along axis a at a face cell: (3/2 v0 - 2 v1 + 1/2 v2)
+// (fdc.py:270-284); `dir` = +1 on the lower face (neighbours at +1,+2), -1 on the upper face
+template <typename T>
+__device__ __forceinline__ T edge_first(const T* __restrict__ phi, long long idx, long long st, int dir) {
+  T t = (T)1.5 * phi[idx];
+  t = t - (T)2 * phi[idx + dir * st];
+  t = t + (T)0.5 * phi[idx + 2 * dir * st];
+  return t;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_apply(GridDev g, EqDev<T> eq, const T* __restrict__ phi,
                                                   T* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.cells;
        idx += (long long)gridDim.x * blockDim.x) {
     Cell c = decode(g, idx);
-    out[idx] = eval_equation<T>(g, eq, c, [&](long long j) { return phi[j]; });
+    T val = eval_equation<T>(g, eq, c, [&](long long j) { return phi[j]; });
+    const OpDev<T>& o = eq.op[0];
+    if (o.edge == 1) {
+      // edge=True Laplacian (fdc.py:223-258): replace by the one-sided second derivative along
+      // the face's axis; axes in order, so the last axis wins on shared edges
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (!g.act[a]) continue;
+        const int i = c.i[a], n = g.n[a];
+        if (i != 0 && i != n - 1) continue;
+        const long long st = stride_of(g, a) * (i == 0 ? 1 : -1);
+        T t = (T)2 * phi[idx];
+        t = t - (T)5 * phi[idx + st];
+        t = t + (T)4 * phi[idx + 2 * st];
+        t = t - phi[idx + 3 * st];
+        val = t / (o.dx[a] * o.dx[a]);
+      }
+    } else if (o.edge == 2) {
+      // edge=True Div on a 1-D mesh (fdc.py:290-348): the only active axis is kernel axis 2
+      const int i = c.i[2], n = g.n[2];
+      if (i == 0) {
+        T t = -edge_first<T>(phi, idx, 1, 1);
+        val = t / o.dx[2] * o.adv_const;
+      } else if (i == n - 1) {
+        T t = edge_first<T>(phi, idx, 1, -1);
+        val = t / o.dx[2] * o.adv_const;
+      }
+    }
+    out[idx] = val;
   }
 }
 
@@ -204,6 +242,12 @@ __global__ void __launch_bounds__(kBlock) k_grad(GridDev g, OpDev<T> o, const T*
       T s = o.coef[a][cls][0] * vp;
       s = s + o.coef[a][cls][1] * vc;
       s = s + o.coef[a][cls][2] * vm;
+      if (o.edge) {  // edge=True Grad (fdc.py:260-288)
+        if (i == 0)
+          s = -edge_first<T>(phi, idx, st, 1) / o.dx[a];
+        else if (i == n - 1)
+          s = edge_first<T>(phi, idx, st, -1) / o.dx[a];
+      }
       if (o.param_field != nullptr)
         s = s * o.param_field[idx];
       else if (o.has_param)

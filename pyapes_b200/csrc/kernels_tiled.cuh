@@ -97,7 +97,7 @@ inline bool plan_tiles(const GridDev& g, const pa_equation& eq, TilePlan& p) {
 template <typename T, int RY>
 inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, int slots) {
   typedef TileCfg<T, RY> C;
-  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr) return false;
+  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0) return false;
   if (!g.act[1] || !g.act[2]) return false;  // 1-D meshes stay on the generic kernels
   if (g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;

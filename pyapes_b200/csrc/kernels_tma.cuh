@@ -141,7 +141,7 @@ template <typename T>
 inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
                      const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
   typedef TmaCfg<T, kTmaRY> C;
-  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr) return false;
+  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0) return false;
   if (!g.act[1] || !g.act[2]) return false;
   if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box

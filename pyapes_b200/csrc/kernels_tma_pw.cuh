@@ -313,7 +313,7 @@ inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, con
   typedef PwCfg<T, kTmaRY> C;
   if (eq.nops < 1 || eq.nops > PA_MAX_OPS) return false;
   for (int k = 0; k < eq.nops; ++k)
-    if (eq.ops[k].kind != PA_OP_STAR || eq.ops[k].param_field != nullptr) return false;
+    if (eq.ops[k].kind != PA_OP_STAR || eq.ops[k].param_field != nullptr || eq.ops[k].edge != 0) return false;
   if (!g.act[1] || !g.act[2]) return false;
   if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   for (int f = 0; f < nfaces; ++f)

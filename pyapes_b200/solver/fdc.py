@@ -97,18 +97,33 @@ class Discretizer:
     def apply(self, A_coeffs, var: Field) -> Tensor:
         """The stencil (fdc.py:67-118) as one kernel launch."""
         assert A_coeffs is not None, "FDC: A_A_coeffs is not defined!"
-        if self._edge():
-            raise NotImplementedError(
-                "pyapes_b200: edge=True one-sided boundary stencils are not built yet (SURVEY.md §8(f) item 1)"
-            )
+        edge = self._edge()
         _scalar_field(var, f"FDC.{self.op_type}")
+        edge_code, adv_const = 0, 0.0
+        if edge:
+            # one-sided differences on the domain faces (fdc.py:203-366)
+            need = 4 if self.op_type == "Laplacian" else 3
+            if min(var.nx) < need:
+                raise IndexError(f"FDC {self.op_type}: edge=True needs at least {need} points per axis")
+            if self.op_type == "Div":
+                if var.mesh.dim > 1:
+                    # the reference indexes var[dim] on a scalar field here (fdc.py:303-307)
+                    raise IndexError("index 1 is out of bounds for dimension 0 with size 1")
+                adv = getattr(self, "var_addition", None)
+                if adv is None:
+                    adv = 1.0
+                if not isinstance(adv, (float, int)):
+                    raise NotImplementedError("pyapes_b200: edge=True Div needs a constant advection speed")
+                edge_code, adv_const = 2, float(adv)
+            else:
+                edge_code = 1
         phi = var()
         N.require_cuda(phi, "field")
         nd = var.mesh.dim
         if getattr(var.mesh, "slab", None) is not None:
             raise NotImplementedError("pyapes_b200: explicit FDC operators on a slab-decomposed mesh are not built yet")
         grid = L.lower_grid(var.nx, var.bcs)
-        op, keep = L.lower_op(A_coeffs, nd, phi.dtype)
+        op, keep = L.lower_op(A_coeffs, nd, phi.dtype, edge=edge_code, dx=var.mesh._dx, adv_const=adv_const)
         code, stream = N.dtype_code(phi.dtype), N.current_stream(phi.device)
         if self.op_type == "Grad":
             out = torch.empty((1, nd, *var.nx), dtype=phi.dtype, device=phi.device)
@@ -248,8 +263,22 @@ class Div(Discretizer):
 
 
 class DiffFlux:
-    def __call__(self, *_):
-        raise NotImplementedError("pyapes_b200: DiffFlux is out of the hot-path scope (SURVEY.md §8(f) item 1)")
+    """Diffusive flux `D_ij d(phi)/dx_j` of a scalar field (fdc.py:820-857): a vector Field built
+    from the edge=True Jacobian and a Hess container of diffusion coefficients."""
+
+    @staticmethod
+    def __call__(diff, var: Field) -> Field:
+        from pyapes_b200.geometry.basis import n2d_coord
+
+        jac = jacobian(var)
+        flux = Field("DiffFlux", len(jac), var.mesh, None)
+        n2d = n2d_coord(var.mesh.coord_sys)
+        for i in range(var.mesh.dim):
+            acc = torch.zeros_like(var()[0])
+            for j in range(var.mesh.dim):
+                acc += diff[n2d[i] + n2d[j]] * jac[n2d[j]]
+            flux.set_var_tensor(acc, i)
+        return flux
 
 
 class FDC:
@@ -280,9 +309,40 @@ class FDC:
                 s.set_config(self.config)
 
 
+def _edge_gradient(mesh, phi0: Tensor) -> Tensor:
+    """edge=True central gradient of a BC-less container field (fdc.py:904-907): `(mesh.dim, *nx)`."""
+    box = Field("container", 1, mesh, None)
+    box.set_var_tensor(phi0)
+    fdc = FDC({"grad": {"edge": True}})
+    out = fdc.grad(box)[0]
+    fdc.grad.reset()
+    FDC({"grad": {"edge": False}})
+    return out
+
+
 def jacobian(var: Field):
-    raise NotImplementedError("pyapes_b200: jacobian() needs edge=True stencils (SURVEY.md §8(f) item 1)")
+    """Jacobian of a scalar field as a `Jac` container (fdc.py:896-914)."""
+    from pyapes_b200.geometry.basis import n2d_coord
+    from pyapes_b200.variables.container import Jac
+
+    assert var().shape[0] == 1, "Scalar: var must be a scalar field."
+    n2d = n2d_coord(var.mesh.coord_sys)
+    g = _edge_gradient(var.mesh, var[0])
+    return Jac(**{n2d[i]: g[i] for i in range(var.mesh.dim)})
 
 
 def hessian(var: Field):
-    raise NotImplementedError("pyapes_b200: hessian() needs edge=True stencils (SURVEY.md §8(f) item 1)")
+    """Hessian as a `Hess` container (upper triangle), gradient of every Jacobian component
+    (fdc.py:917-944)."""
+    from pyapes_b200.geometry.basis import n2d_coord
+    from pyapes_b200.variables.container import Hess
+
+    n2d = n2d_coord(var.mesh.coord_sys)
+    d = var.mesh.dim
+    g = _edge_gradient(var.mesh, var[0])
+    data = {}
+    for i in range(d):
+        gi = _edge_gradient(var.mesh, g[i].contiguous())
+        for j in range(i, d):
+            data[n2d[i] + n2d[j]] = gi[j]
+    return Hess(**data)

@@ -139,6 +139,39 @@ def op_case(name, spec, seed=7, u_const=0.7):
     }
 
 
+def edge_case(name, spec, seed=11, u_const=0.6):
+    """edge=True explicit operators + jacobian / hessian (fdc.py:203-366, 896-944)."""
+    from pyapes.solver.fdc import hessian, jacobian
+
+    mesh, var = build(spec)
+    phi = rand_like(var, seed) - 0.5
+    var.set_var_tensor(phi.clone())
+    out = {}
+    out["lap_edge"] = FDC({"laplacian": {"edge": True}}).laplacian(var).clone()
+    out["grad_edge"] = FDC({"grad": {"edge": True}}).grad(var).clone()
+    has_ns = any(k in ("neumann", "symmetry") for k, _ in spec["bcs"])
+    if mesh.dim == 1:
+        # in >1-D the reference's Div edge treatment raises IndexError (fdc.py:303 indexes var[dim])
+        out["div_upwind_edge"] = FDC({"div": {"limiter": "upwind", "edge": True}}).div(u_const, var).clone()
+        if not has_ns:
+            out["div_central_edge"] = FDC({"div": {"limiter": "none", "edge": True}}).div(u_const, var).clone()
+    else:
+        try:
+            FDC({"div": {"limiter": "upwind", "edge": True}}).div(u_const, var)
+            out["div_edge_raises"] = False
+        except IndexError:
+            out["div_edge_raises"] = True
+    jac = jacobian(var)
+    for k in jac.keys:
+        out["jac_" + k] = jac[k].clone()
+    hess = hessian(var)
+    for k in hess.keys:
+        out["hess_" + k] = hess[k].clone()
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+    return {"name": name, "spec": spec, "bcs": frozen_bcs(mesh, var), "dx": [float(d) for d in mesh._dx],
+            "phi": phi, "u_const": u_const, "out": out}
+
+
 def solver_case(name, spec, terms, rhs_kind, method, tol, max_it, init=0.0, div_cfg=None,
                 keep_solution=True, _second_pass=True, _perturb=0):
     """terms: [(kind, sign, param)], rhs_kind: float | ("rand", seed) | "poisson_nd" | tensor-fn"""
@@ -268,6 +301,22 @@ def main():
     torch.set_default_dtype(torch.float64)
     torch.save(ops, os.path.join(HERE, "ops.pt"))
 
+    print("edge fixtures")
+    edges = []
+    for dt in ("double", "single"):
+        tag = "f64" if dt == "double" else "f32"
+        edges += [
+            edge_case(f"edge_3d_dirichlet_{tag}", dspec([0, 0, 0], [1, 1, 2], [6, 5, 7], [("dirichlet", 0.3)] * 6, dt)),
+            edge_case(f"edge_3d_mixed_{tag}", dspec([0, 0, 0], [1, 2, 1.5], [7, 6, 8], mixed3, dt)),
+            edge_case(f"edge_2d_{tag}", dspec([0, 0], [1, 0.5], [9, 8],
+                                            [("neumann", 0.0), ("dirichlet", 0.0), ("dirichlet", 1.0), ("dirichlet", 1.0)], dt)),
+            edge_case(f"edge_1d_{tag}", dspec([0], [1], [12], [("dirichlet", 0.0), ("neumann", 0.5)], dt)),
+            edge_case(f"edge_1d_periodic_{tag}", dspec([0], [2], [9], [("periodic", None), ("periodic", None)], dt)),
+        ]
+    torch.set_default_dtype(torch.float64)
+    torch.save(edges, os.path.join(HERE, "edges.pt"))
+    print(f"  {len(edges)} edge cases")
+
     print("solver fixtures")
     L1 = [("laplacian", 1.0, 1.0)]
     sol = []
@@ -352,7 +401,7 @@ def main():
                            L1, ("rand", 1234), "bicgstab", 1e-4, 1000))
     torch.set_default_dtype(torch.float64)
     torch.save(sol, os.path.join(HERE, "solvers.pt"))
-    for f in ("ops.pt", "solvers.pt"):
+    for f in ("ops.pt", "edges.pt", "solvers.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) / 1e6, "MB")
 
 

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
 
     assert C.sizeof(N.FaceBC) == 32
     assert C.sizeof(N.Grid) == 60
-    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8
+    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8 + 4 + 4 + 8
     assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
     assert C.sizeof(N.Report) == 24 and C.sizeof(N.SolverCfg) == 24
 
@@ -105,3 +105,23 @@ def test_dsl_semantics_match_reference():
         from pyapes_b200.geometry import Cylinder
 
         Mesh(Cylinder[0:1, 0:1], None, [5, 5], "cpu")
+
+
+def test_derivative_containers():
+    """tests/test_spatial.py:81-128 of the reference."""
+    from pyapes_b200.variables.container import Hess, Jac
+
+    x, y, z = torch.rand(10), torch.rand(10), torch.rand(10)
+    j = Jac(x=x)
+    assert len(j) == 1 and j.keys == ["x"]
+    j = Jac(x=x, y=y, z=z)
+    assert len(j) == 3 and all(torch.equal(a, b) for a, b in zip(j, [x, y, z]))
+    j = Jac(r=x, z=y)
+    assert len(j) == 2 and sorted(j.keys) == ["r", "z"]
+    h = Hess(xx=x, yy=y)
+    assert len(h) == 2 and all(torch.equal(a, b) for a, b in zip(h, [x, y]))
+    h = Hess(xx=x, xy=x, xz=x, yy=y, yz=y, zz=z)
+    assert all(torch.equal(a, b) for a, b in zip(h, [x, x, x, y, y, z]))
+    assert h["zx"] is h.xz
+    with pytest.raises(KeyError):
+        Hess(rr=x, zz=z)["xx"]

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
+EDGES = U.load("edges.pt")
 DEV = "cuda"
 
 
@@ -94,6 +95,74 @@ def test_operator_fixtures_bit_exact(case):
     for bc in var.bcs:
         bc.apply(x, mesh.grid, 0)
     same(x, "bc_applied")
+
+
+@pytest.mark.parametrize("case", EDGES, ids=[c["name"] for c in EDGES])
+def test_edge_fixtures_bit_exact(case):
+    """edge=True one-sided stencils, jacobian, hessian against the real
+    reference's outputs."""
+    from pyapes_b200.solver.fdc import FDC, hessian, jacobian
+
+    mesh, var = U.product_field(case, DEV)
+    var.set_var_tensor(case["phi"].to(DEV).clone())
+    out = case["out"]
+
+    def same(got, key):
+        assert torch.equal(got.cpu(), out[key]), f"{key}: {(got.cpu() - out[key]).abs().max().item():.3e}"
+
+    same(FDC({"laplacian": {"edge": True}}).laplacian(var), "lap_edge")
+    same(FDC({"grad": {"edge": True}}).grad(var), "grad_edge")
+    if mesh.dim == 1:
+        same(FDC({"div": {"limiter": "upwind", "edge": True}}).div(case["u_const"], var), "div_upwind_edge")
+        if "div_central_edge" in out:
+            same(FDC({"div": {"limiter": "none", "edge": True}}).div(case["u_const"], var), "div_central_edge")
+    else:
+        with pytest.raises(IndexError):
+            FDC({"div": {"limiter": "upwind", "edge": True}}).div(case["u_const"], var)
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+    jac = jacobian(var)
+    for k in jac.keys:
+        same(jac[k], "jac_" + k)
+    hess = hessian(var)
+    assert sorted(hess.keys) == sorted(k[5:] for k in out if k.startswith("hess_"))
+    for k in hess.keys:
+        same(hess[k], "hess_" + k)
+
+
+def test_jac_hess_diffflux_like_reference_tests():
+    """tests/test_spatial.py:15-78 of the reference (cartesian parts), on the GPU."""
+    from torch.testing import assert_close
+
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdc import DiffFlux, hessian, jacobian
+    from pyapes_b200.variables import Field
+
+    mesh = Mesh(Box[0:1, 0:1, 0:1], None, [3, 3, 3], DEV)
+    var = Field("test", 1, mesh, {"domain": None, "obstacle": None})
+    var.set_var_tensor(mesh.grid[0] ** 2 + 2 * mesh.grid[2] ** 2)
+    jac = jacobian(var)
+    assert_close(jac.x, 2 * mesh.grid[0])
+    assert_close(jac.y, torch.zeros_like(var()[0]))
+    assert_close(jac.z, 4 * mesh.grid[2])
+    grad = torch.gradient(var()[0], spacing=mesh.dx.tolist(), edge_order=2)
+    hess = hessian(var)
+    flux = DiffFlux()(hess, var)
+    assert_close(flux[0], hess.xx * grad[0] + hess.xy * grad[1] + hess.xz * grad[2])
+    var.set_var_tensor((mesh.grid[0] ** 2) * (mesh.grid[2] ** 2))
+    hess = hessian(var)
+    assert_close(hess.xx, 2 * mesh.grid[2] ** 2)
+    assert_close(hess.xy, torch.zeros_like(var()[0]))
+    assert_close(hess.xz, 4 * mesh.grid[0] * mesh.grid[2])
+    mesh = Mesh(Box[0:1, 0:1], None, [3, 3], DEV)
+    var = Field("test", 1, mesh, {"domain": None, "obstacle": None})
+    var.set_var_tensor(mesh.grid[0] ** 2)
+    jac, hess = jacobian(var), hessian(var)
+    assert_close(hess.xy, hess["yx"])
+    with pytest.raises(KeyError):
+        jac["z"]
+    with pytest.raises(KeyError):
+        hess["zz"]
 
 
 def _run_solver_case(case, **extra):

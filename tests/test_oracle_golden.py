@@ -11,6 +11,7 @@ from tests import _util as U
 
 OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
+EDGES = U.load("edges.pt")
 
 
 @pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
@@ -64,6 +65,35 @@ def test_operator_fixtures(case):
     x = phi.clone()
     O.apply_bcs(x, xs, bcs)
     assert torch.equal(x, out["bc_applied"])
+
+
+@pytest.mark.parametrize("case", EDGES, ids=[c["name"] for c in EDGES])
+def test_edge_fixtures(case):
+    """edge=True one-sided boundary stencils, jacobian, hessian (fdc.py:203-366, 896-944)."""
+    dtype = U.TDTYPE[case["spec"]["dtype"]]
+    torch.set_default_dtype(dtype)
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    phi, out = case["phi"].clone(), case["out"]
+    nd = phi.dim() - 1
+    lap = O.edge_laplacian(O.apply_scalar_op(O.laplacian_coeffs(phi, dx, bcs), phi), phi, dx)
+    assert torch.equal(lap, out["lap_edge"])
+    grad = O.edge_grad(O.apply_grad(O.grad_coeffs(phi, dx, bcs), phi), phi, dx)
+    assert torch.equal(grad, out["grad_edge"])
+    if nd == 1:
+        got = O.apply_div_edge(O.div_coeffs(case["u_const"], phi, dx, bcs, "upwind"), phi, dx, case["u_const"])
+        assert torch.equal(got, out["div_upwind_edge"])
+        if "div_central_edge" in out:
+            got = O.apply_div_edge(O.div_coeffs(case["u_const"], phi, dx, bcs, "none"), phi, dx, case["u_const"])
+            assert torch.equal(got, out["div_central_edge"])
+    else:
+        assert out["div_edge_raises"]
+    names = "xyz"
+    jac = O.jacobian(phi, dx)
+    for a, j in enumerate(jac):
+        assert torch.equal(j, out["jac_" + names[a]])
+    for (a, b), h in O.hessian(phi, dx).items():
+        assert torch.equal(h, out["hess_" + names[a] + names[b]])
 
 
 @pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
