@@ -127,6 +127,11 @@ typedef struct {
   int32_t edge;
   int32_t reserved;
   double adv_const;
+  /* optional per-index coefficient tables: coef_tab[axis] points to n[axis]*3 device values
+   * [Ap, Ac, Am] per index along that kernel axis, used instead of coef[axis][cls][] — the
+   * axisymmetric (rz) operators, whose r-axis coefficients carry 1 +- dr/(2r)
+   * (tools.py:64-108).  NULL = use the three classes. */
+  const void* coef_tab[3];
 } pa_op;
 
 /* sum_k sign_k * param_k * Op_k(phi), accumulated in list order (ops.py:130-149) */

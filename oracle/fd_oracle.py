@@ -32,6 +32,7 @@ import torch
 from torch import Tensor
 
 AXIS_OF = {"x": 0, "y": 1, "z": 2}
+AXIS_OF_RZ = {"r": 0, "z": 1}  # geometry/basis.py:10
 FACES = ["xl", "xu", "yl", "yu", "zl", "zu"]  # geometry/basis.py:16
 
 
@@ -43,10 +44,11 @@ class FaceBC:
     face: str
     kind: str  # dirichlet | neumann | symmetry | periodic
     value: Any = None
+    rz: bool = False
 
     @property
-    def axis(self) -> int:  # bcs.py:72-75
-        return AXIS_OF[self.face[0]]
+    def axis(self) -> int:  # bcs.py:72-75 (an "r" face only exists on rz meshes; their "z" is axis 1)
+        return AXIS_OF[self.face[0]] if not self.rz else AXIS_OF_RZ[self.face[0]]
 
     @property
     def side(self) -> int:  # bcs.py:77-80  (-1 lower, +1 upper)
@@ -151,11 +153,23 @@ def _defaults(phi: Tensor, ap: float, ac: float, am: float):
     return z(), f(ap), f(ac), f(am), z()
 
 
-def laplacian_coeffs(phi: Tensor, dx: list[float], bcs: list[FaceBC]):
-    """fdc.py:375-423 (xyz branch)."""
+def _rz_grid(phi: Tensor, xs: list[Tensor]):
+    """meshgrid of the (r, z) node coordinates, as Mesh.grid (mesh/_mesh.py:95)."""
+    return torch.meshgrid(xs, indexing="ij")
+
+
+def laplacian_coeffs(phi: Tensor, dx: list[float], bcs: list[FaceBC], rz_xs: list[Tensor] | None = None):
+    """fdc.py:375-423; `rz_xs` (node coordinates) switches on the axisymmetric branches
+    (tools.py:86-108, fdc.py:395-403): the r-axis coefficients carry 1 +- dr/(2r)."""
     App, Ap, Ac, Am, Amm = _defaults(phi, 1.0, -2.0, 1.0)
     nd = phi.dim() - 1
     dxt = torch.tensor(dx, dtype=phi.dtype)
+    grid = None
+    if rz_xs is not None:
+        grid = _rz_grid(phi, rz_xs)
+        scale = torch.nan_to_num(dxt[0] / (2 * grid[0]), nan=0.0, posinf=0.0, neginf=0.0)
+        Ap[0] = (1 + scale) * torch.ones_like(phi)
+        Am[0] = (1 - scale) * torch.ones_like(phi)
     for j in range(nd):
         n = phi.shape[1 + j]
         for bc in bcs:
@@ -164,6 +178,9 @@ def laplacian_coeffs(phi: Tensor, dx: list[float], bcs: list[FaceBC]):
             if bc.kind in ("neumann", "symmetry"):
                 pl = _plane(nd, j, _face_idx(bc, n, 1))
                 alpha = torch.zeros_like(Ap[j][0][pl])
+                if grid is not None:
+                    dr = dxt[j] if j == 0 else 0.0
+                    alpha = torch.nan_to_num(2 / 3 * dr / grid[j][pl], nan=0.0, posinf=0.0, neginf=0.0)
                 if bc.side < 0:
                     Ap[j][0][pl] = 2 / 3 + alpha
                     Ac[j][0][pl] = -(2 / 3 + alpha)
@@ -227,7 +244,8 @@ def _adv_tensor(u, phi: Tensor) -> Tensor:
     return u
 
 
-def div_coeffs(u, phi: Tensor, dx: list[float], bcs: list[FaceBC], limiter: str):
+def div_coeffs(u, phi: Tensor, dx: list[float], bcs: list[FaceBC], limiter: str,
+               rz_xs: list[Tensor] | None = None):
     """fdc.py:622-664, 708-772.  limiter: "none" (central) | "upwind" (reference formula)
     | "upwind_fd" (NOT in the reference: the first-order upwind difference its own test
     intends, tests/test_fdm.py:239 — parity unpinned)."""
@@ -235,6 +253,10 @@ def div_coeffs(u, phi: Tensor, dx: list[float], bcs: list[FaceBC], limiter: str)
     App, Ap, Ac, Am, Amm = _defaults(phi, 1.0, 0.0, -1.0)
     nd = phi.dim() - 1
     a0 = adv[0]
+    if rz_xs is not None:  # tools.py:64-76: centre coefficient 2 dr / r on the r axis
+        dxt0 = torch.tensor(dx, dtype=phi.dtype)
+        scale = torch.nan_to_num(2 * dxt0[0] / _rz_grid(phi, rz_xs)[0], nan=0.0, posinf=0.0, neginf=0.0)
+        Ac[0] = scale * torch.ones_like(phi)
     if limiter == "none":
         for j in range(nd):
             Ap[j][0] *= torch.roll(a0, -1, dims=j)
@@ -360,10 +382,11 @@ def hessian(phi: Tensor, dx: list[float]) -> dict[tuple[int, int], Tensor]:
 # ---------------------------------------------------------------------------------------
 # rhs adjustment (fdc.py:425-458, 505-540, 666-694)
 # ---------------------------------------------------------------------------------------
-def laplacian_rhs_adjust(phi, dx, bcs):
+def laplacian_rhs_adjust(phi, dx, bcs, rz_xs: list[Tensor] | None = None):
     out = torch.zeros_like(phi)
     nd = phi.dim() - 1
     dxt = torch.tensor(dx, dtype=phi.dtype)
+    grid = _rz_grid(phi, rz_xs) if rz_xs is not None else None
     for j in range(nd):
         for bc in bcs:
             if bc.kind != "neumann":
@@ -371,6 +394,9 @@ def laplacian_rhs_adjust(phi, dx, bcs):
             n = phi.shape[1 + bc.axis]
             pl = _plane(nd, bc.axis, _face_idx(bc, n, 1))
             alpha = torch.zeros_like(out[0][pl])
+            if grid is not None:  # fdc.py:440-448
+                dr = dxt[j] if j == 0 else 0.0
+                alpha = torch.nan_to_num(1 / 3 * dr / grid[j][pl], nan=0.0, posinf=0.0, neginf=0.0)
             nvec = torch.zeros(3, dtype=phi.dtype)
             nvec[bc.axis] = bc.side
             at_bc = _bc_scalar(bc)
@@ -436,15 +462,17 @@ class Equation:
     dx: list[float]
     xs: list[Tensor]
     bcs: list[FaceBC]
+    rz: bool = False  # axisymmetric (r, z) mesh: Cylinder geometry
 
     def build(self, phi: Tensor) -> "Equation":
+        rz_xs = self.xs if self.rz else None
         for t in self.terms:
             if t.kind == "laplacian":
-                t.coeffs = laplacian_coeffs(phi, self.dx, self.bcs)
+                t.coeffs = laplacian_coeffs(phi, self.dx, self.bcs, rz_xs)
             elif t.kind == "grad":
                 t.coeffs = grad_coeffs(phi, self.dx, self.bcs)
             elif t.kind == "div":
-                t.coeffs = div_coeffs(t.param, phi, self.dx, self.bcs, t.limiter)
+                t.coeffs = div_coeffs(t.param, phi, self.dx, self.bcs, t.limiter, rz_xs)
             else:
                 raise ValueError(t.kind)
         return self
@@ -453,7 +481,7 @@ class Equation:
         """ops.py:63-77 — in place on the caller's tensor, every term contributes."""
         for t in self.terms:
             if t.kind == "laplacian":
-                rhs += laplacian_rhs_adjust(phi, self.dx, self.bcs)
+                rhs += laplacian_rhs_adjust(phi, self.dx, self.bcs, self.xs if self.rz else None)
             elif t.kind == "grad":
                 rhs += grad_rhs_adjust(phi, self.dx, self.bcs)
             else:

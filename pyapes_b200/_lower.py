@@ -138,10 +138,17 @@ class StarCoeffs:
 
     kind = N.OP_STAR
 
-    def __init__(self, vecs: list[list[Tensor]], name: str):
+    def __init__(self, vecs: list[list[Tensor]], name: str, table_axes=()):
         self.vec = vecs
         self.name = name
         self.adv = None
+        # axes whose coefficients vary with the index (rz: the r axis) go to the kernel as a
+        # per-index table instead of three classes
+        self.table_axes = tuple(table_axes)
+
+    def table(self, j: int) -> Tensor:
+        ap, ac, am = self.vec[j]
+        return torch.stack([ap, ac, am], dim=1).contiguous()
 
     def classes(self, j: int) -> list[list[float]]:
         ap, ac, am = self.vec[j]
@@ -164,15 +171,24 @@ def _axis_bcs(bcs, j):
     return [bc for bc in (bcs or []) if bc.bc_face_dim == j]
 
 
-def laplacian_star(nx, dx: list[float], bcs, dtype) -> StarCoeffs:
-    """fdc.py:375-423 with tools.py:79-85 on one 1-D vector per axis."""
+def laplacian_star(nx, dx: list[float], bcs, dtype, rz_x=None) -> StarCoeffs:
+    """fdc.py:375-423 with tools.py:79-85 on one 1-D vector per axis.  `rz_x` = the (r, z) node
+    coordinate vectors of an axisymmetric mesh: r-axis coefficients 1 +- dr/(2r) (tools.py:86-108)
+    and the Neumann/Symmetry edits with alpha = 2/3 dr/r (fdc.py:395-403)."""
     dxt = torch.tensor(dx, dtype=dtype)
     vecs = []
     for j, n in enumerate(nx):
         ap, ac, am = torch.ones(n, dtype=dtype), -2.0 * torch.ones(n, dtype=dtype), torch.ones(n, dtype=dtype)
+        if rz_x is not None and j == 0:
+            scale = torch.nan_to_num(dxt[0] / (2 * rz_x[0]), nan=0.0, posinf=0.0, neginf=0.0)
+            ap, am = (1 + scale) * ap, (1 - scale) * am
         for bc in _axis_bcs(bcs, j):
             if bc.bc_type in ("neumann", "symmetry"):
                 alpha = torch.zeros(1, dtype=dtype)
+                if rz_x is not None:
+                    dr = dxt[j] if j == 0 else 0.0
+                    r = rz_x[j][1 % n] if bc.bc_n_dir < 0 else rz_x[j][(n - 2) % n]
+                    alpha = torch.nan_to_num(2 / 3 * dr / r, nan=0.0, posinf=0.0, neginf=0.0).reshape(1)
                 if bc.bc_n_dir < 0:
                     ap[1 % n] = 2 / 3 + alpha
                     ac[1 % n] = -(2 / 3 + alpha)
@@ -185,7 +201,7 @@ def laplacian_star(nx, dx: list[float], bcs, dtype) -> StarCoeffs:
         ac /= dxt[j] ** 2
         am /= dxt[j] ** 2
         vecs.append([ap, ac, am])
-    return StarCoeffs(vecs, "Laplacian")
+    return StarCoeffs(vecs, "Laplacian", table_axes=(0,) if rz_x is not None else ())
 
 
 def _central_star(nx, dx, bcs, dtype, ap0, ac0, am0, gamma, name, allow_ns=True) -> StarCoeffs:
@@ -229,9 +245,12 @@ def grad_star(nx, dx, bcs, dtype) -> StarCoeffs:
                          lambda n: -1.0 * one(n), 1.0, "Grad")
 
 
-def div_star_const(u: float, nx, dx, bcs, dtype, limiter: str) -> StarCoeffs:
-    """Div with a constant advection speed (fdc.py:622-664, 708-772)."""
+def div_star_const(u: float, nx, dx, bcs, dtype, limiter: str, rz_x=None) -> StarCoeffs:
+    """Div with a constant advection speed (fdc.py:622-664, 708-772).  rz: the centre coefficient
+    on the r axis starts as 2 dr / r (tools.py:64-76)."""
     adv = torch.ones(1, dtype=dtype) * u  # fdc.py:779
+    if rz_x is not None:
+        return _div_star_const_rz(u, adv, nx, dx, bcs, dtype, limiter, rz_x)
     if limiter == "none":
         if any(bc.bc_type in ("neumann", "symmetry") for bc in (bcs or [])):
             raise IndexError(
@@ -264,6 +283,36 @@ def div_star_const(u: float, nx, dx, bcs, dtype, limiter: str) -> StarCoeffs:
     return StarCoeffs(vecs, "Div")
 
 
+def _div_star_const_rz(u, adv, nx, dx, bcs, dtype, limiter, rz_x) -> StarCoeffs:
+    dxt = torch.tensor(dx, dtype=dtype)
+    zero = torch.zeros(1, dtype=dtype)
+    vecs = []
+    for j, n in enumerate(nx):
+        ap, ac, am = torch.ones(n, dtype=dtype), torch.zeros(n, dtype=dtype), -1.0 * torch.ones(n, dtype=dtype)
+        if j == 0:
+            ac = torch.nan_to_num(2 * dxt[0] / rz_x[0], nan=0.0, posinf=0.0, neginf=0.0) * torch.ones(n, dtype=dtype)
+        if limiter == "none":
+            if any(bc.bc_type in ("neumann", "symmetry") for bc in (bcs or [])):
+                raise IndexError("FDC Div: central scheme with Neumann/Symmetry faces is not usable "
+                                 "(the reference raises IndexError in fdc.py:583-584 as well)")
+            ap, ac, am = ap * adv[0], ac * adv[0], am * adv[0]
+            for bc in _axis_bcs(bcs, j):
+                if bc.bc_type == "periodic":
+                    if bc.bc_n_dir < 0:
+                        am[1 % n] = 0.0
+                    else:
+                        ap[(n - 2) % n] = 0.0
+            ap, ac, am = ap / (2.0 * dxt[j]), ac / (2.0 * dxt[j]), am / (2.0 * dxt[j])
+        elif limiter == "upwind":
+            ap = (2.0 * torch.min(adv, zero)).expand(n).clone()
+            ac = ac * (2.0 * adv)
+            am = (2.0 * torch.max(adv, zero)).expand(n).clone()
+        else:
+            raise NotImplementedError(f"pyapes_b200: limiter {limiter!r} on rz meshes")
+        vecs.append([ap, ac, am])
+    return StarCoeffs(vecs, "Div", table_axes=(0,))
+
+
 def div_field(adv: Tensor, nx, dx, bcs, limiter: str) -> FieldCoeffs:
     nd = len(nx)
     zl, zh = [0] * 3, [0] * 3
@@ -293,7 +342,7 @@ def div_field(adv: Tensor, nx, dx, bcs, limiter: str) -> FieldCoeffs:
 
 
 def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=None, edge: int = 0,
-             dx=None, adv_const: float = 0.0) -> tuple[N.Op, Any]:
+             dx=None, adv_const: float = 0.0, field_device=None) -> tuple[N.Op, Any]:
     """StarCoeffs / FieldCoeffs -> pa_op.  `param` is None, a float, or a Tensor broadcastable to
     the field (the reference multiplies the stencil result by it elementwise, fdm.py:169)."""
     op = N.Op()
@@ -318,6 +367,7 @@ def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=
         dxt0 = torch.tensor(dx, dtype=dtype)
         for j in range(nd):
             op.dx[kernel_axis(j, nd)] = float(dxt0[j])
+    tkeep = []
     if isinstance(coeffs, StarCoeffs):
         for j in range(nd):
             a = kernel_axis(j, nd)
@@ -325,6 +375,11 @@ def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=
             for c in range(3):
                 for k in range(3):
                     op.coef[a][c][k] = cls[c][k]
+            if j in coeffs.table_axes:
+                dev = field_device if field_device is not None else "cuda"
+                tab = coeffs.table(j).to(device=dev, dtype=dtype)
+                op.coef_tab[a] = tab.data_ptr()
+                tkeep.append(tab)
     else:
         adv = coeffs.adv
         N.require_cuda(adv, "advection field")
@@ -338,4 +393,4 @@ def lower_op(coeffs, nd: int, dtype, sign: float = 1.0, param=None, field_shape=
         for a in range(3):
             op.zero_am_lo[a] = coeffs.zero_am_lo[a]
             op.zero_ap_hi[a] = coeffs.zero_ap_hi[a]
-    return op, (keep, pkeep)
+    return op, (keep, pkeep, tkeep)

@@ -61,6 +61,7 @@ class Op(C.Structure):
         ("edge", C.c_int32),
         ("reserved", C.c_int32),
         ("adv_const", C.c_double),
+        ("coef_tab", C.c_void_p * 3),
     ]
 
 

@@ -235,6 +235,21 @@ static int solver_stream(cudaStream_t caller, cudaStream_t* out) {
   return PA_OK;
 }
 
+// second private stream for the halo exchange, with the two events that fork/join it
+struct CommLane {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static CommLane* comm_lane() {
+  static CommLane lane;
+  if (!lane.s) {
+    if (cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&lane.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&lane.join, cudaEventDisableTiming);
+  }
+  return &lane;
+}
+
 // ---- CG -----------------------------------------------------------------------------------
 // One iteration = [d update] -> d.Ad -> x/r update -> BC faces -> shell norm + scalars.
 // Tiled variant fuses the first two and recomputes Ad in the third (8 words / cell).
@@ -246,6 +261,7 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
   auto mark = [&](int i) {
     if (marks) cudaEventRecord(marks[i], L.s);
   };
+  bool overlapped = false;
   mark(0);
   T* r = (T*)w.vec[0];
   T* d = (T*)w.vec[1];
@@ -260,8 +276,22 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
       L.count += 2;
     }
     mark(1);
-    launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials);
-    ++L.count;
+    CommLane* lane = (dist && tma->tile.chunks >= 6) ? comm_lane() : nullptr;  // enough interior work to hide it
+    if (lane) {
+      // overlap: boundary chunks first, their r planes go out on the comm stream while the
+      // interior chunks run
+      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, 1);
+      cudaEventRecord(lane->fork, L.s);
+      cudaStreamWaitEvent(lane->s, lane->fork, 0);
+      dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, lane->s);
+      cudaEventRecord(lane->join, lane->s);
+      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, 2);
+      L.count += 3;
+      overlapped = true;
+    } else {
+      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials);
+      ++L.count;
+    }
   } else if (tiled) {
     // the fused d-update recomputes d_new on tile halos, so d is double-buffered: neighbours
     // must still see d_old there (kernels_tiled.cuh)
@@ -303,9 +333,10 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
       launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
       launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_NONE);
     }
-    dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
+    if (!overlapped) dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
     dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
     k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_FIN, w.st);
+    if (overlapped) cudaStreamWaitEvent(L.s, comm_lane()->join, 0);  // r ghosts before the next phase A
     L.count += 3;
   }
   mark(3);

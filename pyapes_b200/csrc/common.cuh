@@ -58,6 +58,7 @@ struct OpDev {
   const T* param_field;
   int edge;
   T adv_const;
+  const T* coef_tab[3];
 };
 
 template <typename T>
@@ -89,6 +90,7 @@ inline EqDev<T> make_eq(const pa_equation& e) {
     o.param_field = (const T*)s.param_field;
     o.edge = s.edge;
     o.adv_const = (T)s.adv_const;
+    for (int a = 0; a < 3; ++a) o.coef_tab[a] = (const T*)s.coef_tab[a];
   }
   return d;
 }
@@ -180,7 +182,12 @@ __device__ __forceinline__ T eval_equation(const GridDev& g, const EqDev<T>& eq,
     for (int a = 0; a < 3; ++a) {
       if (!g.act[a]) continue;
       T Ap, Ac, Am;
-      if (o.kind == PA_OP_STAR) {
+      if (o.kind == PA_OP_STAR && o.coef_tab[a] != nullptr) {  // per-index table (rz)
+        const T* t = o.coef_tab[a] + 3 * c.i[a];
+        Ap = t[0];
+        Ac = t[1];
+        Am = t[2];
+      } else if (o.kind == PA_OP_STAR) {
         Ap = o.coef[a][cls[a]][0];
         Ac = o.coef[a][cls[a]][1];
         Am = o.coef[a][cls[a]][2];

@@ -164,9 +164,10 @@ struct StoreSums {
   SolverState* st;
   int slot0;
   int stage;  // ST_NONE: just store
+  int accum = 0;  // add to what an earlier sub-launch stored
   __device__ void operator()(double (&acc)[NS]) const {
 #pragma unroll
-    for (int s = 0; s < NS; ++s) st->sum[slot0 + s] = acc[s];
+    for (int s = 0; s < NS; ++s) st->sum[slot0 + s] = accum ? st->sum[slot0 + s] + acc[s] : acc[s];
     if (stage != ST_NONE) finalize_stage<T>(stage, st);
   }
 };
@@ -239,9 +240,10 @@ __global__ void __launch_bounds__(kBlock) k_grad(GridDev g, OpDev<T> o, const T*
       T vp = phi[(i + 1 == n) ? idx - (long long)(n - 1) * st : idx + st];
       T vm = phi[(i == 0) ? idx + (long long)(n - 1) * st : idx - st];
       int cls = coef_class(g, a, i);
-      T s = o.coef[a][cls][0] * vp;
-      s = s + o.coef[a][cls][1] * vc;
-      s = s + o.coef[a][cls][2] * vm;
+      const T* ct = o.coef_tab[a] != nullptr ? o.coef_tab[a] + 3 * i : &o.coef[a][cls][0];
+      T s = ct[0] * vp;
+      s = s + ct[1] * vc;
+      s = s + ct[2] * vm;
       if (o.edge) {  // edge=True Grad (fdc.py:260-288)
         if (i == 0)
           s = -edge_first<T>(phi, idx, st, 1) / o.dx[a];
@@ -676,7 +678,9 @@ __device__ __forceinline__ T eq_diag(const GridDev& g, const EqDev<T>& eq, const
     for (int a = 0; a < 3; ++a) {
       if (!g.act[a]) continue;
       T Ac;
-      if (o.kind == PA_OP_STAR) {
+      if (o.kind == PA_OP_STAR && o.coef_tab[a] != nullptr) {
+        Ac = o.coef_tab[a][3 * c.i[a] + 1];
+      } else if (o.kind == PA_OP_STAR) {
         Ac = o.coef[a][coef_class(g, a, c.i[a])][1];
       } else if (o.kind == PA_OP_DIV_UPWINDFD_FIELD) {
         T u = o.adv[c.idx];

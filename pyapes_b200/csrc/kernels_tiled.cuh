@@ -43,6 +43,9 @@ struct TilePlan {
   int fuse_fin;                      // phase B also finalizes the iteration (static shell)
   int ry;                            // rows per thread of the instantiation to launch (2 or 4)
   int dist;                          // multi-GPU: leave raw sums for the NCCL all-reduce
+  // sub-launch over a subset of the chunks (halo-exchange overlap): chunk = chunk0 + z*step;
+  // accum = 1 adds this launch's sums to the ones an earlier sub-launch stored
+  int chunk0, chunk_step, accum;
 };
 
 template <typename T>
@@ -97,7 +100,7 @@ inline bool plan_tiles(const GridDev& g, const pa_equation& eq, TilePlan& p) {
 template <typename T, int RY>
 inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, int slots) {
   typedef TileCfg<T, RY> C;
-  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0) return false;
+  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0 || eq.ops[0].coef_tab[0] || eq.ops[0].coef_tab[1] || eq.ops[0].coef_tab[2]) return false;
   if (!g.act[1] || !g.act[2]) return false;  // 1-D meshes stay on the generic kernels
   if (g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;
@@ -128,6 +131,9 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.vec_ok = (g.n[2] % C::VEC == 0) ? 1 : 0;
   p.fuse_fin = 0;
   p.dist = 0;
+  p.chunk0 = 0;
+  p.chunk_step = 1;
+  p.accum = 0;
   return true;
 }
 

@@ -141,7 +141,7 @@ template <typename T>
 inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
                      const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
   typedef TmaCfg<T, kTmaRY> C;
-  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0) return false;
+  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0 || eq.ops[0].coef_tab[0] || eq.ops[0].coef_tab[1] || eq.ops[0].coef_tab[2]) return false;
   if (!g.act[1] || !g.act[2]) return false;
   if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
@@ -174,6 +174,9 @@ inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const 
   p.vec_ok = 1;
   p.fuse_fin = 0;
   p.dist = 0;
+  p.chunk0 = 0;
+  p.chunk_step = 1;
+  p.accum = 0;
   bool ok = make_map<T>(&tp.x_own[0], x, g, C::TZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::TZ, C::TY) &&
             make_map<T>(&tp.r_own, r, g, C::TZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
             make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) &&
@@ -439,7 +442,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const int x0 = (p.chunk0 + (int)blockIdx.z * p.chunk_step) * p.cx, x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
@@ -485,7 +488,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
     if (threadIdx.x == 0) st->sum[R_SHELL] = 0.0;
     grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_CG_FIN});
   } else {
-    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_NONE});
+    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_NONE, p.accum});
   }
 }
 
@@ -615,7 +618,7 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const int x0 = (p.chunk0 + (int)blockIdx.z * p.chunk_step) * p.cx, x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
@@ -672,17 +675,29 @@ inline void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDe
 
 template <typename T>
 inline void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
-                                 int parity, T* x_new, T* r, SolverState* st, double* partials) {
+                                 int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
   typedef TmaCfg<T, kTmaRY> C;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_cg_phaseB_tma<T, kTmaRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;
   }
-  dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
+  TilePlan tile = tp.tile;
+  int nz = tile.chunks;
+  if (sub == 1) {         // boundary chunks: first and last
+    tile.chunk0 = 0;
+    tile.chunk_step = tile.chunks - 1;
+    nz = 2;
+  } else if (sub == 2) {  // interior chunks, sums added to the boundary launch's
+    tile.chunk0 = 1;
+    tile.chunk_step = 1;
+    tile.accum = 1;
+    nz = tile.chunks - 2;
+  }
+  dim3 grid(tile.tiles_z, tile.tiles_y, nz);
   k_cg_phaseB_tma<T, kTmaRY><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own,
-                                                                tp.tile, g, eq.op[0], x_new, r, st, partials);
+                                                                tile, g, eq.op[0], x_new, r, st, partials);
 }
 
 }  // namespace pa

@@ -313,7 +313,7 @@ inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, con
   typedef PwCfg<T, kTmaRY> C;
   if (eq.nops < 1 || eq.nops > PA_MAX_OPS) return false;
   for (int k = 0; k < eq.nops; ++k)
-    if (eq.ops[k].kind != PA_OP_STAR || eq.ops[k].param_field != nullptr || eq.ops[k].edge != 0) return false;
+    if (eq.ops[k].kind != PA_OP_STAR || eq.ops[k].param_field != nullptr || eq.ops[k].edge != 0 || eq.ops[k].coef_tab[0] || eq.ops[k].coef_tab[1] || eq.ops[k].coef_tab[2]) return false;
   if (!g.act[1] || !g.act[2]) return false;
   if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
   for (int f = 0; f < nfaces; ++f)
@@ -351,6 +351,9 @@ inline void pw_tile_plan(const GridDev& g, TilePlan& p) {
   p.vec_ok = 1;
   p.fuse_fin = 0;
   p.dist = 0;
+  p.chunk0 = 0;
+  p.chunk_step = 1;
+  p.accum = 0;
 }
 
 // One launch of the engine.  `in` is the stencilled field, `aux` rhs / r0 (may be null).

@@ -80,10 +80,7 @@ class Mesh:
         self.dtype = DType(dtype)
         self.domain = domain
         if self.coord_sys == "rz":
-            raise NotImplementedError(
-                "pyapes_b200: axisymmetric (rz / Cylinder) meshes are not built yet "
-                "(SURVEY.md §8(f) item 2); there is no fallback path."
-            )
+            assert self.dim == 2, "Mesh: rz coordinate system only accept 2D domain"
         if obstacle is not None:
             raise NotImplementedError(
                 "pyapes_b200: inner obstacles are not supported (the reference's solvers raise "
@@ -146,7 +143,7 @@ class Mesh:
         raise TypeError(f"Mesh: domain type ({self.domain.type=}) not identifiable")
 
     def d_mask_dim(self, d_face: str) -> int:
-        return DIR_TO_NUM[d_face[0]]
+        return (DIR_TO_NUM_RZ if self.coord_sys == "rz" else DIR_TO_NUM)[d_face[0]]
 
     def d_mask_dir(self, d_face: str) -> int:
         return 1 if d_face[1] == "r" else -1
@@ -187,7 +184,9 @@ class Mesh:
 
     @property
     def R(self) -> Tensor:
-        raise KeyError("Mesh: R coordinate only available in axisymmetric case.")
+        if self.coord_sys != "rz":
+            raise KeyError("Mesh: R coordinate only available in axisymmetric case.")
+        return self.grid[0]
 
     @property
     def X(self) -> Tensor:
@@ -198,10 +197,14 @@ class Mesh:
 
     @property
     def Y(self) -> Tensor:
+        if self.coord_sys == "rz":
+            return self._empty()
         return self.grid[1] if self.dim > 1 else self._empty()
 
     @property
     def Z(self) -> Tensor:
+        if self.coord_sys == "rz":
+            return self.grid[1]
         return self.grid[2] if self.dim > 2 else self._empty()
 
     @cached_property

@@ -10,7 +10,7 @@ from pyapes_b200 import _lower as L
 from pyapes_b200 import _native as N
 
 
-def cg_kernel_times(n: int, iters: int = 20, variant: int = 0, dtype: str = "double", device: str = "cuda") -> dict:
+def cg_kernel_times(n, iters: int = 20, variant: int = 0, dtype: str = "double", device: str = "cuda") -> dict:
     """n^3 Dirichlet Poisson, `iters` CG iterations, every launch group bracketed by CUDA
     events on the launching stream (csrc/api.cu profile_cg).  Times are averages per iteration."""
     from pyapes_b200.geometry import Box
@@ -20,10 +20,11 @@ def cg_kernel_times(n: int, iters: int = 20, variant: int = 0, dtype: str = "dou
     from pyapes_b200.variables import Field
     from pyapes_b200.variables.bcs import homogeneous_bcs
 
-    mesh = Mesh(Box[0:1, 0:1, 0:1], None, [n, n, n], device, dtype)
+    shape = [n, n, n] if isinstance(n, int) else list(n)
+    mesh = Mesh(Box[0:1, 0:1, 0:1], None, shape, device, dtype)
     var = Field("p", 1, mesh, {"domain": homogeneous_bcs(3, 0.0, "dirichlet"), "obstacle": None})
     g = torch.Generator().manual_seed(1234)
-    rhs = torch.rand(1, n, n, n, generator=g, dtype=torch.float64).to(device=device, dtype=var().dtype)
+    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64).to(device=device, dtype=var().dtype)
     solver = Solver({"fdm": {"method": "cg", "tol": 1e-30, "max_it": iters, "report": False}})
     solver.set_eq(FDM().laplacian(1.0, var) == rhs)
     x = var()

@@ -23,6 +23,11 @@ from pyapes_b200.solver.types import DiscretizerConfigType, DivConfigType
 from pyapes_b200.variables import Field
 
 
+def _rz_x(var: Field):
+    """Host node-coordinate vectors of an axisymmetric mesh (None for Cartesian ones)."""
+    return var.mesh._x_host if var.mesh.coord_sys == "rz" else None
+
+
 def _scalar_field(var: Field, who: str) -> None:
     if var.dim != 1:
         raise NotImplementedError(
@@ -123,7 +128,10 @@ class Discretizer:
         if getattr(var.mesh, "slab", None) is not None:
             raise NotImplementedError("pyapes_b200: explicit FDC operators on a slab-decomposed mesh are not built yet")
         grid = L.lower_grid(var.nx, var.bcs)
-        op, keep = L.lower_op(A_coeffs, nd, phi.dtype, edge=edge_code, dx=var.mesh._dx, adv_const=adv_const)
+        if edge and var.mesh.coord_sys == "rz":
+            raise NotImplementedError("pyapes_b200: edge=True on rz meshes is not built")
+        op, keep = L.lower_op(A_coeffs, nd, phi.dtype, edge=edge_code, dx=var.mesh._dx, adv_const=adv_const,
+                              field_device=phi.device)
         code, stream = N.dtype_code(phi.dtype), N.current_stream(phi.device)
         if self.op_type == "Grad":
             out = torch.empty((1, nd, *var.nx), dtype=phi.dtype, device=phi.device)
@@ -166,7 +174,7 @@ class Laplacian(Discretizer):
     def build_A_coeffs(var: Field) -> L.StarCoeffs:
         """fdc.py:375-423: Neumann/Symmetry faces edit the plane next to them
         (2/3, -2/3, 0 | 0, -2/3, 2/3), everything / dx^2."""
-        return L.laplacian_star(var.nx, var.mesh._dx, var.bcs, var().dtype)
+        return L.laplacian_star(var.nx, var.mesh._dx, var.bcs, var().dtype, _rz_x(var))
 
     @staticmethod
     def adjust_rhs(var: Field) -> Tensor:
@@ -181,6 +189,9 @@ class Laplacian(Discretizer):
                     continue
                 pl = _plane(var, bc, 1)
                 alpha = torch.zeros_like(out[0][pl])
+                if var.mesh.coord_sys == "rz":  # fdc.py:440-448
+                    dr = dx[j] if j == 0 else 0.0
+                    alpha = torch.nan_to_num(1 / 3 * dr / var.mesh.grid[j][pl], nan=0.0, posinf=0.0, neginf=0.0)
                 at_bc = _return_bc_val(bc, var, 0, out[0][pl].shape)
                 out[0][pl] += (2 / 3 - alpha) * (at_bc * bc.bc_n_vec[j]) / dx[j]
         return out
@@ -235,7 +246,9 @@ class Div(Discretizer):
         limiter = _check_limiter(config["div"])
         adv = _adv_of(var_j, var_i)
         if isinstance(adv, float):
-            return L.div_star_const(adv, var_i.nx, var_i.mesh._dx, var_i.bcs, var_i().dtype, limiter)
+            return L.div_star_const(adv, var_i.nx, var_i.mesh._dx, var_i.bcs, var_i().dtype, limiter, _rz_x(var_i))
+        if var_i.mesh.coord_sys == "rz":
+            raise NotImplementedError("pyapes_b200: field-valued advection on rz meshes (SURVEY.md §8(f) item 3)")
         if adv.shape[0] != 1:
             adv = adv[0:1]  # scalar var_i uses adv[0] on every axis (fdc.py:735,760)
         return L.div_field(adv.contiguous(), var_i.nx, var_i.mesh._dx, var_i.bcs, limiter)

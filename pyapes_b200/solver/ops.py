@@ -119,7 +119,8 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field):
                 from pyapes_b200.solver.fdc import FDC
 
                 coeffs = FDC(cfg).div.build_A_coeffs(var_j, target, cfg)  # live field (fdm.py:309-312)
-        op, kp = L.lower_op(coeffs, nd, dtype, sign=float(e["sign"]), param=param, field_shape=target().shape)
+        op, kp = L.lower_op(coeffs, nd, dtype, sign=float(e["sign"]), param=param, field_shape=target().shape,
+                            field_device=target().device)
         eq.ops[k] = op
         keep.append(kp)
         k += 1

@@ -200,7 +200,10 @@ class Field:
             target = torch.ones_like(self._VAR[0])
         val = torch.zeros(self.dim, device=self._VAR.device, dtype=self._VAR.dtype)
         for i in range(self.dim):
-            val[i] = torch.sum(target * self._VAR[i] * self.mesh.dx.prod())
+            if self.mesh.coord_sys == "xyz":
+                val[i] = torch.sum(target * self._VAR[i] * self.mesh.dx.prod())
+            else:  # axisymmetric: 2 pi r dr dz (fields.py:350-356)
+                val[i] = torch.sum(2.0 * torch.pi * self._VAR[i] * self.mesh.grid[0] * self.mesh.dx.prod())
         return val
 
     # ---- boundary conditions ---------------------------------------------------------------

@@ -16,7 +16,7 @@ def load(name: str):
 
 
 def oracle_bcs(case) -> list[O.FaceBC]:
-    return [O.FaceBC(f, k, v) for f, k, v in case["bcs"]]
+    return [O.FaceBC(f, k, v, rz=bool(case["spec"].get("rz"))) for f, k, v in case["bcs"]]
 
 
 def oracle_axes(case):
@@ -36,6 +36,10 @@ def case_rhs(case, shape, dtype):
     return torch.zeros(shape, dtype=dtype) + float(rhs)
 
 
+def is_rz(case) -> bool:
+    return bool(case["spec"].get("rz"))
+
+
 def oracle_terms(case):
     limiter = (case.get("div_cfg") or {}).get("div", {}).get("limiter", "none")
     return [O.Term(kind, sign=float(sign), param=param, limiter=limiter if kind == "div" else "none")
@@ -50,7 +54,13 @@ def product_field(case, device="cuda", init=0.0):
     from pyapes_b200.variables import Field
 
     spec = case["spec"]
-    mesh = Mesh(Box(list(spec["lower"]), list(spec["upper"])), None, list(spec["nx"]), device, spec["dtype"])
+    if spec.get("rz"):
+        from pyapes_b200.geometry import Cylinder
+
+        geo = Cylinder(list(spec["lower"]), list(spec["upper"]))
+    else:
+        geo = Box(list(spec["lower"]), list(spec["upper"]))
+    mesh = Mesh(geo, None, list(spec["nx"]), device, spec["dtype"])
     cfg = []
     for face, kind, val in case["bcs"]:
         if isinstance(val, torch.Tensor):

@@ -42,11 +42,18 @@ def box(lower, upper):
 
 
 def build(spec):
-    """spec: lower, upper, nx, dtype ("double"|"single"), bcs [(kind, value)] in FDIR order."""
-    mesh = Mesh(box(spec["lower"], spec["upper"]), None, list(spec["nx"]), "cpu", spec["dtype"])
+    """spec: lower, upper, nx, dtype ("double"|"single"), bcs [(kind, value)] in FDIR order
+    (rl, ru, zl, zu for spec["rz"])."""
+    from pyapes.geometry import Cylinder
+
+    geo = Cylinder(list(spec["lower"]), list(spec["upper"])) if spec.get("rz") else box(spec["lower"], spec["upper"])
+    mesh = Mesh(geo, None, list(spec["nx"]), "cpu", spec["dtype"])
     vals = [CALLABLES[v] if isinstance(v, str) else v for _, v in spec["bcs"]]
     kinds = [k for k, _ in spec["bcs"]]
     cfg = mixed_bcs(vals, kinds)
+    if spec.get("rz"):
+        for c, f in zip(cfg, ["rl", "ru", "zl", "zu"]):
+            c["bc_face"] = f
     var = Field("p", 1, mesh, {"domain": cfg, "obstacle": None})
     return mesh, var
 
@@ -137,6 +144,51 @@ def op_case(name, spec, seed=7, u_const=0.7):
         "u_const": u_const,
         "out": out,
     }
+
+
+def rz_bc_ru(grid, mask, *_):
+    from math import cos
+
+    return torch.exp(-grid[1][mask]) * cos(1)
+
+
+def rz_bc_zl(grid, mask, *_):
+    return torch.cos(grid[0][mask])
+
+
+def rz_bc_zu(grid, mask, *_):
+    from math import exp
+
+    return torch.cos(grid[0][mask]) * exp(-1)
+
+
+CALLABLES.update({"rz_bc_ru": rz_bc_ru, "rz_bc_zl": rz_bc_zl, "rz_bc_zu": rz_bc_zu})
+
+
+def rz_op_case(name, spec, seed=21, u_const=0.4):
+    """Axisymmetric operators (tools.py:64-108, fdc.py:395-448)."""
+    mesh, var = build(spec)
+    phi = rand_like(var, seed) - 0.5
+    var.set_var_tensor(phi.clone())
+    out = {}
+    for tag, make in (("lap", lambda f: f.laplacian(var)), ("neg_lap_c", lambda f: -f.laplacian(1.5, var))):
+        s = Solver(None)
+        rhs = torch.zeros_like(var())
+        s.set_eq(make(FDM()) == rhs)
+        out[tag] = s.Aop(var).clone()
+        out[tag + "_rhs_adj"] = rhs.clone()
+    fdc = FDC({"grad": {"edge": False}})
+    out["grad"] = fdc.grad(var).clone()
+    fdc = FDC({"div": {"limiter": "upwind", "edge": False}})
+    out["div_upwind_const"] = fdc.div(u_const, var).clone()
+    if not any(k in ("neumann", "symmetry") for k, _ in spec["bcs"]):
+        fdc = FDC({"div": {"limiter": "none", "edge": False}})
+        out["div_central_const"] = fdc.div(u_const, var).clone()
+    var.set_var_tensor(phi.clone())
+    _apply_bc_otf(var, mesh)
+    out["bc_applied"] = var().clone()
+    return {"name": name, "spec": spec, "bcs": frozen_bcs(mesh, var), "dx": [float(d) for d in mesh._dx],
+            "phi": phi, "u_const": u_const, "out": out}
 
 
 def edge_case(name, spec, seed=11, u_const=0.6):
@@ -317,6 +369,20 @@ def main():
     torch.save(edges, os.path.join(HERE, "edges.pt"))
     print(f"  {len(edges)} edge cases")
 
+    print("rz fixtures")
+    rzs = []
+    for dt in ("double", "single"):
+        tag = "f64" if dt == "double" else "f32"
+        rz_a = dict(dspec([0, 0], [1, 1], [9, 11], [("neumann", 0.0), ("dirichlet", "rz_bc_ru"), ("dirichlet", "rz_bc_zl"),
+                                                   ("dirichlet", "rz_bc_zu")], dt), rz=True)
+        rz_b = dict(dspec([0.5, 0], [2, 1], [10, 8], [("dirichlet", 0.5), ("neumann", 0.3), ("symmetry", None),
+                                                     ("neumann", -0.2)], dt), rz=True)
+        rz_c = dict(dspec([0, -1], [1, 1], [8, 9], [("dirichlet", 0.0)] * 4, dt), rz=True)
+        rzs += [rz_op_case(f"rz_axis_{tag}", rz_a), rz_op_case(f"rz_offaxis_{tag}", rz_b), rz_op_case(f"rz_dirichlet_{tag}", rz_c)]
+    torch.set_default_dtype(torch.float64)
+    torch.save(rzs, os.path.join(HERE, "rz_ops.pt"))
+    print(f"  {len(rzs)} rz cases")
+
     print("solver fixtures")
     L1 = [("laplacian", 1.0, 1.0)]
     sol = []
@@ -394,6 +460,17 @@ def main():
     sol.append(solver_case("advdiff_2d_33_bicgstab", dspec([0, 0], [1, 1], [33, 33], [D0] * 4),
                            [("div", 1.0, 0.5), ("laplacian", -1.0, 0.1)], ("rand", 1234), "bicgstab", 1e-8, 2000,
                            div_cfg={"div": {"limiter": "upwind", "edge": False}}))
+    def rhs_rz(mesh, var):
+        r = torch.zeros_like(var())
+        r[0] = -torch.sin(mesh.X) / (mesh.X * torch.exp(mesh.Z))
+        r[0][mesh.X.eq(0.0)] = -1.0 / torch.exp(mesh.Z[mesh.X.eq(0.0)])
+        return r
+
+    rz_bcs = [("neumann", 0.0), ("dirichlet", "rz_bc_ru"), ("dirichlet", "rz_bc_zl"), ("dirichlet", "rz_bc_zu")]
+    sol.append(solver_case("t_poisson_rz_101_bicgstab", dict(dspec([0, 0], [1, 1], [101, 101], rz_bcs), rz=True),
+                           L1, rhs_rz, "bicgstab", 1e-5, 1000))
+    sol.append(solver_case("rz_33_bicgstab_it12", dict(dspec([0, 0], [1, 1], [33, 29], rz_bcs), rz=True),
+                           L1, rhs_rz, "bicgstab", 1e-30, 12))
     # fp32: global default dtype flips to float32 inside the reference
     sol.append(solver_case("cfg1_2d_64_cg_f32", dspec([0, 0], [1, 1], [64, 64], [("dirichlet", "poisson_2d_bc")] * 4, "single"),
                            L1, "poisson_nd", "cg", 1e-6, 1000))
@@ -401,7 +478,7 @@ def main():
                            L1, ("rand", 1234), "bicgstab", 1e-4, 1000))
     torch.set_default_dtype(torch.float64)
     torch.save(sol, os.path.join(HERE, "solvers.pt"))
-    for f in ("ops.pt", "edges.pt", "solvers.pt"):
+    for f in ("ops.pt", "edges.pt", "rz_ops.pt", "solvers.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) / 1e6, "MB")
 
 

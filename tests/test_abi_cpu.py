@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
 
     assert C.sizeof(N.FaceBC) == 32
     assert C.sizeof(N.Grid) == 60
-    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8 + 4 + 4 + 8
+    assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8 + 4 + 4 + 8 + 24
     assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
     assert C.sizeof(N.Report) == 24 and C.sizeof(N.SolverCfg) == 24
 
@@ -101,10 +101,12 @@ def test_dsl_semantics_match_reference():
         from pyapes_b200.solver.linalg import solve
 
         solve(var, rhs, None, s.eqs, s.config["fdm"], mesh)
-    with pytest.raises(NotImplementedError):
-        from pyapes_b200.geometry import Cylinder
+    from pyapes_b200.geometry import Cylinder
 
-        Mesh(Cylinder[0:1, 0:1], None, [5, 5], "cpu")
+    rz = Mesh(Cylinder[0:1, 0:2], None, [5, 7], "cpu")
+    assert rz.coord_sys == "rz" and list(rz.d_mask) == ["zl", "zu", "rl", "ru"] and rz.R.shape == (5, 7)
+    with pytest.raises(KeyError):
+        mesh.R
 
 
 def test_derivative_containers():

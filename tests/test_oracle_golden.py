@@ -12,6 +12,7 @@ from tests import _util as U
 OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
 EDGES = U.load("edges.pt")
+RZ = U.load("rz_ops.pt")
 
 
 @pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
@@ -96,6 +97,29 @@ def test_edge_fixtures(case):
         assert torch.equal(h, out["hess_" + names[a] + names[b]])
 
 
+@pytest.mark.parametrize("case", RZ, ids=[c["name"] for c in RZ])
+def test_rz_operator_fixtures(case):
+    """Axisymmetric (Cylinder) coefficient variants (tools.py:64-108, fdc.py:395-448)."""
+    dtype = U.TDTYPE[case["spec"]["dtype"]]
+    torch.set_default_dtype(dtype)
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    phi, out = case["phi"].clone(), case["out"]
+    for tag, term in (("lap", O.Term("laplacian", 1.0, None)), ("neg_lap_c", O.Term("laplacian", -1.0, 1.5))):
+        e = O.Equation([term], dx, xs, bcs, rz=True).build(phi)
+        assert torch.equal(e.aop(phi), out[tag]), tag
+        assert torch.equal(e.adjust_rhs(phi, torch.zeros_like(phi)), out[tag + "_rhs_adj"]), tag
+    assert torch.equal(O.apply_grad(O.grad_coeffs(phi, dx, bcs), phi), out["grad"])
+    got = O.apply_scalar_op(O.div_coeffs(case["u_const"], phi, dx, bcs, "upwind", xs), phi)
+    assert torch.equal(got, out["div_upwind_const"])
+    if "div_central_const" in out:
+        got = O.apply_scalar_op(O.div_coeffs(case["u_const"], phi, dx, bcs, "none", xs), phi)
+        assert torch.equal(got, out["div_central_const"])
+    x = phi.clone()
+    O.apply_bcs(x, xs, bcs)
+    assert torch.equal(x, out["bc_applied"])
+
+
 @pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
 def test_solver_fixtures(case):
     if case["name"] == "rand_3d_64_cg":
@@ -107,7 +131,7 @@ def test_solver_fixtures(case):
     shape = (1, *case["spec"]["nx"])
     x = torch.zeros(shape, dtype=dtype) + case["init"]
     rhs = U.case_rhs(case, shape, dtype)
-    eq = O.Equation(U.oracle_terms(case), dx, xs, bcs).build(x)
+    eq = O.Equation(U.oracle_terms(case), dx, xs, bcs, rz=U.is_rz(case)).build(x)
     eq.adjust_rhs(x, rhs)
     assert rhs.double().sum().item() == case["rhs_adjusted_sum"]
     fn = {"cg": O.cg, "bicgstab": O.bicgstab}[case["method"]]
