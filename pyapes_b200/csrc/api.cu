@@ -93,6 +93,7 @@ static int static_shell(int nfaces, const pa_face_bc* faces) {
 struct Launcher {
   cudaStream_t s;
   int count = 0;
+  bool ok = true;  // false once a TMA launch could not be issued (tensor-map encode failed)
 };
 
 template <typename T>
@@ -425,7 +426,7 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   else
     k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
   if (pw)
-    launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_BI_V);
+    L.ok &= launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_BI_V);
   else
     k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_BI_V);
   if (stream_ok)
@@ -433,7 +434,7 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   else
     k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_BI_S);
   if (pw)
-    launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_BI_T);
+    L.ok &= launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_BI_T);
   else
     k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_BI_T);
   if (stream_ok)
@@ -454,8 +455,8 @@ static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, 
   if (pw) {
     // static shell: the sweep also finalizes the iteration (shell part of the norm is 0)
     const bool fuse = static_shell(nfaces, faces) != 0;
-    launch_star_tma<T, PW_JACOBI>(L.s, g, eq, *pw, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
-                                  fuse ? ST_JA_FIN : ST_NONE);
+    L.ok &= launch_star_tma<T, PW_JACOBI>(L.s, g, eq, *pw, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
+                                          fuse ? ST_JA_FIN : ST_NONE);
     ++L.count;
     if (fuse) return;
   } else {
@@ -523,8 +524,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     const long long plane = (long long)g.n[1] * g.n[2];
     if (dist) dist_halo_exchange<T>(*dist, x, plane, g.olo0, g.ohi0, stream);  // x ghosts for r0
     if (pw)
-      launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r, d, (T)0, w.st, w.partials,
-                                   dist ? ST_NONE : ST_CG_INIT);
+      L.ok &= launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r, d, (T)0, w.st, w.partials,
+                                           dist ? ST_NONE : ST_CG_INIT);
     else
       k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r, d, w.st, w.partials,
                                                     dist ? ST_NONE : ST_CG_INIT);
@@ -546,13 +547,14 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     T* r = (T*)w.vec[1];
     for (int i = 2; i < 6; ++i) PA_CUDA(cudaMemsetAsync(w.vec[i], 0, vbytes, stream));
     if (pw)
-      launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r0, r, (T)0, w.st, w.partials, ST_BI_INIT);
+      L.ok &= launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r0, r, (T)0, w.st, w.partials, ST_BI_INIT);
     else
       k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials,
                                                     ST_BI_INIT);
     ++L.count;
   }
   PA_CUDA(cudaGetLastError());
+  if (!L.ok) return fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed (TMA tile descriptor)");
 
   // while-loop entry condition of cg/jacobi: tol = 1.0 > tolerance (linalg.py:90,109)
   if (method != PA_METHOD_BICGSTAB && !(1.0 > cfg->tol)) {
@@ -615,6 +617,10 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       }
     }
     if (rc != PA_OK) break;
+    if (!L.ok) {
+      rc = fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed (TMA tile descriptor)");
+      break;
+    }
     it += chunk;
     rc = poll_state(stream, w.st, &h);
     if (rc != PA_OK) break;
