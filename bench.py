@@ -118,7 +118,7 @@ def host_rhs(n, rank=0, pin=True):
     return rhs.pin_memory() if pin and torch.cuda.is_available() else rhs
 
 
-def cpu_baseline(n_cpu=128, iters=20):
+def cpu_baseline(n_cpu=256, iters=20):
     """Oracle port of the reference's CPU torch algorithm (roll + full coefficient tensors),
     all host threads, bounded sample.  Returns (GLUP/s, seconds, threads)."""
     import torch
@@ -376,8 +376,8 @@ def main():
     ap.add_argument("--n", type=int, default=512, help="grid points per axis per GPU")
     ap.add_argument("--iters", type=int, default=50, help="CG iterations per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-n", type=int, default=128)
-    ap.add_argument("--cpu-iters", type=int, default=20)
+    ap.add_argument("--cpu-n", type=int, default=256, help="grid of the bounded CPU sample (reference arm)")
+    ap.add_argument("--cpu-iters", type=int, default=20, help="CG iterations of the CPU sample (~10-30 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,6 +14,36 @@
 
 namespace pa {
 
+// The tiled / TMA kernels are instantiated in their own translation units (tu_*.cu), compiled
+// in parallel by __graft_entry__.build(); here they are only declared.
+#define PA_EXTERN(T)                                                                                           \
+  extern template void launch_cg_phaseA<T>(cudaStream_t, const TilePlan&, const GridDev&, const EqDev<T>&,     \
+                                           const T*, const T*, T*, SolverState*, double*);                     \
+  extern template void launch_cg_phaseB<T>(cudaStream_t, const TilePlan&, const GridDev&, const EqDev<T>&,     \
+                                           const T*, T*, const T*, T*, SolverState*, double*);                 \
+  extern template void launch_cg_phaseA_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&,  \
+                                               int, T*, SolverState*, double*);                                \
+  extern template void launch_cg_phaseB_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&,  \
+                                               int, T*, T*, SolverState*, double*, int);                       \
+  extern template bool launch_star_tma<T, PW_RESID>(cudaStream_t, const GridDev&, const EqDev<T>&,             \
+                                                    const TilePlan&, const T*, const T*, T*, T*, T,            \
+                                                    SolverState*, double*, int);                               \
+  extern template bool launch_star_tma<T, PW_JACOBI>(cudaStream_t, const GridDev&, const EqDev<T>&,            \
+                                                     const TilePlan&, const T*, const T*, T*, T*, T,           \
+                                                     SolverState*, double*, int);                              \
+  extern template bool launch_star_tma<T, PW_EULER>(cudaStream_t, const GridDev&, const EqDev<T>&,             \
+                                                    const TilePlan&, const T*, const T*, T*, T*, T,            \
+                                                    SolverState*, double*, int);                               \
+  extern template bool launch_star_tma<T, PW_APPLY_V>(cudaStream_t, const GridDev&, const EqDev<T>&,           \
+                                                      const TilePlan&, const T*, const T*, T*, T*, T,          \
+                                                      SolverState*, double*, int);                             \
+  extern template bool launch_star_tma<T, PW_APPLY_T>(cudaStream_t, const GridDev&, const EqDev<T>&,           \
+                                                      const TilePlan&, const T*, const T*, T*, T*, T,          \
+                                                      SolverState*, double*, int);
+PA_EXTERN(double)
+PA_EXTERN(float)
+#undef PA_EXTERN
+
 static thread_local std::string g_err;
 
 static int fail(int code, const std::string& msg) {

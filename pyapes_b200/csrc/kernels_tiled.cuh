@@ -679,7 +679,7 @@ inline void launch_cg_phaseB_ry(cudaStream_t s, const TilePlan& p, const GridDev
 }
 
 template <typename T>
-inline void launch_cg_phaseA(cudaStream_t s, const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
+void launch_cg_phaseA(cudaStream_t s, const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
                              const T* r, const T* d_old, T* d_new, SolverState* st, double* partials) {
   if (p.ry == 2)
     launch_cg_phaseA_ry<T, 2>(s, p, g, eq, r, d_old, d_new, st, partials);
@@ -688,7 +688,7 @@ inline void launch_cg_phaseA(cudaStream_t s, const TilePlan& p, const GridDev& g
 }
 
 template <typename T>
-inline void launch_cg_phaseB(cudaStream_t s, const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
+void launch_cg_phaseB(cudaStream_t s, const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
                              const T* x_old, T* x_new, const T* d, T* r, SolverState* st,
                              double* partials) {
   if (p.ry == 2)

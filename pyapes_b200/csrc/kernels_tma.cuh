@@ -660,7 +660,7 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
 
 // ---- launchers -----------------------------------------------------------------------------------
 template <typename T>
-inline void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                  int parity, T* d_new, SolverState* st, double* partials) {
   typedef TmaCfg<T, kTmaRY> C;
   static bool attr = false;
@@ -674,7 +674,7 @@ inline void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDe
 }
 
 template <typename T>
-inline void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                  int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
   typedef TmaCfg<T, kTmaRY> C;
   static bool attr = false;

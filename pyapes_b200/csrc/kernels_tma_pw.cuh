@@ -374,7 +374,7 @@ inline void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CU
 }
 
 template <typename T, int MODE>
-inline bool launch_star_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
+bool launch_star_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
                             const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
                             double* partials, int stage) {
   typedef PwCfg<T, kTmaRY> C;

@@ -71,21 +71,22 @@ def euler_case(name, shape, limiter, steps):
             "words_per_LUP": 2, "hbm_frac": round(glups * 1e9 * 16 / HBM, 3)}
 
 
-out = []
-N3 = 256 if quick else 512
-D6 = (["dirichlet"] * 6, [0.0] * 6)
-out.append(solver_case("config2 CG 256^3 Dirichlet", [256] * 3, "cg", D6, 50, 8))
-out.append(solver_case(f"config4 BiCGSTAB {N3}^3 mixed", [N3] * 3, "bicgstab", MIXED, 20, 17))
-out.append(solver_case(f"config4 Jacobi {N3}^3 mixed", [N3] * 3, "jacobi", MIXED, 50, 3))
-out.append(solver_case(f"Jacobi {N3}^3 Dirichlet", [N3] * 3, "jacobi", D6, 50, 3))
-out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet", [N3] * 3, "bicgstab", D6, 20, 17))
-out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet generic", [N3] * 3, "bicgstab", D6, 20, 17, variant=1))
-out.append(solver_case("CG 512^3 Dirichlet fp32", [512] * 3, "cg", D6, 50, 8, dtype="single"))
-out.append(solver_case("CG 1024^2 Dirichlet (2-D)", [1024, 1024], "cg", (["dirichlet"] * 4, [0.0] * 4), 200, 8))
-torch.set_default_dtype(torch.float64)
-out.append(euler_case("config3 Euler 256^3 upwind", [256] * 3, "upwind", 100))
-out.append(euler_case("config3 Euler 256^3 upwind_fd", [256] * 3, "upwind_fd", 100))
-out.append(euler_case("config3 Euler 1024^2 upwind", [1024, 1024], "upwind", 100))
-out.append(euler_case(f"Euler {N3}^3 upwind", [N3] * 3, "upwind", 20))
-for o in out:
-    print(json.dumps(o))
+if __name__ == "__main__":
+    out = []
+    N3 = 256 if quick else 512
+    D6 = (["dirichlet"] * 6, [0.0] * 6)
+    out.append(solver_case("config2 CG 256^3 Dirichlet", [256] * 3, "cg", D6, 50, 8))
+    out.append(solver_case(f"config4 BiCGSTAB {N3}^3 mixed", [N3] * 3, "bicgstab", MIXED, 20, 17))
+    out.append(solver_case(f"config4 Jacobi {N3}^3 mixed", [N3] * 3, "jacobi", MIXED, 50, 3))
+    out.append(solver_case(f"Jacobi {N3}^3 Dirichlet", [N3] * 3, "jacobi", D6, 50, 3))
+    out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet", [N3] * 3, "bicgstab", D6, 20, 17))
+    out.append(solver_case(f"BiCGSTAB {N3}^3 Dirichlet generic", [N3] * 3, "bicgstab", D6, 20, 17, variant=1))
+    out.append(solver_case("CG 512^3 Dirichlet fp32", [512] * 3, "cg", D6, 50, 8, dtype="single"))
+    out.append(solver_case("CG 1024^2 Dirichlet (2-D)", [1024, 1024], "cg", (["dirichlet"] * 4, [0.0] * 4), 200, 8))
+    torch.set_default_dtype(torch.float64)
+    out.append(euler_case("config3 Euler 256^3 upwind", [256] * 3, "upwind", 100))
+    out.append(euler_case("config3 Euler 256^3 upwind_fd", [256] * 3, "upwind_fd", 100))
+    out.append(euler_case("config3 Euler 1024^2 upwind", [1024, 1024], "upwind", 100))
+    out.append(euler_case(f"Euler {N3}^3 upwind", [N3] * 3, "upwind", 20))
+    for o in out:
+        print(json.dumps(o))
