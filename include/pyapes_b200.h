@@ -15,9 +15,9 @@
  *   - Plain C: pointers + sizes, no torch types.  All array pointers are DEVICE pointers
  *     unless the function name ends in `_host`.  `stream` is a cudaStream_t passed as void*.
  *   - Fields are contiguous row-major scalar fields (the reference's `(1, *nx)` tensor,
- *     variables/fields.py:52-58).  Meshes of dimension d<3 are embedded in kernel
- *     coordinates (n0,n1,n2) with LEADING singleton axes: mesh axis j -> kernel axis
- *     j + 3 - d, so the last (contiguous) axis is always kernel axis 2.
+ *     variables/fields.py:52-58).  Kernel coordinates are (n0,n1,n2) with kernel axis 2 the
+ *     contiguous one.  3-D meshes map axis j -> kernel axis j; 2-D meshes use kernel axes
+ *     (0, 2) (n1 = 1: the kernels march along axis 0); 1-D meshes use kernel axis 2.
  *   - dtype: PA_F64 (reference default) or PA_F32 (backend.py:28-42).
  *   - Every function returns 0 on success or a negative pa_status; pa_last_error() gives
  *     the message.  There is NO CPU fallback: without a CUDA device every compute entry
@@ -86,7 +86,7 @@ typedef struct {
   int32_t goff0;
   int32_t olo0;
   int32_t ohi0;
-  int32_t ndim; /* mesh dimension 1..3; active kernel axes are 3-ndim .. 2 */
+  int32_t ndim; /* mesh dimension 1..3; active kernel axes: 3 -> 0,1,2; 2 -> 0,2; 1 -> 2 */
   int32_t reserved;
 } pa_grid;
 

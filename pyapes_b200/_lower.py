@@ -17,9 +17,13 @@ from torch import Tensor
 from pyapes_b200 import _native as N
 
 
+_KERNEL_AXES = {1: (2,), 2: (0, 2), 3: (0, 1, 2)}
+
+
 def kernel_axis(mesh_axis: int, ndim: int) -> int:
-    """Mesh axis j -> kernel axis j + 3 - ndim (leading singleton axes for 1-D / 2-D)."""
-    return mesh_axis + 3 - ndim
+    """Mesh axis -> kernel axis.  Kernel axis 2 is the contiguous one; 2-D meshes use kernel axes
+    (0, 2) so that the kernels march along the first mesh axis."""
+    return _KERNEL_AXES[ndim][mesh_axis]
 
 
 def lower_grid(nx, bcs, slab=None) -> N.Grid:
@@ -27,9 +31,10 @@ def lower_grid(nx, bcs, slab=None) -> N.Grid:
     places a local block with ghost planes inside the global grid along kernel axis 0."""
     nd = len(nx)
     g = N.Grid()
-    n = [1] * (3 - nd) + [int(v) for v in nx]
-    lo = [0] * (3 - nd) + [1] * nd
-    hi = [1] * (3 - nd) + [int(v) - 1 for v in nx]
+    n, lo, hi = [1, 1, 1], [0, 0, 0], [1, 1, 1]
+    for j, v in enumerate(nx):
+        a = kernel_axis(j, nd)
+        n[a], lo[a], hi[a] = int(v), 1, int(v) - 1
     for bc in bcs or []:
         if bc.bc_type == "periodic":
             a = kernel_axis(bc.bc_face_dim, nd)

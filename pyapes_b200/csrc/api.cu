@@ -63,8 +63,8 @@ static int check_grid(const pa_grid* g) {
   if (g->ndim < 1 || g->ndim > 3) return fail(PA_ERR_ARG, "grid.ndim must be 1..3");
   for (int a = 0; a < 3; ++a) {
     if (g->n[a] < 1) return fail(PA_ERR_ARG, "grid.n must be >= 1");
-    if (a < 3 - g->ndim && g->n[a] != 1)
-      return fail(PA_ERR_ARG, "leading (inactive) kernel axes must have extent 1");
+    const bool active = (a == 2) || (a == 0 && g->ndim >= 2) || (a == 1 && g->ndim == 3);
+    if (!active && g->n[a] != 1) return fail(PA_ERR_ARG, "inactive kernel axes must have extent 1");
     if (g->lo[a] < 0 || g->hi[a] > g->n[a] || g->lo[a] > g->hi[a])
       return fail(PA_ERR_ARG, "grid.lo/hi out of range");
   }

@@ -32,8 +32,12 @@ inline GridDev make_grid(const pa_grid& g) {
     d.n[a] = g.n[a];
     d.lo[a] = g.lo[a];
     d.hi[a] = g.hi[a];
-    d.act[a] = (a >= 3 - g.ndim) ? 1 : 0;
   }
+  // mesh axis -> kernel axis: 3-D (0,1,2); 2-D (0,2) so that the march runs along the first mesh
+  // axis and the second is the contiguous one; 1-D (2)
+  d.act[0] = g.ndim >= 2;
+  d.act[1] = g.ndim == 3;
+  d.act[2] = 1;
   d.gn0 = g.gn0;
   d.goff0 = g.goff0;
   d.olo0 = g.olo0;

@@ -8,7 +8,7 @@
 //     a per-stage `full` mbarrier (expect_tx bytes).  Out-of-bounds halo cells are zero-filled
 //     by the TMA unit, which is exactly what a non-periodic edge needs (those values only
 //     reach cells outside the solver region, which are masked).
-//   * warps 0-7 are CONSUMERS: a thread owns RY consecutive rows x one 16-byte vector and keeps
+//   * warps 0-7 are CONSUMERS: a thread owns K::RY consecutive rows x one 16-byte vector and keeps
 //     planes x-1, x, x+1 of its cells in registers (3x unrolled loop: no register rotation);
 //     axis-1/axis-2 neighbours are read straight from the staged halo tile.  When a warp is
 //     done with a stage it arrives on that stage's `empty` mbarrier; the producer refills it.
@@ -29,22 +29,44 @@
 
 namespace pa {
 
-template <typename T, int RY_>
+// tile shapes: K::RY consecutive rows per thread; the 8 consumer warps are stacked along axis 1
+// (3-D meshes) or, FLAT, laid side by side along the contiguous axis (2-D meshes: n1 == 1, the
+// march runs along the first mesh axis and a "plane" is a single row)
+struct KStd {
+  static constexpr int RY = 2;
+  static constexpr bool FLAT = false;
+};
+struct KFlat {
+  static constexpr int RY = 1;
+  static constexpr bool FLAT = true;
+};
+
+template <typename T, typename K>
 struct TmaCfg {
   static constexpr int VEC = VecOf<T>::N;
-  static constexpr int RY = RY_;
-  static constexpr int CWARPS = 8;                 // consumer warps
+  static constexpr int RY = K::RY;
+  static constexpr bool FLAT = K::FLAT;
+  static constexpr int CWARPS = 8;                   // consumer warps
   static constexpr int THREADS = (CWARPS + 1) * 32;  // + producer warp
-  static constexpr int TY = CWARPS * RY;
-  static constexpr int TZ = 32 * VEC;
-  static constexpr int HZ = VEC;                   // z halo, keeps own cells 16-B aligned
-  static constexpr int BOXZ = TZ + 2 * HZ;
-  static constexpr int BOXY = TY + 2;
-  static constexpr int S = 4;                      // pipeline stages (power of two)
-  static constexpr int HALO_BYTES = BOXY * BOXZ * (int)sizeof(T);
-  static constexpr int OWN_BYTES = TY * TZ * (int)sizeof(T);
-  static constexpr int HALO_SLOT = (HALO_BYTES + 127) / 128 * 128;
-  static constexpr int OWN_SLOT = (OWN_BYTES + 127) / 128 * 128;
+  static constexpr int WZ = FLAT ? CWARPS : 1;       // warps along axis 2
+  static constexpr int TY = FLAT ? 1 : CWARPS * RY;
+  static constexpr int TZ = WZ * 32 * VEC;
+  static constexpr int HZ = VEC;                     // z halo, keeps own cells 16-B aligned
+  // A TMA box dimension is limited to 256 elements, so a FLAT tile (512 cells wide) is staged as
+  // NB boxes, one per consumer warp, each with its own z halo.
+  static constexpr int NB = FLAT ? CWARPS : 1;
+  static constexpr int OBOXZ = TZ / NB;              // own-tile box width
+  static constexpr int BOXZ = OBOXZ + 2 * HZ;        // halo box width
+  static constexpr int BOXY = FLAT ? 1 : TY + 2;     // no axis-1 halo when axis 1 is inactive
+  static constexpr int S = 4;                        // pipeline stages (power of two)
+  static constexpr int HBOX_BYTES = BOXY * BOXZ * (int)sizeof(T);
+  static constexpr int OBOX_BYTES = TY * OBOXZ * (int)sizeof(T);
+  static constexpr int HBOX_SLOT = (HBOX_BYTES + 127) / 128 * 128;
+  static constexpr int OBOX_SLOT = (OBOX_BYTES + 127) / 128 * 128;
+  static constexpr int HALO_BYTES = NB * HBOX_BYTES;  // bytes one stage's halo tile transfers
+  static constexpr int OWN_BYTES = NB * OBOX_BYTES;
+  static constexpr int HALO_SLOT = NB * HBOX_SLOT;
+  static constexpr int OWN_SLOT = NB * OBOX_SLOT;
   static constexpr int STAGE_A = 2 * HALO_SLOT;              // r halo, d halo
   static constexpr int STAGE_B = HALO_SLOT + 2 * OWN_SLOT;   // d halo, x own, r own
   static constexpr int BAR_BYTES = 128;                      // 2*S mbarriers
@@ -52,7 +74,6 @@ struct TmaCfg {
   static constexpr size_t SMEM_B = (size_t)S * STAGE_B + BAR_BYTES + 128;
 };
 
-constexpr int kTmaRY = 2;
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -137,24 +158,14 @@ struct TmaPlan {
   CUtensorMap d_halo[2];    // the two d buffers
 };
 
-template <typename T>
-inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
-                     const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
-  typedef TmaCfg<T, kTmaRY> C;
-  if (eq.nops != 1 || eq.ops[0].kind != PA_OP_STAR || eq.ops[0].param_field != nullptr || eq.ops[0].edge != 0 || eq.ops[0].coef_tab[0] || eq.ops[0].coef_tab[1] || eq.ops[0].coef_tab[2]) return false;
-  if (!g.act[1] || !g.act[2]) return false;
-  if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
-  for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
-    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
-  TilePlan& p = tp.tile;
-  p.ry = kTmaRY;
-  p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;
-  p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
-  const int tiles = p.tiles_y * p.tiles_z;
+// wave-aware chunking along axis 0 (shared by the CG and the star-engine plans)
+inline void tma_chunks(const GridDev& g, int tiles, TilePlan& p) {
   const int slots = kNumSMs * 2;
   int best_c = 1;
   double best = -1.0;
-  const int maxc = g.n[0] >= 16 ? g.n[0] / 8 : 1;
+  // chunks of >= 8 planes, except on small grids where filling the SMs matters more than the
+  // two halo planes a chunk re-reads
+  const int maxc = (long long)tiles * (g.n[0] / 8) >= slots ? g.n[0] / 8 : (g.n[0] >= 4 ? g.n[0] / 2 : 1);
   for (int c = 1; c <= maxc; ++c) {
     const int cx = (g.n[0] + c - 1) / c;
     const int cc = (g.n[0] + cx - 1) / cx;
@@ -177,44 +188,79 @@ inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const 
   p.chunk0 = 0;
   p.chunk_step = 1;
   p.accum = 0;
-  bool ok = make_map<T>(&tp.x_own[0], x, g, C::TZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::TZ, C::TY) &&
-            make_map<T>(&tp.r_own, r, g, C::TZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
-            make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) &&
-            make_map<T>(&tp.d_halo[1], d1, g, C::BOXZ, C::BOXY);
-  return ok;
+}
+
+// 3-D meshes: tiles of the (axis1, axis2) plane; 2-D meshes (axis 1 inactive): FLAT row tiles
+inline bool tma_flat(const GridDev& g) { return !g.act[1]; }
+
+template <typename T, typename K>
+inline bool plan_tma_k(const GridDev& g, const T* x, const T* x_alt, const T* r, const T* d0, const T* d1,
+                       TmaPlan& tp) {
+  typedef TmaCfg<T, K> C;
+  if (g.n[2] % C::VEC != 0 || g.n[2] < 2 * C::VEC) return false;
+  if (!C::FLAT && g.n[1] < 4) return false;
+  TilePlan& p = tp.tile;
+  p.ry = K::RY;
+  p.tiles_y = C::FLAT ? 1 : (g.n[1] + C::TY - 1) / C::TY;
+  p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
+  tma_chunks(g, p.tiles_y * p.tiles_z, p);
+  return make_map<T>(&tp.x_own[0], x, g, C::OBOXZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::OBOXZ, C::TY) &&
+         make_map<T>(&tp.r_own, r, g, C::OBOXZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
+         make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) && make_map<T>(&tp.d_halo[1], d1, g, C::BOXZ, C::BOXY);
+}
+
+template <typename T>
+inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
+                     const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
+  const pa_op& o = eq.ops[0];
+  if (eq.nops != 1 || o.kind != PA_OP_STAR || o.param_field != nullptr || o.edge != 0 || o.coef_tab[0] ||
+      o.coef_tab[1] || o.coef_tab[2])
+    return false;
+  if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;  // 1-D meshes stay on the generic kernels
+  for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
+    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
+  return tma_flat(g) ? plan_tma_k<T, KFlat>(g, x, x_alt, r, d0, d1, tp)
+                     : plan_tma_k<T, KStd>(g, x, x_alt, r, d0, d1, tp);
 }
 
 // ---- consumer-side geometry -----------------------------------------------------------------------
-template <typename T, int RY>
+template <typename T, typename K>
 struct ConsCtx {
   int lane, warp;
   int hoff;   // element offset of (own row 0, own element 0) inside a halo tile
   int ooff;   // same inside an own tile
   long long goff;  // element offset of (own row 0, element 0) inside a global plane
   unsigned valid, inreg, nonshell;  // bit k*VEC+e   (GENERAL path)
-  int cly[RY], clz[VecOf<T>::N];
+  int cly[K::RY], clz[VecOf<T>::N];
 };
 
-template <typename T, int RY>
-__device__ __forceinline__ void cons_setup(const GridDev& g, ConsCtx<T, RY>& c, int y0, int z0) {
-  typedef TmaCfg<T, RY> C;
+template <typename T, typename K>
+__device__ __forceinline__ void cons_setup(const GridDev& g, ConsCtx<T, K>& c, int y0, int z0) {
+  typedef TmaCfg<T, K> C;
   c.lane = threadIdx.x & 31;
   c.warp = threadIdx.x >> 5;
-  c.hoff = (c.warp * RY + 1) * C::BOXZ + C::HZ + c.lane * C::VEC;
-  c.ooff = (c.warp * RY) * C::TZ + c.lane * C::VEC;
-  const int yb = y0 + c.warp * RY, zg = z0 + c.lane * C::VEC;
+  const int wy = C::FLAT ? 0 : c.warp, wz = C::FLAT ? c.warp : 0;
+  const int col = (wz * 32 + c.lane) * C::VEC;
+  if (C::FLAT) {  // one box per warp
+    c.hoff = wz * (C::HBOX_SLOT / (int)sizeof(T)) + C::HZ + c.lane * C::VEC;
+    c.ooff = wz * (C::OBOX_SLOT / (int)sizeof(T)) + c.lane * C::VEC;
+  } else {
+    c.hoff = (wy * K::RY + 1) * C::BOXZ + C::HZ + col;
+    c.ooff = (wy * K::RY) * C::OBOXZ + col;
+  }
+  const int yb = y0 + wy * K::RY, zg = z0 + col;
   c.goff = (long long)yb * g.n[2] + zg;
   c.valid = c.inreg = c.nonshell = 0u;
 #pragma unroll
-  for (int k = 0; k < RY; ++k) {
+  for (int k = 0; k < K::RY; ++k) {
     const int y = yb + k;
-    c.cly[k] = (y < g.n[1]) ? coef_class(g, 1, y) : 0;
+    c.cly[k] = (!C::FLAT && y < g.n[1]) ? coef_class(g, 1, y) : 0;
 #pragma unroll
     for (int e = 0; e < C::VEC; ++e) {
       const int z = zg + e;
       const bool v = (y < g.n[1]) && (z < g.n[2]);
       const bool rg = v && y >= g.lo[1] && y < g.hi[1] && z >= g.lo[2] && z < g.hi[2];
-      const bool ns = v && y != 0 && y != g.n[1] - 1 && z != 0 && z != g.n[2] - 1;
+      const bool ns = v && (C::FLAT || (y != 0 && y != g.n[1] - 1)) && z != 0 && z != g.n[2] - 1;
       const unsigned bit = 1u << (k * C::VEC + e);
       if (v) c.valid |= bit;
       if (rg) c.inreg |= bit;
@@ -234,8 +280,8 @@ __device__ __forceinline__ void lds_vec(const T* p, T (&v)[VecOf<T>::N]) {
   for (int e = 0; e < VecOf<T>::N; ++e) v[e] = s[e];
 }
 
-template <typename T, int RY, bool LEAN>
-__device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, RY>& c, int k, const T (&v)[VecOf<T>::N]) {
+template <typename T, typename K, bool LEAN>
+__device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, const T (&v)[VecOf<T>::N]) {
   typedef typename VecOf<T>::type V;
   constexpr int N = VecOf<T>::N;
   const unsigned m = (c.valid >> (k * N)) & ((1u << N) - 1u);
@@ -253,15 +299,15 @@ __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, RY>& c, int k, co
 }
 
 // the star operator on the thread's cells (same arithmetic order as eval_equation)
-template <typename T, int RY, bool LEAN, typename F>
-__device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, RY>& c, const T (&cx)[3],
-                                           bool actx, const T (&vm)[RY][VecOf<T>::N],
-                                           const T (&vc)[RY][VecOf<T>::N], const T (&vp)[RY][VecOf<T>::N],
+template <typename T, typename K, bool LEAN, typename F>
+__device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K>& c, const T (&cx)[3],
+                                           bool actx, const T (&vm)[K::RY][VecOf<T>::N],
+                                           const T (&vc)[K::RY][VecOf<T>::N], const T (&vp)[K::RY][VecOf<T>::N],
                                            const T (&up)[VecOf<T>::N], const T (&dn)[VecOf<T>::N],
-                                           const T (&zl)[RY], const T (&zr)[RY], F emit) {
+                                           const T (&zl)[K::RY], const T (&zr)[K::RY], F emit) {
   constexpr int VEC = VecOf<T>::N;
 #pragma unroll
-  for (int k = 0; k < RY; ++k) {
+  for (int k = 0; k < K::RY; ++k) {
     const int cy = LEAN ? 0 : c.cly[k];
     const T yap = o.coef[1][cy][0], yac = o.coef[1][cy][1], yam = o.coef[1][cy][2];
 #pragma unroll
@@ -269,7 +315,7 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, R
       const int cz = LEAN ? 0 : c.clz[e];
       const T zap = o.coef[2][cz][0], zac = o.coef[2][cz][1], zam = o.coef[2][cz][2];
       const T v0 = vc[k][e];
-      const T yp = (k == RY - 1) ? dn[e] : vc[k + 1 < RY ? k + 1 : k][e];
+      const T yp = (k == K::RY - 1) ? dn[e] : vc[k + 1 < K::RY ? k + 1 : k][e];
       const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
       const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
       const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
@@ -280,7 +326,7 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, R
         s = s + cx[2] * vm[k][e];
         acc = acc + s;
       }
-      {
+      if (!K::FLAT) {
         T s = yap * yp;
         s = s + yac * v0;
         s = s + yam * ym;
@@ -303,15 +349,15 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, R
 // =========================================================================================
 // phase B
 // =========================================================================================
-template <typename T, int RY, bool LEAN>
+template <typename T, typename K, bool LEAN>
 __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ x_new, T* __restrict__ r, T alpha,
                                               unsigned char* stages, uint64_t* full, uint64_t* empty,
                                               int y0, int z0, int x0, int x1, double (&acc_out)[2]) {
-  typedef TmaCfg<T, RY> C;
+  typedef TmaCfg<T, K> C;
   constexpr int VEC = C::VEC;
-  ConsCtx<T, RY> c;
-  cons_setup<T, RY>(g, c, y0, z0);
+  ConsCtx<T, K> c;
+  cons_setup<T, K>(g, c, y0, z0);
   const bool actx = g.act[0] != 0;
   const long long n12 = (long long)g.n[1] * g.n[2];
   T* xo = x_new + (long long)x0 * n12 + c.goff;
@@ -322,17 +368,17 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
   auto ownr = [&](int s) {
     return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B + C::HALO_SLOT + C::OWN_SLOT);
   };
-  auto load_own = [&](int s, T (&v)[RY][VEC]) {
+  auto load_own = [&](int s, T (&v)[K::RY][VEC]) {
     const T* h = halo(s) + c.hoff;
 #pragma unroll
-    for (int k = 0; k < RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
+    for (int k = 0; k < K::RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
   };
   auto release = [&](int s) {
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&empty[s]);
   };
 
-  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
   double a0 = 0.0, a1 = 0.0;
 
   // prologue: plane x0-1 (counter 0) -> A ; plane x0 (counter 1) -> B
@@ -344,7 +390,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
   mbar_wait(&full[1 % C::S], 0);
   load_own(1 % C::S, B);
 
-  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
     // i = pipeline counter of plane x+1; plane x sits in stage (i-1)%S
     const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
     if (actx) {
@@ -357,27 +403,32 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
     if (xreg) {
-      T ad[RY][VEC];
+      T ad[K::RY][VEC];
       {
-        T up[VEC], dn[VEC], zl[RY], zr[RY];
-        lds_vec<T>(h - C::BOXZ, up);
-        lds_vec<T>(h + RY * C::BOXZ, dn);
+        T up[VEC], dn[VEC], zl[K::RY], zr[K::RY];
+        if (!K::FLAT) {
+          lds_vec<T>(h - C::BOXZ, up);
+          lds_vec<T>(h + K::RY * C::BOXZ, dn);
+        } else {
 #pragma unroll
-        for (int k = 0; k < RY; ++k) {
+          for (int e = 0; e < VEC; ++e) up[e] = dn[e] = (T)0;
+        }
+#pragma unroll
+        for (int k = 0; k < K::RY; ++k) {
           zl[k] = h[k * C::BOXZ - 1];
           zr[k] = h[k * C::BOXZ + VEC];
         }
         const int clx = actx ? coef_class(g, 0, x) : 0;
         const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
-        star_cells<T, RY, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr,
+        star_cells<T, K, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr,
                                 [&](int k, int e, T v) { ad[k][e] = v; });
       }
       // x and r of this plane are only needed now: keep their live range short
 #pragma unroll
-      for (int k = 0; k < RY; ++k) {
+      for (int k = 0; k < K::RY; ++k) {
         T xv[VEC], rv[VEC], xn[VEC], rn[VEC];
-        lds_vec<T>(ownx(sc) + c.ooff + k * C::TZ, xv);
-        lds_vec<T>(ownr(sc) + c.ooff + k * C::TZ, rv);
+        lds_vec<T>(ownx(sc) + c.ooff + k * C::OBOXZ, xv);
+        lds_vec<T>(ownr(sc) + c.ooff + k * C::OBOXZ, rv);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const bool in = LEAN || ((c.inreg >> (k * VEC + e)) & 1u);
@@ -396,15 +447,15 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
             }
           }
         }
-        stg_row<T, RY, LEAN>(xo + (long long)k * g.n[2], c, k, xn);
-        stg_row<T, RY, LEAN>(ro + (long long)k * g.n[2], c, k, rn);
+        stg_row<T, K, LEAN>(xo + (long long)k * g.n[2], c, k, xn);
+        stg_row<T, K, LEAN>(ro + (long long)k * g.n[2], c, k, rn);
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < RY; ++k) {
+      for (int k = 0; k < K::RY; ++k) {
         T xv[VEC];
-        lds_vec<T>(ownx(sc) + c.ooff + k * C::TZ, xv);
-        stg_row<T, RY, LEAN>(xo + (long long)k * g.n[2], c, k, xv);
+        lds_vec<T>(ownx(sc) + c.ooff + k * C::OBOXZ, xv);
+        stg_row<T, K, LEAN>(xo + (long long)k * g.n[2], c, k, xv);
       }
     }
     xo += n12;
@@ -428,12 +479,12 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
   acc_out[1] = a1;
 }
 
-template <typename T, int RY>
-__global__ void __launch_bounds__(TmaCfg<T, RY>::THREADS, 2)
+template <typename T, typename K>
+__global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_r, TilePlan p, GridDev g, OpDev<T> o,
                 T* __restrict__ x_new, T* __restrict__ r, SolverState* st, double* partials) {
-  typedef TmaCfg<T, RY> C;
+  typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
@@ -466,21 +517,24 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
         mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? 2 * C::OWN_BYTES : 0)));
         unsigned char* sb = stages + (size_t)s * C::STAGE_B;
         const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
-        tma_load_3d(sb, &tm_d, z0 - C::HZ, y0 - 1, xw, &full[s]);
-        if (inner) {
-          tma_load_3d(sb + C::HALO_SLOT, &tm_x, z0, y0, xw, &full[s]);
-          tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT, &tm_r, z0, y0, xw, &full[s]);
+        for (int b = 0; b < C::NB; ++b) {
+          const int zb = z0 + b * C::OBOXZ;
+          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_d, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          if (inner) {
+            tma_load_3d(sb + C::HALO_SLOT + b * C::OBOX_SLOT, &tm_x, zb, y0, xw, &full[s]);
+            tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT + b * C::OBOX_SLOT, &tm_r, zb, y0, xw, &full[s]);
+          }
         }
       }
     }
   } else {
     const T alpha = (T)st->scal[S_ALPHA];
-    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
     if (full_tile && !edge)
-      tmaB_consumer<T, RY, true>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+      tmaB_consumer<T, K, true>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
     else
-      tmaB_consumer<T, RY, false>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+      tmaB_consumer<T, K, false>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -495,15 +549,15 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
 // =========================================================================================
 // phase A
 // =========================================================================================
-template <typename T, int RY, bool LEAN>
+template <typename T, typename K, bool LEAN>
 __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ d_new, T beta, unsigned char* stages,
                                               uint64_t* full, uint64_t* empty, int y0, int z0, int x0,
                                               int x1, double& acc_out) {
-  typedef TmaCfg<T, RY> C;
+  typedef TmaCfg<T, K> C;
   constexpr int VEC = C::VEC;
-  ConsCtx<T, RY> c;
-  cons_setup<T, RY>(g, c, y0, z0);
+  ConsCtx<T, K> c;
+  cons_setup<T, K>(g, c, y0, z0);
   const bool actx = g.act[0] != 0;
   const long long n12 = (long long)g.n[1] * g.n[2];
   T* dout = d_new + (long long)x0 * n12 + c.goff;
@@ -513,11 +567,11 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
     return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_A + C::HALO_SLOT) + c.hoff;
   };
   // d_new = r + beta*d on the thread's own cells of the plane in stage s   (linalg.py:141)
-  auto own_dn = [&](int s, T (&v)[RY][VEC]) {
+  auto own_dn = [&](int s, T (&v)[K::RY][VEC]) {
     const T* rp = rt(s);
     const T* dp = dt(s);
 #pragma unroll
-    for (int k = 0; k < RY; ++k) {
+    for (int k = 0; k < K::RY; ++k) {
       T a[VEC], b[VEC];
       lds_vec<T>(rp + k * C::BOXZ, a);
       lds_vec<T>(dp + k * C::BOXZ, b);
@@ -525,9 +579,9 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       for (int e = 0; e < VEC; ++e) v[k][e] = a[e] + beta * b[e];
     }
   };
-  auto write_d = [&](const T (&v)[RY][VEC]) {
+  auto write_d = [&](const T (&v)[K::RY][VEC]) {
 #pragma unroll
-    for (int k = 0; k < RY; ++k) stg_row<T, RY, LEAN>(dout + (long long)k * g.n[2], c, k, v[k]);
+    for (int k = 0; k < K::RY; ++k) stg_row<T, K, LEAN>(dout + (long long)k * g.n[2], c, k, v[k]);
     dout += n12;
   };
   auto release = [&](int s) {
@@ -535,7 +589,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
     if (c.lane == 0) mbar_arrive(&empty[s]);
   };
 
-  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
   double acc = 0.0;
 
   if (actx) {
@@ -547,7 +601,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
   own_dn(1 % C::S, B);
   write_d(B);
 
-  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
     const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
     if (actx) {
       mbar_wait(&full[sn], (i / C::S) & 1);
@@ -559,27 +613,30 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       // halo neighbours of the centre plane: recomputed from the staged raw r, d
       const T* rp = rt(sc);
       const T* dp = dt(sc);
-      T up[VEC], dn[VEC], zl[RY], zr[RY];
-      {
+      T up[VEC], dn[VEC], zl[K::RY], zr[K::RY];
+      if (!K::FLAT) {
         T a[VEC], b[VEC];
         lds_vec<T>(rp - C::BOXZ, a);
         lds_vec<T>(dp - C::BOXZ, b);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) up[e] = a[e] + beta * b[e];
-        lds_vec<T>(rp + RY * C::BOXZ, a);
-        lds_vec<T>(dp + RY * C::BOXZ, b);
+        lds_vec<T>(rp + K::RY * C::BOXZ, a);
+        lds_vec<T>(dp + K::RY * C::BOXZ, b);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) dn[e] = a[e] + beta * b[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) up[e] = dn[e] = (T)0;
       }
 #pragma unroll
-      for (int k = 0; k < RY; ++k) {
+      for (int k = 0; k < K::RY; ++k) {
         zl[k] = rp[k * C::BOXZ - 1] + beta * dp[k * C::BOXZ - 1];
         zr[k] = rp[k * C::BOXZ + VEC] + beta * dp[k * C::BOXZ + VEC];
       }
       const int clx = actx ? coef_class(g, 0, x) : 0;
       const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
       // d == 0 outside the solver region: d*Ad needs no region mask, only array bounds
-      star_cells<T, RY, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T ad) {
+      star_cells<T, K, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T ad) {
         if (LEAN || ((c.valid >> (k * VEC + e)) & 1u)) {
           const T q = vc[k][e] * ad;
           acc += (double)q;
@@ -604,12 +661,12 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
   acc_out = acc;
 }
 
-template <typename T, int RY>
-__global__ void __launch_bounds__(TmaCfg<T, RY>::THREADS, 2)
+template <typename T, typename K>
+__global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_d,
                 TilePlan p, GridDev g, OpDev<T> o, T* __restrict__ d_new, SolverState* st,
                 double* partials) {
-  typedef TmaCfg<T, RY> C;
+  typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
@@ -640,18 +697,21 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
         mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
         unsigned char* sb = stages + (size_t)s * C::STAGE_A;
         const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
-        tma_load_3d(sb, &tm_r, z0 - C::HZ, y0 - 1, xw, &full[s]);
-        tma_load_3d(sb + C::HALO_SLOT, &tm_d, z0 - C::HZ, y0 - 1, xw, &full[s]);
+        for (int b = 0; b < C::NB; ++b) {
+          const int zb = z0 + b * C::OBOXZ;
+          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, &tm_d, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+        }
       }
     }
   } else {
     const T beta = (T)st->scal[S_BETA];
-    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
     if (full_tile && !edge)
-      tmaA_consumer<T, RY, true>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+      tmaA_consumer<T, K, true>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
     else
-      tmaA_consumer<T, RY, false>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+      tmaA_consumer<T, K, false>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -659,27 +719,36 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-template <typename T>
-void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
-                                 int parity, T* d_new, SolverState* st, double* partials) {
-  typedef TmaCfg<T, kTmaRY> C;
+template <typename T, typename K>
+static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                                   int parity, T* d_new, SolverState* st, double* partials) {
+  typedef TmaCfg<T, K> C;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseA_tma<T, kTmaRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
+    cudaFuncSetAttribute(k_cg_phaseA_tma<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
     attr = true;
   }
   dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
-  k_cg_phaseA_tma<T, kTmaRY><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tp.tile, g,
-                                                                eq.op[0], d_new, st, partials);
+  k_cg_phaseA_tma<T, K><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tp.tile, g, eq.op[0],
+                                                           d_new, st, partials);
 }
 
 template <typename T>
-void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
-                                 int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
-  typedef TmaCfg<T, kTmaRY> C;
+void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                          int parity, T* d_new, SolverState* st, double* partials) {
+  if (tma_flat(g))
+    launch_cg_phaseA_tma_k<T, KFlat>(s, tp, g, eq, parity, d_new, st, partials);
+  else
+    launch_cg_phaseA_tma_k<T, KStd>(s, tp, g, eq, parity, d_new, st, partials);
+}
+
+template <typename T, typename K>
+static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                                   int parity, T* x_new, T* r, SolverState* st, double* partials, int sub) {
+  typedef TmaCfg<T, K> C;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseB_tma<T, kTmaRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
+    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;
   }
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
@@ -696,8 +765,17 @@ void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, c
     nz = tile.chunks - 2;
   }
   dim3 grid(tile.tiles_z, tile.tiles_y, nz);
-  k_cg_phaseB_tma<T, kTmaRY><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own,
-                                                                tile, g, eq.op[0], x_new, r, st, partials);
+  k_cg_phaseB_tma<T, K><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
+                                                           g, eq.op[0], x_new, r, st, partials);
+}
+
+template <typename T>
+void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
+                          int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
+  if (tma_flat(g))
+    launch_cg_phaseB_tma_k<T, KFlat>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+  else
+    launch_cg_phaseB_tma_k<T, KStd>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
 }
 
 }  // namespace pa

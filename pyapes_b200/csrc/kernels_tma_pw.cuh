@@ -18,9 +18,9 @@ enum PwMode {
   PW_APPLY_T = 4,  // out = A(in) ...; sums out*in, out*out, r0*out; skipped when finished_flag
 };
 
-template <typename T, int RY_>
-struct PwCfg : TmaCfg<T, RY_> {
-  typedef TmaCfg<T, RY_> B;
+template <typename T, typename K>
+struct PwCfg : TmaCfg<T, K> {
+  typedef TmaCfg<T, K> B;
   static constexpr int STAGE = B::HALO_SLOT + B::OWN_SLOT;  // in halo, aux own
   static constexpr size_t SMEM = (size_t)B::S * STAGE + B::BAR_BYTES + 128;
 };
@@ -33,22 +33,22 @@ struct PwPlan {
 };
 
 // sum over operators of sign*param*(star), reference order (ops.py:130-149, fdc.py:103-108)
-template <typename T, int RY, bool LEAN, int NOPS, typename F>
-__device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<T, RY>& c, int clx,
-                                              bool actx, const T (&vm)[RY][VecOf<T>::N],
-                                              const T (&vc)[RY][VecOf<T>::N],
-                                              const T (&vp)[RY][VecOf<T>::N], const T (&up)[VecOf<T>::N],
-                                              const T (&dn)[VecOf<T>::N], const T (&zl)[RY],
-                                              const T (&zr)[RY], F emit) {
+template <typename T, typename K, bool LEAN, int NOPS, typename F>
+__device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<T, K>& c, int clx,
+                                              bool actx, const T (&vm)[K::RY][VecOf<T>::N],
+                                              const T (&vc)[K::RY][VecOf<T>::N],
+                                              const T (&vp)[K::RY][VecOf<T>::N], const T (&up)[VecOf<T>::N],
+                                              const T (&dn)[VecOf<T>::N], const T (&zl)[K::RY],
+                                              const T (&zr)[K::RY], F emit) {
   constexpr int VEC = VecOf<T>::N;
 #pragma unroll
-  for (int k = 0; k < RY; ++k) {
+  for (int k = 0; k < K::RY; ++k) {
     const int cy = LEAN ? 0 : c.cly[k];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const int cz = LEAN ? 0 : c.clz[e];
       const T v0 = vc[k][e];
-      const T yp = (k == RY - 1) ? dn[e] : vc[k + 1 < RY ? k + 1 : k][e];
+      const T yp = (k == K::RY - 1) ? dn[e] : vc[k + 1 < K::RY ? k + 1 : k][e];
       const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
       const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
       const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
@@ -65,7 +65,7 @@ __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<
           acc = acc + s;
           dacc = dacc + o.coef[0][clx][1];
         }
-        {
+        if (!K::FLAT) {
           T s = o.coef[1][cy][0] * yp;
           s = s + o.coef[1][cy][1] * v0;
           s = s + o.coef[1][cy][2] * ym;
@@ -93,15 +93,15 @@ __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<
   }
 }
 
-template <typename T, int RY, int MODE, bool LEAN, int NOPS>
+template <typename T, typename K, int MODE, bool LEAN, int NOPS>
 __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
                                             T* __restrict__ out, T* __restrict__ out2, T dt, bool has_aux,
                                             unsigned char* stages, uint64_t* full, uint64_t* empty,
                                             int y0, int z0, int x0, int x1, double (&acc_out)[3]) {
-  typedef PwCfg<T, RY> C;
+  typedef PwCfg<T, K> C;
   constexpr int VEC = C::VEC;
-  ConsCtx<T, RY> c;
-  cons_setup<T, RY>(g, c, y0, z0);
+  ConsCtx<T, K> c;
+  cons_setup<T, K>(g, c, y0, z0);
   const bool actx = g.act[0] != 0;
   const long long n12 = (long long)g.n[1] * g.n[2];
   T* op_ = out + (long long)x0 * n12 + c.goff;
@@ -109,17 +109,17 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
 
   auto halo = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE); };
   auto aux = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE + C::HALO_SLOT); };
-  auto load_own = [&](int s, T (&v)[RY][VEC]) {
+  auto load_own = [&](int s, T (&v)[K::RY][VEC]) {
     const T* h = halo(s) + c.hoff;
 #pragma unroll
-    for (int k = 0; k < RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
+    for (int k = 0; k < K::RY; ++k) lds_vec<T>(h + k * C::BOXZ, v[k]);
   };
   auto release = [&](int s) {
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&empty[s]);
   };
 
-  T A[RY][VEC], B[RY][VEC], Cc[RY][VEC];
+  T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   if (actx) {
     mbar_wait(&full[0], 0);
@@ -129,7 +129,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
   mbar_wait(&full[1 % C::S], 0);
   load_own(1 % C::S, B);
 
-  auto step = [&](T (&vm)[RY][VEC], T (&vc)[RY][VEC], T (&vp)[RY][VEC], int x, int i) {
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
     const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
     if (actx) {
       mbar_wait(&full[sn], (i / C::S) & 1);
@@ -140,27 +140,32 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
     const bool xown = x >= g.olo0 && x < g.ohi0;
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
-    T ax[RY][VEC], dg[RY][VEC];
+    T ax[K::RY][VEC], dg[K::RY][VEC];
     if (xreg) {
-      T up[VEC], dn[VEC], zl[RY], zr[RY];
-      lds_vec<T>(h - C::BOXZ, up);
-      lds_vec<T>(h + RY * C::BOXZ, dn);
+      T up[VEC], dn[VEC], zl[K::RY], zr[K::RY];
+      if (!K::FLAT) {
+        lds_vec<T>(h - C::BOXZ, up);
+        lds_vec<T>(h + K::RY * C::BOXZ, dn);
+      } else {
 #pragma unroll
-      for (int k = 0; k < RY; ++k) {
+        for (int e = 0; e < VEC; ++e) up[e] = dn[e] = (T)0;
+      }
+#pragma unroll
+      for (int k = 0; k < K::RY; ++k) {
         zl[k] = h[k * C::BOXZ - 1];
         zr[k] = h[k * C::BOXZ + VEC];
       }
       const int clx = actx ? coef_class(g, 0, x) : 0;
-      star_cells_eq<T, RY, LEAN, NOPS>(eq, c, clx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T v, T d) {
+      star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T v, T d) {
         ax[k][e] = v;
         dg[k][e] = d;
       });
     }
 #pragma unroll
-    for (int k = 0; k < RY; ++k) {
+    for (int k = 0; k < K::RY; ++k) {
       T av[VEC], o[VEC];
       if (has_aux) {
-        lds_vec<T>(aux(sc) + c.ooff + k * C::TZ, av);
+        lds_vec<T>(aux(sc) + c.ooff + k * C::OBOXZ, av);
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) av[e] = (T)0;
@@ -211,8 +216,8 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           }
         }
       }
-      stg_row<T, RY, LEAN>(op_ + (long long)k * g.n[2], c, k, o);
-      if (MODE == PW_RESID && op2_) stg_row<T, RY, LEAN>(op2_ + (long long)k * g.n[2], c, k, o);
+      stg_row<T, K, LEAN>(op_ + (long long)k * g.n[2], c, k, o);
+      if (MODE == PW_RESID && op2_) stg_row<T, K, LEAN>(op2_ + (long long)k * g.n[2], c, k, o);
     }
     op_ += n12;
     if (op2_) op2_ += n12;
@@ -236,7 +241,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
     for (; x < x1; ++x, ++i) {
       step(A, B, Cc, x, i);
 #pragma unroll
-      for (int k = 0; k < RY; ++k)
+      for (int k = 0; k < K::RY; ++k)
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           A[k][e] = B[k][e];
@@ -249,12 +254,12 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
   acc_out[2] = a2;
 }
 
-template <typename T, int RY, int MODE, int NOPS>
-__global__ void __launch_bounds__(PwCfg<T, RY>::THREADS, 2)
+template <typename T, typename K, int MODE, int NOPS>
+__global__ void __launch_bounds__(PwCfg<T, K>::THREADS, 2)
 k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_aux,
            TilePlan p, GridDev g, EqDev<T> eq, T* __restrict__ out, T* __restrict__ out2, T dt,
            int has_aux, SolverState* st, double* partials, int stage) {
-  typedef PwCfg<T, RY> C;
+  typedef PwCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st != nullptr && st->done) return;
   if (MODE == PW_APPLY_T && st->finished_flag) return;
@@ -287,18 +292,21 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
         mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? C::OWN_BYTES : 0)));
         unsigned char* sb = stages + (size_t)s * C::STAGE;
         const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
-        tma_load_3d(sb, &tm_in, z0 - C::HZ, y0 - 1, xw, &full[s]);
-        if (inner) tma_load_3d(sb + C::HALO_SLOT, &tm_aux, z0, y0, xw, &full[s]);
+        for (int b = 0; b < C::NB; ++b) {
+          const int zb = z0 + b * C::OBOXZ;
+          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_in, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          if (inner) tma_load_3d(sb + C::HALO_SLOT + b * C::OBOX_SLOT, &tm_aux, zb, y0, xw, &full[s]);
+        }
       }
     }
   } else {
-    const bool full_tile = (y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (y0 < 2) || (y0 + C::TY > g.n[1] - 2) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
     if (full_tile && !edge)
-      pw_consumer<T, RY, MODE, true, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
+      pw_consumer<T, K, MODE, true, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                            x1, acc);
     else
-      pw_consumer<T, RY, MODE, false, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
+      pw_consumer<T, K, MODE, false, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                             x1, acc);
   }
   if (MODE == PW_EULER) return;  // no reductions
@@ -310,12 +318,17 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
 // ---- host ------------------------------------------------------------------------------------
 template <typename T>
 inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces) {
-  typedef PwCfg<T, kTmaRY> C;
+  constexpr int VEC = VecOf<T>::N;
   if (eq.nops < 1 || eq.nops > PA_MAX_OPS) return false;
-  for (int k = 0; k < eq.nops; ++k)
-    if (eq.ops[k].kind != PA_OP_STAR || eq.ops[k].param_field != nullptr || eq.ops[k].edge != 0 || eq.ops[k].coef_tab[0] || eq.ops[k].coef_tab[1] || eq.ops[k].coef_tab[2]) return false;
-  if (!g.act[1] || !g.act[2]) return false;
-  if (g.n[2] % C::VEC != 0 || g.n[1] < 4 || g.n[2] < 2 * C::VEC) return false;
+  for (int k = 0; k < eq.nops; ++k) {
+    const pa_op& o = eq.ops[k];
+    if (o.kind != PA_OP_STAR || o.param_field != nullptr || o.edge != 0 || o.coef_tab[0] || o.coef_tab[1] ||
+        o.coef_tab[2])
+      return false;
+  }
+  if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;
+  if (g.n[2] % VEC != 0 || g.n[2] < 2 * VEC) return false;
+  if (g.act[1] && g.n[1] < 4) return false;
   for (int f = 0; f < nfaces; ++f)
     if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
   return encode_tiled_fn() != nullptr;
@@ -323,72 +336,55 @@ inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, con
 
 template <typename T>
 inline void pw_tile_plan(const GridDev& g, TilePlan& p) {
-  typedef PwCfg<T, kTmaRY> C;
-  p.ry = kTmaRY;
-  p.tiles_y = (g.n[1] + C::TY - 1) / C::TY;
-  p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
-  const int tiles = p.tiles_y * p.tiles_z;
-  const int slots = kNumSMs * 2;
-  int best_c = 1;
-  double best = -1.0;
-  const int maxc = g.n[0] >= 16 ? g.n[0] / 8 : 1;
-  for (int c = 1; c <= maxc; ++c) {
-    const int cx = (g.n[0] + c - 1) / c;
-    const int cc = (g.n[0] + cx - 1) / cx;
-    const long long items = (long long)cc * tiles;
-    if (items > kMaxPartials) break;
-    const long long waves = (items + slots - 1) / slots;
-    const double quant = (double)items / (double)(waves * slots);
-    const double halo = g.act[0] ? (double)cx / (double)(cx + 2) : 1.0;
-    const double score = quant * halo * (items >= slots ? 1.0 : (double)items / slots);
-    if (score > best + 1e-9) {
-      best = score;
-      best_c = cc;
-    }
-  }
-  p.cx = (g.n[0] + best_c - 1) / best_c;
-  p.chunks = (g.n[0] + p.cx - 1) / p.cx;
-  p.vec_ok = 1;
-  p.fuse_fin = 0;
-  p.dist = 0;
-  p.chunk0 = 0;
-  p.chunk_step = 1;
-  p.accum = 0;
+  const bool flat = tma_flat(g);
+  const int ty = flat ? 1 : PwCfg<T, KStd>::TY;
+  const int tz = flat ? PwCfg<T, KFlat>::TZ : PwCfg<T, KStd>::TZ;
+  p.ry = flat ? 1 : KStd::RY;
+  p.tiles_y = flat ? 1 : (g.n[1] + ty - 1) / ty;
+  p.tiles_z = (g.n[2] + tz - 1) / tz;
+  tma_chunks(g, p.tiles_y * p.tiles_z, p);
 }
 
 // One launch of the engine.  `in` is the stencilled field, `aux` rhs / r0 (may be null).
-template <typename T, int MODE, int NOPS>
-inline void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CUtensorMap& tm_aux,
+template <typename T, typename K, int MODE, int NOPS>
+static void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CUtensorMap& tm_aux,
                               const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, bool has_aux, T* out,
                               T* out2, T dt, SolverState* st, double* partials, int stage) {
-  typedef PwCfg<T, kTmaRY> C;
+  typedef PwCfg<T, K> C;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_star_tma<T, kTmaRY, MODE, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)C::SMEM);
+    cudaFuncSetAttribute(k_star_tma<T, K, MODE, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr = true;
   }
   dim3 grid(tile.tiles_z, tile.tiles_y, tile.chunks);
-  k_star_tma<T, kTmaRY, MODE, NOPS><<<grid, C::THREADS, C::SMEM, s>>>(tm_in, tm_aux, tile, g, eq, out, out2, dt,
-                                                                     has_aux ? 1 : 0, st, partials, stage);
+  k_star_tma<T, K, MODE, NOPS><<<grid, C::THREADS, C::SMEM, s>>>(tm_in, tm_aux, tile, g, eq, out, out2, dt,
+                                                                has_aux ? 1 : 0, st, partials, stage);
+}
+
+template <typename T, typename K, int MODE>
+static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
+                              const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
+                              double* partials, int stage) {
+  typedef PwCfg<T, K> C;
+  CUtensorMap tm_in, tm_aux;
+  if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
+  if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::OBOXZ, C::TY)) return false;
+  // operator count known at compile time for the common equations (1: Poisson, 2: adv-diff)
+  if (eq.nops == 1)
+    launch_star_tma_n<T, K, MODE, 1>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  else if (eq.nops == 2)
+    launch_star_tma_n<T, K, MODE, 2>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  else
+    launch_star_tma_n<T, K, MODE, 0>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
+  return true;
 }
 
 template <typename T, int MODE>
 bool launch_star_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
-                            const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
-                            double* partials, int stage) {
-  typedef PwCfg<T, kTmaRY> C;
-  CUtensorMap tm_in, tm_aux;
-  if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
-  if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::TZ, C::TY)) return false;
-  // operator count known at compile time for the common equations (1: Poisson, 2: adv-diff)
-  if (eq.nops == 1)
-    launch_star_tma_n<T, MODE, 1>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
-  else if (eq.nops == 2)
-    launch_star_tma_n<T, MODE, 2>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
-  else
-    launch_star_tma_n<T, MODE, 0>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
-  return true;
+                     const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
+                     double* partials, int stage) {
+  return tma_flat(g) ? launch_star_tma_k<T, KFlat, MODE>(s, g, eq, tile, in, aux, out, out2, dt, st, partials, stage)
+                     : launch_star_tma_k<T, KStd, MODE>(s, g, eq, tile, in, aux, out, out2, dt, st, partials, stage);
 }
 
 }  // namespace pa
