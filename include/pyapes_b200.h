@@ -235,6 +235,20 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
                      size_t ws_bytes, void* comm, int rank, int nranks, pa_report* report,
                      void* stream);
 
+/* --- any of the three solvers on a slab (method = PA_METHOD_*); pa_cg_solve_dist is the CG case.
+ *     BiCGSTAB: p and s get their ghost planes by one send/recv pair each before the operator
+ *     application that reads them, and {r0.v}, {|s|^2}, {t.s, t.t, r0.t}, {|r|^2} are all-reduced
+ *     (4 per iteration).  Jacobi: one exchange of the new iterate + one all-reduce {|dx|^2}. */
+int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg, void* ws,
+                  size_t ws_bytes, void* comm, int rank, int nranks, pa_report* report, void* stream);
+
+/* --- pa_euler_steps on a slab: every step ends with the exchange of the new field's boundary
+ *     planes (no reduction). */
+int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                        int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
+                        int* result_in_alt, void* comm, int rank, int nranks, void* stream);
+
 /* --- instrumented CG pass (measurement only): `iters` iterations with every section bracketed
  *     by CUDA events on the launching stream.  out_ms[6] = average per iteration of
  *     {phase A (d update + d.Ad), phase B (x,r update), BC faces + shell norm, whole iteration,

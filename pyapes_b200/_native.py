@@ -107,6 +107,11 @@ SYMBOLS = {
     "pa_cg_solve_dist": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                    _P, _P, _P, C.POINTER(SolverCfg), _P, C.c_size_t, _P, C.c_int, C.c_int,
                                    C.POINTER(Report), _P]),
+    "pa_solve_dist": (C.c_int, [C.c_int, C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
+                                _P, _P, _P, C.POINTER(SolverCfg), _P, C.c_size_t, _P, C.c_int, C.c_int,
+                                C.POINTER(Report), _P]),
+    "pa_euler_steps_dist": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
+                                      _P, _P, _P, C.c_double, C.c_int, C.POINTER(C.c_int), _P, C.c_int, C.c_int, _P]),
     "pa_cg_profile": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                 _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(C.c_double), _P]),
     "pa_bicgstab_solve": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,

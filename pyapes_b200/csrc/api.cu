@@ -307,7 +307,7 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
       L.count += 2;
     }
     mark(1);
-    CommLane* lane = (dist && tma->tile.chunks >= 6) ? comm_lane() : nullptr;  // enough interior work to hide it
+    CommLane* lane = (dist && tma_interior_chunks(*tma, g) >= 4) ? comm_lane() : nullptr;  // enough interior work to hide it
     if (lane) {
       // overlap: boundary chunks first, their r planes go out on the comm stream while the
       // interior chunks run
@@ -435,10 +435,14 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
   return PA_OK;
 }
 
+// Multi-GPU (slab) variant: the axpy stages run over the OWNED planes only (a contiguous range),
+// p and s get their ghost planes by one halo exchange each before the stencil that reads them
+// (one exchange per operator application), and each of the four reductions is
+// all-reduced before its scalar stage is finalized by k_finalize.
 template <typename T>
 static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
                                const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt,
-                               const TilePlan* pw = nullptr) {
+                               const TilePlan* pw = nullptr, const Dist* dist = nullptr) {
   T* r0 = (T*)w.vec[0];
   T* r = (T*)w.vec[1];
   T* p = (T*)w.vec[2];
@@ -446,45 +450,74 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   T* s = (T*)w.vec[4];
   T* t = (T*)w.vec[5];
   int nb = grid_blocks(g.cells);
-  // streaming axpy stages: legal when every cell is owned and the cell count is a multiple of
-  // the 16-byte vector width (the region test is unnecessary: everything is 0 outside it)
+  // streaming axpy stages: legal when the owned range starts and ends on a 16-byte vector
+  // boundary (the region test is unnecessary: everything is 0 outside it)
   constexpr int SV = StreamVec<T>::N;
-  const bool stream_ok = (g.cells % SV == 0) && g.olo0 == 0 && g.ohi0 == g.n[0];
-  const long long nvec = g.cells / SV;
+  const long long plane = (long long)g.n[1] * g.n[2];
+  const long long off = (long long)g.olo0 * plane;
+  const long long nown = (long long)(g.ohi0 - g.olo0) * plane;
+  const bool stream_ok = (nown % SV == 0) && (off % SV == 0);
+  const long long nvec = nown / SV;
+  auto reduce = [&](int count, int stage) {  // rank-sum of the raw sums, then the scalar stage
+    if (!dist) return;
+    dist_allreduce(*dist, &w.st->sum[R_A], count, L.s);
+    k_finalize<T><<<1, 1, 0, L.s>>>(stage, w.st);
+    L.count += 2;
+  };
+  const int ST_V = dist ? ST_NONE : ST_BI_V, ST_S = dist ? ST_NONE : ST_BI_S, ST_T = dist ? ST_NONE : ST_BI_T;
   if (stream_ok)
-    k_bi_p_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r, p, v, w.st);
+    k_bi_p_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r + off, p + off, v + off, w.st);
   else
     k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
+  if (dist) {
+    dist_halo_exchange<T>(*dist, p, plane, g.olo0, g.ohi0, L.s);
+    ++L.count;
+  }
   if (pw)
-    L.ok &= launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_BI_V);
+    L.ok &= launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_V);
   else
-    k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_BI_V);
+    k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_V);
+  reduce(1, ST_BI_V);
   if (stream_ok)
-    k_bi_s_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r, v, s, w.st, w.partials, ST_BI_S);
+    k_bi_s_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r + off, v + off, s + off, w.st, w.partials, ST_S);
   else
-    k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_BI_S);
+    k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_S);
+  reduce(1, ST_BI_S);
+  if (dist) {
+    dist_halo_exchange<T>(*dist, s, plane, g.olo0, g.ohi0, L.s);
+    ++L.count;
+  }
   if (pw)
-    L.ok &= launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_BI_T);
+    L.ok &= launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_T);
   else
-    k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_BI_T);
+    k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_T);
+  reduce(3, ST_BI_T);
   if (stream_ok)
-    k_bi_x_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, cur, nxt, p, s, t, r, w.st, w.partials);
+    k_bi_x_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, cur + off, nxt + off, p + off, s + off, t + off, r + off, w.st,
+                                             w.partials);
   else
     k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
   L.count += 5;
   launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+  if (dist) {
+    dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
+    ++L.count;
+  }
   k_finalize<T><<<1, 1, 0, L.s>>>(ST_BI_FIN, w.st);
   ++L.count;
 }
 
+// Multi-GPU: the sweep reads x with its ghost planes (valid on entry), then the new iterate's
+// boundary planes go to the neighbours and {|dx|^2 interior, |dx|^2 shell} are all-reduced.
 template <typename T>
 static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int nfaces,
                              const pa_face_bc* faces, const Workspace& w, T* cur, T* nxt,
-                             const T* rhs, const TilePlan* pw = nullptr) {
+                             const T* rhs, const TilePlan* pw = nullptr, const Dist* dist = nullptr) {
   int nb = grid_blocks(g.cells);
+  const bool stat = static_shell(nfaces, faces) != 0;
   if (pw) {
     // static shell: the sweep also finalizes the iteration (shell part of the norm is 0)
-    const bool fuse = static_shell(nfaces, faces) != 0;
+    const bool fuse = stat && !dist;
     L.ok &= launch_star_tma<T, PW_JACOBI>(L.s, g, eq, *pw, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
                                           fuse ? ST_JA_FIN : ST_NONE);
     ++L.count;
@@ -493,8 +526,18 @@ static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, 
     k_pointwise_update<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, rhs, (T)0, w.st, w.partials);
     ++L.count;
   }
-  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
-  launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_JA_FIN);
+  if (dist && stat) {
+    cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
+  } else {
+    launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+    launch_shell<T>(L, g, nxt, cur, w.st, w.partials, dist ? ST_NONE : ST_JA_FIN);
+  }
+  if (dist) {
+    dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
+    dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
+    k_finalize<T><<<1, 1, 0, L.s>>>(ST_JA_FIN, w.st);
+    L.count += 3;
+  }
 }
 
 // Shared driver: init, then iterate in pairs (x -> x_alt -> x) so that a pair can be
@@ -531,7 +574,6 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     tiled = plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
   if (dist) {
-    if (method != PA_METHOD_CG) return fail(PA_ERR_UNSUPPORTED, "multi-GPU: only CG is slab-decomposed so far");
     if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
     plan.dist = tmap.tile.dist = 1;
     plan.fuse_fin = tmap.tile.fuse_fin = 0;
@@ -576,11 +618,31 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     T* r0 = (T*)w.vec[0];
     T* r = (T*)w.vec[1];
     for (int i = 2; i < 6; ++i) PA_CUDA(cudaMemsetAsync(w.vec[i], 0, vbytes, stream));
+    const long long plane = (long long)g.n[1] * g.n[2];
+    if (dist) {
+      dist_halo_exchange<T>(*dist, x, plane, g.olo0, g.ohi0, stream);  // x ghosts for r0
+      // the iteration only writes the owned planes of the iterates: give x_alt the same ghosts
+      if (g.olo0 > 0)
+        PA_CUDA(cudaMemcpyAsync(x_alt, x, (size_t)g.olo0 * plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      if (g.ohi0 < g.n[0])
+        PA_CUDA(cudaMemcpyAsync(x_alt + (long long)g.ohi0 * plane, x + (long long)g.ohi0 * plane,
+                                (size_t)(g.n[0] - g.ohi0) * plane * sizeof(T), cudaMemcpyDeviceToDevice,
+                                stream));
+      ++L.count;
+    }
+    const int st_init = dist ? ST_NONE : ST_BI_INIT;
     if (pw)
-      L.ok &= launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r0, r, (T)0, w.st, w.partials, ST_BI_INIT);
+      L.ok &= launch_star_tma<T, PW_RESID>(stream, g, eq, *pw, x, rhs, r0, r, (T)0, w.st, w.partials, st_init);
     else
-      k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials,
-                                                    ST_BI_INIT);
+      k_residual_init<T><<<nb, kBlock, 0, stream>>>(g, eq, x, rhs, r0, r, w.st, w.partials, st_init);
+    ++L.count;
+    if (dist) {
+      dist_allreduce(*dist, &w.st->sum[R_A], 1, stream);
+      k_finalize<T><<<1, 1, 0, stream>>>(ST_BI_INIT, w.st);
+      L.count += 2;
+    }
+  } else if (dist) {  // Jacobi: the first sweep reads x with its ghost planes
+    dist_halo_exchange<T>(*dist, x, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, stream);
     ++L.count;
   }
   PA_CUDA(cudaGetLastError());
@@ -602,9 +664,9 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
                       use_tma ? &tmap : nullptr, dist);
     else if (method == PA_METHOD_BICGSTAB)
-      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, pw);
+      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, pw, dist);
     else
-      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs, pw);
+      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs, pw, dist);
   };
 
   const long long max_iters = (method == PA_METHOD_BICGSTAB)
@@ -665,6 +727,13 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (rc != PA_OK) return rc;
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(PA_ERR_CUDA, cudaGetErrorString(le));
+  if (dist && method == PA_METHOD_BICGSTAB) {
+    // the axpy stages only touched owned planes: refresh the ghost planes of both iterates
+    const long long plane = (long long)g.n[1] * g.n[2];
+    dist_halo_exchange<T>(*dist, x, plane, g.olo0, g.ohi0, stream);
+    dist_halo_exchange<T>(*dist, x_alt, plane, g.olo0, g.ohi0, stream);
+    PA_CUDA(cudaStreamSynchronize(stream));
+  }
   fill_report(rep, h, L.count);
   // iterations completed with an update == number of ping-pong swaps
   int swaps = h->itr;
@@ -848,6 +917,23 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
                                    nranks > 1 ? &d : nullptr));
 }
 
+int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                  int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg, void* ws,
+                  size_t ws_bytes_, void* comm, int rank, int nranks, pa_report* report, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
+  if (rc) return rc;
+  if (method != PA_METHOD_CG && method != PA_METHOD_BICGSTAB && method != PA_METHOD_JACOBI)
+    return fail(PA_ERR_ARG, "unknown solver method");
+  if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
+  for (int f = 0; f < nfaces; ++f)
+    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
+      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
+  Dist d{(ncclComm_t)comm, rank, nranks};
+  PA_DISPATCH(dtype, run_solver<T>(method, g, eq, nfaces, faces, (T*)x, (T*)x_alt, (const T*)rhs, cfg, ws,
+                                   ws_bytes_, report, (cudaStream_t)stream, nranks > 1 ? &d : nullptr));
+}
+
 int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
                   int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
                   size_t ws_bytes_, double* out_ms, void* stream) {
@@ -888,10 +974,11 @@ int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
 // steps is captured once as a CUDA graph and replayed.  Static shell (all faces Dirichlet):
 // after the first step the shell already holds the BC values and later steps copy it, so BC
 // launches are only needed in the first step.
+// Multi-GPU: every step ends with the halo exchange of the new field's boundary planes.
 template <typename T>
 static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
                       const pa_face_bc* faces, T* a, T* b, const T* rhs, double dt, int nsteps,
-                      int* result_in_b, cudaStream_t caller) {
+                      int* result_in_b, cudaStream_t caller, const Dist* dist = nullptr) {
   cudaStream_t s;
   int rcs = solver_stream(caller, &s);
   if (rcs != PA_OK) return rcs;
@@ -910,7 +997,12 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
       k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, cur, nxt, rhs, (T)dt, nullptr,
                                                                        nullptr);
     if (bcs) launch_bcs<T>(L, g, nfaces, faces, nxt, nullptr);
+    if (dist) dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, s);
   };
+  if (dist) {
+    if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+    if (nsteps > 0) dist_halo_exchange<T>(*dist, a, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, s);
+  }
   int done_steps = 0;
   T* cur = a;
   T* nxt = b;
@@ -971,6 +1063,23 @@ int pa_euler_steps(const pa_grid* g, const pa_equation* eq, int nfaces, const pa
     return fail(PA_ERR_ARG, "bad argument");
   PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (T*)phi, (T*)phi_alt, (const T*)rhs, dt, nsteps,
                                    result_in_alt, (cudaStream_t)stream));
+}
+
+int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
+                        int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
+                        int* result_in_alt, void* comm, int rank, int nranks, void* stream) {
+  PA_REQUIRE_DEVICE();
+  int rc;
+  if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
+  if (!phi || !phi_alt || phi == phi_alt || !result_in_alt || nsteps < 0)
+    return fail(PA_ERR_ARG, "bad argument");
+  if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
+  for (int f = 0; f < nfaces; ++f)
+    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
+      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
+  Dist d{(ncclComm_t)comm, rank, nranks};
+  PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (T*)phi, (T*)phi_alt, (const T*)rhs, dt, nsteps,
+                                   result_in_alt, (cudaStream_t)stream, nranks > 1 ? &d : nullptr));
 }
 
 int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,

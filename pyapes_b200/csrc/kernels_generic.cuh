@@ -99,6 +99,7 @@ __device__ void finalize_stage(int stage, SolverState* st) {
       st->finished_flag = ((double)tol <= st->tolerance) ? 1 : 0;
     } break;
     case ST_BI_T: {  // omega, rho_next                                     linalg.py:246-250
+      if (st->finished_flag) break;  // early exit taken after the first half step (linalg.py:235-240)
       T w = (T)sum[R_A] / (T)sum[R_B];
       w = nan_to_num0<T>(w);
       sc[S_OMEGA] = (double)w;

@@ -43,9 +43,10 @@ struct TilePlan {
   int fuse_fin;                      // phase B also finalizes the iteration (static shell)
   int ry;                            // rows per thread of the instantiation to launch (2 or 4)
   int dist;                          // multi-GPU: leave raw sums for the NCCL all-reduce
-  // sub-launch over a subset of the chunks (halo-exchange overlap): chunk = chunk0 + z*step;
+  // sub-launch over a subset of the chunks (halo-exchange overlap): blockIdx.z < chunk_split maps
+  // to chunk0 + z, the rest to chunk_hi0 + (z - chunk_split);
   // accum = 1 adds this launch's sums to the ones an earlier sub-launch stored
-  int chunk0, chunk_step, accum;
+  int chunk0, chunk_split, chunk_hi0, accum;
 };
 
 template <typename T>
@@ -132,7 +133,8 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.fuse_fin = 0;
   p.dist = 0;
   p.chunk0 = 0;
-  p.chunk_step = 1;
+  p.chunk_split = 1 << 30;
+  p.chunk_hi0 = 0;
   p.accum = 0;
   return true;
 }

@@ -186,7 +186,8 @@ inline void tma_chunks(const GridDev& g, int tiles, TilePlan& p) {
   p.fuse_fin = 0;
   p.dist = 0;
   p.chunk0 = 0;
-  p.chunk_step = 1;
+  p.chunk_split = 1 << 30;
+  p.chunk_hi0 = 0;
   p.accum = 0;
 }
 
@@ -493,7 +494,9 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int x0 = (p.chunk0 + (int)blockIdx.z * p.chunk_step) * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const int zc = (int)blockIdx.z;
+  const int x0 = (zc < p.chunk_split ? p.chunk0 + zc : p.chunk_hi0 + (zc - p.chunk_split)) * p.cx;
+  const int x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
@@ -675,7 +678,9 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int x0 = (p.chunk0 + (int)blockIdx.z * p.chunk_step) * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  const int zc = (int)blockIdx.z;
+  const int x0 = (zc < p.chunk_split ? p.chunk0 + zc : p.chunk_hi0 + (zc - p.chunk_split)) * p.cx;
+  const int x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
@@ -718,6 +723,11 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, p.dist ? ST_NONE : ST_CG_DAD});
 }
 
+// chunks left to the interior sub-launch when phase B is split around the halo exchange
+inline int tma_interior_chunks(const TmaPlan& tp, const GridDev& g) {
+  return (g.ohi0 - 1) / tp.tile.cx - g.olo0 / tp.tile.cx - 1;
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 template <typename T, typename K>
 static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
@@ -754,15 +764,19 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
   TilePlan tile = tp.tile;
   int nz = tile.chunks;
-  if (sub == 1) {         // boundary chunks: first and last
+  // the boundary sub-launch must produce the first and the last OWNED plane (they leave with the
+  // halo exchange while the interior sub-launch runs): every chunk up to the one holding plane
+  // olo0 and from the one holding plane ohi0-1 on
+  const int c_lo = g.olo0 / tile.cx, c_hi = (g.ohi0 - 1) / tile.cx;
+  if (sub == 1) {
     tile.chunk0 = 0;
-    tile.chunk_step = tile.chunks - 1;
-    nz = 2;
+    tile.chunk_split = c_lo + 1;
+    tile.chunk_hi0 = c_hi;
+    nz = (c_lo + 1) + (tile.chunks - c_hi);
   } else if (sub == 2) {  // interior chunks, sums added to the boundary launch's
-    tile.chunk0 = 1;
-    tile.chunk_step = 1;
+    tile.chunk0 = c_lo + 1;
     tile.accum = 1;
-    nz = tile.chunks - 2;
+    nz = c_hi - c_lo - 1;
   }
   dim3 grid(tile.tiles_z, tile.tiles_y, nz);
   k_cg_phaseB_tma<T, K><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,

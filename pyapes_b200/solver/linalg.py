@@ -84,11 +84,9 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     if slab is not None and slab["world"] > 1:
         from pyapes_b200 import parallel
 
-        if method != "cg":
-            raise NotImplementedError("pyapes_b200: only CG runs on slab-decomposed meshes so far")
-        N.check(lib.pa_cg_solve_dist(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
-                                     rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, parallel.get_comm(x.device),
-                                     slab["rank"], slab["world"], rep, N.current_stream(x.device)))
+        N.check(lib.pa_solve_dist(N.METHOD[method], grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
+                                  rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, parallel.get_comm(x.device),
+                                  slab["rank"], slab["world"], rep, N.current_stream(x.device)))
     else:
         N.check(getattr(lib, _SOLVERS[method])(grid, eq, nfaces, faces, code, x.data_ptr(), x_alt.data_ptr(),
                                                rhs_c.data_ptr(), cfg, ws.data_ptr(), ws_bytes, rep,
@@ -142,7 +140,8 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
     N.require_cuda(x, "field")
     nd = mesh.dim
     code = N.dtype_code(x.dtype)
-    grid = L.lower_grid(mesh.nx, var.bcs)
+    slab = getattr(mesh, "slab", None)
+    grid = L.lower_grid(mesh.nx, var.bcs, slab)
     faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd)
     eq, keep_e = L_lower_equation(eqs, var)
     dt = float(eqs[0]["param"][0])
@@ -155,8 +154,15 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
 
     alt = torch.empty_like(x)
     in_alt = C.c_int(0)
-    N.check(N.lib().pa_euler_steps(grid, eq, nfaces, faces, code, x.data_ptr(), alt.data_ptr(), rhs_ptr, dt, n_steps,
-                                   C.byref(in_alt), N.current_stream(x.device)))
+    if slab is not None and slab["world"] > 1:
+        from pyapes_b200 import parallel
+
+        N.check(N.lib().pa_euler_steps_dist(grid, eq, nfaces, faces, code, x.data_ptr(), alt.data_ptr(), rhs_ptr, dt,
+                                            n_steps, C.byref(in_alt), parallel.get_comm(x.device), slab["rank"],
+                                            slab["world"], N.current_stream(x.device)))
+    else:
+        N.check(N.lib().pa_euler_steps(grid, eq, nfaces, faces, code, x.data_ptr(), alt.data_ptr(), rhs_ptr, dt,
+                                       n_steps, C.byref(in_alt), N.current_stream(x.device)))
     for _ in range(n_steps):
         var.update_time()
     if n_steps > 0:
