@@ -214,6 +214,11 @@ int pa_euler_steps(const pa_grid* g, const pa_equation* eq, int nfaces, const pa
                    int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
                    int* result_in_alt, void* stream);
 
+/* --- out[i] = y[i] + a*x[i], i < n (a rounded to dtype first; out may alias y).  Builds the
+ *     right-hand side rhs + phi_old/dt of an implicit Euler step (fdm.Ddt with a Krylov method;
+ *     the reference's Ddt is a stub, fdm.py:315-353, intended semantics tests/test_fdm.py:275-299). */
+int pa_axpy(int dtype, long long n, double a, const void* x, const void* y, void* out, void* stream);
+
 /* --- end-to-end entry with HOST buffers: copies x and rhs to the device, solves with CG,
  *     copies the solution back.  x_host, rhs_host: n0*n1*n2 elements of dtype (pinned
  *     memory recommended).  Device scratch is allocated and freed inside the call. */

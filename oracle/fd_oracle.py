@@ -449,9 +449,9 @@ def div_rhs_adjust(u, phi, dx, bcs, limiter):
 # ---------------------------------------------------------------------------------------
 @dataclass
 class Term:
-    kind: str  # laplacian | grad | div
+    kind: str  # laplacian | grad | div | ddt
     sign: float = 1.0
-    param: Any = None  # laplacian/grad: float|None ; div: advection (float|Tensor)
+    param: Any = None  # laplacian/grad: float|None ; div: advection (float|Tensor) ; ddt: dt
     limiter: str = "none"
     coeffs: Any = field(default=None, repr=False)
 
@@ -473,6 +473,10 @@ class Equation:
                 t.coeffs = grad_coeffs(phi, self.dx, self.bcs)
             elif t.kind == "div":
                 t.coeffs = div_coeffs(t.param, phi, self.dx, self.bcs, t.limiter, rz_xs)
+            elif t.kind == "ddt":
+                # implicit Euler: the linear part of (phi - phi_old)/dt, as a multiplication by
+                # 1/dt rounded in the field dtype (NOT in the reference, see implicit_euler_step)
+                t.coeffs = torch.ones(1, dtype=phi.dtype) / t.param
             else:
                 raise ValueError(t.kind)
         return self
@@ -480,6 +484,8 @@ class Equation:
     def adjust_rhs(self, phi: Tensor, rhs: Tensor) -> Tensor:
         """ops.py:63-77 — in place on the caller's tensor, every term contributes."""
         for t in self.terms:
+            if t.kind == "ddt":  # ops.py:70-71 skips Ddt
+                continue
             if t.kind == "laplacian":
                 rhs += laplacian_rhs_adjust(phi, self.dx, self.bcs, self.xs if self.rz else None)
             elif t.kind == "grad":
@@ -492,6 +498,8 @@ class Equation:
         """ops.py:122-154."""
         res = torch.zeros_like(phi)
         for t in self.terms:
+            if t.kind == "ddt":  # skipped in the loop, added after it (ops.py:133-134,151-152)
+                continue
             if t.kind == "grad":
                 ax = apply_grad(t.coeffs, phi)
                 if t.param is not None:
@@ -503,18 +511,26 @@ class Equation:
                     ax = ax * t.param
                 ax = ax * t.sign
             res += ax
+        for t in self.terms:
+            if t.kind == "ddt":
+                res += t.coeffs * phi
         return res
 
     def diag(self, phi: Tensor) -> Tensor:
         """Centre coefficient of the summed operator (for Jacobi; not in the reference)."""
         res = torch.zeros_like(phi)
         for t in self.terms:
+            if t.kind == "ddt":
+                continue
             d = torch.zeros_like(phi)
             for j in range(phi.dim() - 1):
                 d[0] += t.coeffs[2][j][0]
             if t.kind in ("laplacian", "grad") and t.param is not None:
                 d = d * t.param
             res += d * t.sign
+        for t in self.terms:
+            if t.kind == "ddt":
+                res += t.coeffs * torch.ones_like(phi)
         return res
 
 
@@ -644,3 +660,18 @@ def euler_step(eq: Equation, x: Tensor, rhs: Tensor | None, dt: float) -> Tensor
     new[0][sl] = x[0][sl] + dt * (src[0][sl] - ax[0][sl])
     apply_bcs(new, eq.xs, eq.bcs)
     return new
+
+
+def implicit_euler_step(eq: Equation, x: Tensor, rhs: Tensor | None, dt: float, method: str, tolerance: float,
+                        max_it: int):
+    """NOT in the reference: `fdm.Ddt` registers nothing (fdm.py:322-339); the semantics its
+    failing test intends is Aop = (phi - phi_old)/dt + spatial operators (tests/test_fdm.py:275-299).
+    Implicit Euler: with c = 1/dt rounded in the field dtype, solve
+        c*phi_new + A_spatial(phi_new) = rhs + c*phi_old
+    with the named solver, initial guess phi_old.  `eq` must hold a Term("ddt", param=dt); its
+    contribution c*phi is added after the spatial operators (ops.py:151-152).  Parity unpinned."""
+    c = torch.ones(1, dtype=x.dtype) / dt
+    src = torch.zeros_like(x) if rhs is None else rhs
+    rhs_eff = src + c * x
+    solver = {"cg": cg, "bicgstab": bicgstab, "jacobi": jacobi}[method]
+    return solver(eq, x.clone(), rhs_eff, tolerance, max_it)

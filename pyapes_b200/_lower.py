@@ -49,6 +49,12 @@ def lower_grid(nx, bcs, slab=None) -> N.Grid:
     if slab is not None:
         assert nd == 3, "slab decomposition is along axis 0 of a 3-D mesh"
         g.gn0, g.goff0, g.olo0, g.ohi0 = slab["gn0"], slab["goff0"], slab["olo0"], slab["ohi0"]
+        per0 = (lo[0] == 0, hi[0] == n[0])
+        if slab["world"] > 1 and (any(per0) != bool(slab.get("periodic", False)) or per0[0] != per0[1]):
+            raise ValueError(
+                "pyapes_b200: Periodic BCs on the x faces of a slab-decomposed mesh need both faces periodic "
+                "and SlabMesh(..., periodic=True) (wrap-around ghost planes); and vice versa"
+            )
         # region along axis 0: owned planes that are inside the global slicer
         glo, ghi = (0 if lo[0] == 0 else 1), (slab["gn0"] if hi[0] == n[0] else slab["gn0"] - 1)
         g.lo[0] = max(slab["olo0"], glo - slab["goff0"])

@@ -122,6 +122,7 @@ SYMBOLS = {
                                 _P, _P, _P, C.c_double, _P]),
     "pa_euler_steps": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                  _P, _P, _P, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
+    "pa_axpy": (C.c_int, [C.c_int, C.c_longlong, C.c_double, _P, _P, _P, _P]),
     "pa_cg_solve_host": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                    _P, _P, C.POINTER(SolverCfg), C.POINTER(Report)]),
 }

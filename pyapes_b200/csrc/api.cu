@@ -126,9 +126,35 @@ struct Launcher {
   bool ok = true;  // false once a TMA launch could not be issued (tensor-map encode failed)
 };
 
+// device scratch of the slab-periodic boundary condition (two planes), grown on demand — never
+// while a stream capture is active (run_solver / euler_impl reserve it before capturing)
+static void* bc_scratch(size_t bytes) {
+  static void* p = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, bytes) == cudaSuccess) cap = bytes;
+  }
+  return p;
+}
+
+// phi[face] = (phi[1 inward] - phi[N-1]) + phi[N-2]  with the two far planes in `far` (N-2 first)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_bc_periodic_lo_slab(long long n, T* __restrict__ face,
+                                                                const T* __restrict__ inner,
+                                                                const T* __restrict__ far, const SolverState* st) {
+  if (st != nullptr && st->done) return;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    T t = inner[k] - far[n + k];
+    face[k] = t + far[k];
+  }
+}
+
 template <typename T>
 static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_bc* faces, T* phi,
-                       const SolverState* st) {
+                       const SolverState* st, const Dist* dist = nullptr) {
   for (int f = 0; f < nfaces; ++f) {
     FaceDev<T> fd;
     fd.axis = faces[f].axis;
@@ -137,6 +163,34 @@ static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_
     fd.value = (T)faces[f].value;
     fd.values = (const T*)faces[f].values;
     if (!g.act[fd.axis]) continue;
+    if (fd.axis == 0 && fd.kind == PA_BC_PERIODIC && dist && dist->ring) {
+      // periodic faces along the slab axis (bcs.py:262-280) need the other end of the ring, at
+      // this position of the face list:
+      //   lower: phi[0] = phi[1] - phi[N-1] + phi[N-2]   rank P-1 sends its last two planes to rank 0
+      //   upper: phi[N-1] = phi[0]                        rank 0 sends plane 0 to rank P-1
+      const long long plane = (long long)g.n[1] * g.n[2];
+      const int last = dist->nranks - 1;
+      if (fd.side < 0) {
+        if (dist->rank == last) dist_send<T>(*dist, phi + (long long)(g.ohi0 - 2) * plane, 2 * plane, 0, L.s);
+        if (dist->rank == 0) {
+          T* far = (T*)bc_scratch((size_t)(2 * plane) * sizeof(T));
+          if (!far) {
+            L.ok = false;
+            continue;
+          }
+          dist_recv<T>(*dist, far, 2 * plane, last, L.s);
+          int blocks = (int)((plane + kBlock - 1) / kBlock);
+          if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+          k_bc_periodic_lo_slab<T><<<blocks, kBlock, 0, L.s>>>(plane, phi + (long long)g.olo0 * plane,
+                                                               phi + (long long)(g.olo0 + 1) * plane, far, st);
+        }
+      } else {
+        if (dist->rank == 0) dist_send<T>(*dist, phi + (long long)g.olo0 * plane, plane, last, L.s);
+        if (dist->rank == last) dist_recv<T>(*dist, phi + (long long)(g.ohi0 - 1) * plane, plane, 0, L.s);
+      }
+      ++L.count;
+      continue;
+    }
     // along the slab axis only the rank that owns the face plane applies it
     if (fd.axis == 0) {
       int gi = fd.side < 0 ? 0 : g.gn0 - 1;
@@ -361,7 +415,7 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     if (static_shell(nfaces, faces)) {
       cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
     } else {
-      launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+      launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
       launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_NONE);
     }
     if (!overlapped) dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
@@ -498,7 +552,7 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   else
     k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
   L.count += 5;
-  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+  launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
   if (dist) {
     dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
     ++L.count;
@@ -529,7 +583,7 @@ static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, 
   if (dist && stat) {
     cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
   } else {
-    launch_bcs<T>(L, g, nfaces, faces, nxt, w.st);
+    launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
     launch_shell<T>(L, g, nxt, cur, w.st, w.partials, dist ? ST_NONE : ST_JA_FIN);
   }
   if (dist) {
@@ -586,7 +640,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
 
   k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
   ++L.count;
-  launch_bcs<T>(L, g, nfaces, faces, x, nullptr);
+  if (dist && dist->ring) bc_scratch((size_t)2 * g.n[1] * g.n[2] * sizeof(T));  // before any capture
+  launch_bcs<T>(L, g, nfaces, faces, x, nullptr, dist);
   int nb = grid_blocks(g.cells);
   size_t vbytes = (size_t)g.cells * sizeof(T);
 
@@ -848,6 +903,21 @@ size_t pa_solver_workspace_bytes(const pa_grid* g, int dtype, int method) {
   return ws_bytes(cells, dtype == PA_F64 ? 8 : 4, method_nvec(method));
 }
 
+// Periodic faces along the slab axis: both ends must be periodic and every rank must carry the
+// wrap-around ghost planes (pyapes_b200.parallel.SlabMesh(..., periodic=True)).
+static int slab_ring(const pa_grid* g, int nfaces, const pa_face_bc* faces, int nranks, int* ring) {
+  int lo = 0, hi = 0;
+  for (int f = 0; f < nfaces; ++f)
+    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC) (faces[f].side < 0 ? lo : hi) = 1;
+  *ring = 0;
+  if (nranks < 2 || (!lo && !hi)) return PA_OK;
+  if (lo != hi) return fail(PA_ERR_UNSUPPORTED, "multi-GPU: a single periodic face along the slab axis");
+  if (g->olo0 != 1 || g->ohi0 != g->n[0] - 1)
+    return fail(PA_ERR_ARG, "multi-GPU: periodic slab axis needs a ghost plane on both sides of every rank");
+  *ring = 1;
+  return PA_OK;
+}
+
 static int check_solver_args(const pa_grid* g, const pa_equation* eq, int nfaces,
                              const pa_face_bc* faces, void* x, void* x_alt, const void* rhs,
                              const pa_solver_cfg* cfg, void* ws, pa_report* rep) {
@@ -908,10 +978,8 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
-  for (int f = 0; f < nfaces; ++f)
-    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
-      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
   Dist d{(ncclComm_t)comm, rank, nranks};
+  if ((rc = slab_ring(g, nfaces, faces, nranks, &d.ring))) return rc;
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
                                    (const T*)rhs, cfg, ws, ws_bytes_, report, (cudaStream_t)stream,
                                    nranks > 1 ? &d : nullptr));
@@ -926,10 +994,8 @@ int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nface
   if (method != PA_METHOD_CG && method != PA_METHOD_BICGSTAB && method != PA_METHOD_JACOBI)
     return fail(PA_ERR_ARG, "unknown solver method");
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
-  for (int f = 0; f < nfaces; ++f)
-    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
-      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
   Dist d{(ncclComm_t)comm, rank, nranks};
+  if ((rc = slab_ring(g, nfaces, faces, nranks, &d.ring))) return rc;
   PA_DISPATCH(dtype, run_solver<T>(method, g, eq, nfaces, faces, (T*)x, (T*)x_alt, (const T*)rhs, cfg, ws,
                                    ws_bytes_, report, (cudaStream_t)stream, nranks > 1 ? &d : nullptr));
 }
@@ -970,6 +1036,22 @@ int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
 }
 
 }  // extern "C"
+// out = y + a*x  (one rounding per operation; out may alias y)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_axpy(long long n, T a, const T* __restrict__ x, const T* y, T* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    T t = a * x[i];
+    out[i] = y[i] + t;
+  }
+}
+template <typename T>
+static int axpy_impl(long long n, double a, const T* x, const T* y, T* out, cudaStream_t s) {
+  if (n == 0) return PA_OK;
+  k_axpy<T><<<grid_blocks(n), kBlock, 0, s>>>(n, (T)a, x, y, out);
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
 // n explicit Euler steps, ping-ponging between `a` (holds phi on entry) and `b`.  A pair of
 // steps is captured once as a CUDA graph and replayed.  Static shell (all faces Dirichlet):
 // after the first step the shell already holds the BC values and later steps copy it, so BC
@@ -996,11 +1078,12 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
     if (!done)
       k_pointwise_update<T, 1><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, cur, nxt, rhs, (T)dt, nullptr,
                                                                        nullptr);
-    if (bcs) launch_bcs<T>(L, g, nfaces, faces, nxt, nullptr);
+    if (bcs) launch_bcs<T>(L, g, nfaces, faces, nxt, nullptr, dist);
     if (dist) dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, s);
   };
   if (dist) {
     if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+    if (dist->ring) bc_scratch((size_t)2 * g.n[1] * g.n[2] * sizeof(T));  // before any capture
     if (nsteps > 0) dist_halo_exchange<T>(*dist, a, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, s);
   }
   int done_steps = 0;
@@ -1074,12 +1157,16 @@ int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, con
   if (!phi || !phi_alt || phi == phi_alt || !result_in_alt || nsteps < 0)
     return fail(PA_ERR_ARG, "bad argument");
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
-  for (int f = 0; f < nfaces; ++f)
-    if (faces[f].axis == 0 && faces[f].kind == PA_BC_PERIODIC && nranks > 1)
-      return fail(PA_ERR_UNSUPPORTED, "multi-GPU: periodic faces along the slab axis are not supported");
   Dist d{(ncclComm_t)comm, rank, nranks};
+  if ((rc = slab_ring(g, nfaces, faces, nranks, &d.ring))) return rc;
   PA_DISPATCH(dtype, euler_impl<T>(g, eq, nfaces, faces, (T*)phi, (T*)phi_alt, (const T*)rhs, dt, nsteps,
                                    result_in_alt, (cudaStream_t)stream, nranks > 1 ? &d : nullptr));
+}
+
+int pa_axpy(int dtype, long long n, double a, const void* x, const void* y, void* out, void* stream) {
+  PA_REQUIRE_DEVICE();
+  if (n < 0 || !x || !y || !out) return fail(PA_ERR_ARG, "bad argument");
+  PA_DISPATCH(dtype, axpy_impl<T>(n, a, (const T*)x, (const T*)y, (T*)out, (cudaStream_t)stream));
 }
 
 int pa_cg_solve_host(const pa_grid* g, const pa_equation* eq, int nfaces,

@@ -67,6 +67,7 @@ static inline NcclApi& nccl_api() {
 struct Dist {
   ncclComm_t comm;
   int rank, nranks;
+  int ring = 0;  // axis 0 is periodic: rank 0 and rank P-1 are neighbours (wrap-around ghost planes)
 };
 
 // sum-all-reduce `count` doubles in place (device memory)
@@ -76,22 +77,34 @@ static inline ncclResult_t dist_allreduce(const Dist& d, double* buf, int count,
 
 // exchange the boundary planes of a slab-decomposed vector: first/last OWNED plane -> the
 // neighbour's ghost plane.  plane_elems = n1*n2.  Planes are contiguous runs, no packing.
+// Order inside the group: [first plane -> lower neighbour, upper ghost <- upper neighbour], then
+// [last plane -> upper neighbour, lower ghost <- lower neighbour]; NCCL matches the operations
+// between two ranks in issue order, which keeps the pairing right when both neighbours are the
+// same rank (ring of two).
 template <typename T>
 static inline ncclResult_t dist_halo_exchange(const Dist& d, T* v, long long plane_elems, int olo0,
                                               int ohi0, cudaStream_t s) {
   NcclApi& a = nccl_api();
   const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+  const int lower = d.rank > 0 ? d.rank - 1 : (d.ring ? d.nranks - 1 : -1);
+  const int upper = d.rank < d.nranks - 1 ? d.rank + 1 : (d.ring ? 0 : -1);
   ncclResult_t rc = a.GroupStart();
   if (rc != ncclSuccess) return rc;
-  if (d.rank > 0) {
-    a.Send(v + (long long)olo0 * plane_elems, (size_t)plane_elems, dt, d.rank - 1, d.comm, s);
-    a.Recv(v + (long long)(olo0 - 1) * plane_elems, (size_t)plane_elems, dt, d.rank - 1, d.comm, s);
-  }
-  if (d.rank < d.nranks - 1) {
-    a.Send(v + (long long)(ohi0 - 1) * plane_elems, (size_t)plane_elems, dt, d.rank + 1, d.comm, s);
-    a.Recv(v + (long long)ohi0 * plane_elems, (size_t)plane_elems, dt, d.rank + 1, d.comm, s);
-  }
+  if (lower >= 0) a.Send(v + (long long)olo0 * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s);
+  if (upper >= 0) a.Recv(v + (long long)ohi0 * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s);
+  if (upper >= 0) a.Send(v + (long long)(ohi0 - 1) * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s);
+  if (lower >= 0) a.Recv(v + (long long)(olo0 - 1) * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s);
   return a.GroupEnd();
+}
+
+// point-to-point helpers of the slab-periodic boundary condition (api.cu launch_bcs)
+template <typename T>
+static inline ncclResult_t dist_send(const Dist& d, const T* p, long long n, int peer, cudaStream_t s) {
+  return nccl_api().Send(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s);
+}
+template <typename T>
+static inline ncclResult_t dist_recv(const Dist& d, T* p, long long n, int peer, cudaStream_t s) {
+  return nccl_api().Recv(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s);
 }
 
 }  // namespace pa

@@ -33,16 +33,19 @@ def partition(n0: int, world: int) -> list[tuple[int, int]]:
     return out
 
 
-def slab_layout(n0: int, rank: int, world: int) -> dict:
+def slab_layout(n0: int, rank: int, world: int, periodic: bool = False) -> dict:
     """Local block of rank `rank`: owned planes [start, stop) plus one ghost plane towards each
-    existing neighbour.  All indices as the C ABI's pa_grid wants them."""
+    existing neighbour.  `periodic`: axis 0 carries Periodic BCs, so rank 0 and rank world-1 are
+    neighbours too and every rank has both ghost planes (the wrap-around pair of SURVEY.md §8e).
+    All indices as the C ABI's pa_grid wants them (goff0 is -1 on rank 0 of a periodic slab)."""
     start, stop = partition(n0, world)[rank]
-    lo_ghost = 1 if rank > 0 else 0
-    hi_ghost = 1 if rank < world - 1 else 0
+    ring = bool(periodic) and world > 1
+    lo_ghost = 1 if (rank > 0 or ring) else 0
+    hi_ghost = 1 if (rank < world - 1 or ring) else 0
     if stop - start < 3:
         raise ValueError(f"slab decomposition needs >= 3 planes per rank (n0={n0}, world={world})")
     return {
-        "rank": rank, "world": world, "start": start, "stop": stop,
+        "rank": rank, "world": world, "start": start, "stop": stop, "periodic": ring,
         "gn0": n0, "goff0": start - lo_ghost, "olo0": lo_ghost, "ohi0": lo_ghost + (stop - start),
         "n0_local": (stop - start) + lo_ghost + hi_ghost,
     }
@@ -50,21 +53,32 @@ def slab_layout(n0: int, rank: int, world: int) -> dict:
 
 class SlabMesh(Mesh):
     """A Mesh whose tensors cover only this rank's slab (owned planes + ghost planes) of the
-    global grid.  `nx` is the LOCAL shape; `global_nx` the full one; `slab` the layout."""
+    global grid.  `nx` is the LOCAL shape; `global_nx` the full one; `slab` the layout.
+    Pass `periodic=True` when the Field on this mesh has Periodic BCs on the two x faces."""
 
     def __init__(self, domain, obstacle, spacing, rank: int, world: int, device: str = "cuda",
-                 dtype: str | int = "double"):
-        self._slab_rank, self._slab_world = int(rank), int(world)
+                 dtype: str | int = "double", periodic: bool = False):
+        self._slab_rank, self._slab_world, self._slab_periodic = int(rank), int(world), bool(periodic)
         super().__init__(domain, obstacle, spacing, device, dtype)
 
     def _localize(self) -> None:
         if self.dim != 3:
             raise NotImplementedError("SlabMesh: slab decomposition is implemented for 3-D meshes")
         self.global_nx = list(self._nx)
-        self.slab = slab_layout(self._nx[0], self._slab_rank, self._slab_world)
+        n0 = self._nx[0]
+        self.slab = slab_layout(n0, self._slab_rank, self._slab_world, self._slab_periodic)
         a, b = self.slab["goff0"], self.slab["goff0"] + self.slab["n0_local"]
-        self._x_host[0] = self._x_host[0][a:b].clone()
+        idx = torch.tensor([i % n0 for i in range(a, b)], dtype=torch.long)  # wrap-around ghosts
+        self._x_host[0] = self._x_host[0][idx].clone()
         self._nx = [self.slab["n0_local"], self._nx[1], self._nx[2]]
+
+    def local_slice(self, t: torch.Tensor) -> torch.Tensor:
+        """This rank's block (owned + ghost planes, wrap-around included) of a GLOBAL
+        `(1, N0, ny, nz)` tensor."""
+        n0 = self.slab["gn0"]
+        a, b = self.slab["goff0"], self.slab["goff0"] + self.slab["n0_local"]
+        idx = torch.tensor([i % n0 for i in range(a, b)], dtype=torch.long, device=t.device)
+        return t.index_select(1, idx).contiguous()
 
     def owned(self, t: torch.Tensor) -> torch.Tensor:
         """View of the owned planes of a local `(1, n0_local, ny, nz)` tensor."""

@@ -181,10 +181,13 @@ def _no_adjust(var: Field) -> Tensor:
 
 
 class Ddt(Operators):
-    """Explicit Euler time derivative.  `solver.set_eq(fdm.ddt(var) + <spatial ops> == rhs)` then
-    `solver.solve()` advances `var` by `n_steps` steps of
-        var_new[slicer] = var + dt * (rhs - A_spatial(var)),   BCs,   var.update_time().
-    Not in the reference (its Ddt registers nothing, fdm.py:322-339)."""
+    """Euler time derivative.  `solver.set_eq(fdm.ddt(var) + <spatial ops> == rhs)` then
+    `solver.solve()` advances `var` by `n_steps` steps; the solver config's `method` picks the scheme:
+      "euler":                 explicit,  var_new[slicer] = var + dt * (rhs - A_spatial(var)), BCs;
+      "cg"/"bicgstab"/"jacobi": implicit,  (1/dt) var_new + A_spatial(var_new) = rhs + (1/dt) var
+                                solved with that method (linalg.euler_implicit);
+    each step ends with var.update_time().  Not in the reference (its Ddt registers nothing,
+    fdm.py:322-339; intended semantics in tests/test_fdm.py:275-299)."""
 
     def __call__(self, var: Field) -> "Ddt":
         try:
@@ -193,7 +196,7 @@ class Ddt(Operators):
             raise AttributeError("FDM: No time step is specified.")
         self._var = var
         self._ops[0] = _entry("Ddt", self.Aop, var, (dt,), None, _no_adjust)
-        self._ops[0]["other"] = {"scheme": "euler_explicit"}
+        self._ops[0]["other"] = {"scheme": "euler"}
         return self
 
     var = property(lambda self: self._var)  # type: ignore[assignment]

@@ -52,7 +52,8 @@ def solve(var: Field, rhs: Tensor, Aop: Callable, eqs: dict[int, OPStype], confi
     )
 
 
-def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mesh: Mesh) -> N.Report:
+def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mesh: Mesh,
+         implicit_ddt: bool = False) -> N.Report:
     from pyapes_b200.solver.ops import L_lower_equation
 
     x = var()
@@ -69,7 +70,7 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     slab = getattr(mesh, "slab", None)
     grid = L.lower_grid(mesh.nx, var.bcs, slab)
     faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd)
-    eq, keep_e = L_lower_equation(eqs, var)
+    eq, keep_e = L_lower_equation(eqs, var, implicit_ddt)
     lib = N.lib()
     ws_bytes = lib.pa_solver_workspace_bytes(grid, code, N.METHOD[method])
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -169,6 +170,44 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
         var.VAR, var.VARo = (alt, x) if in_alt.value else (x, alt)
     del keep_f, keep_e
     return _write_report(n_steps, 0.0, True)
+
+
+def euler_implicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig, mesh: Mesh) -> ReportType:
+    """`n_steps` implicit Euler steps of d(var)/dt + A_spatial(var) = rhs: per step solve
+        (1/dt) var_new + A_spatial(var_new) = rhs + (1/dt) var_old
+    with `config["method"]` (cg / bicgstab / jacobi), initial guess var_old, then
+    `var.update_time()`.  The reference's Ddt is a stub (fdm.py:315-353); this is the semantics
+    its test intends (tests/test_fdm.py:275-299), SURVEY.md §8f item 4.  The report is the last
+    step's; `itr` sums the steps."""
+    from pyapes_b200.solver.ops import inv_dt_of
+
+    method = str(config["method"]).lower()
+    if method not in _SOLVERS:
+        raise RuntimeError(
+            f"Linalg: solver only supports CG and BICGSTAB. {method=} would be a typo or is not supported."
+        )
+    x = var()
+    N.require_cuda(x, "field")
+    c = inv_dt_of(eqs, x.dtype)
+    n_steps = int(config.get("n_steps", 1))
+    src = torch.zeros_like(x) if rhs is None else (rhs if rhs.is_contiguous() else rhs.contiguous())
+    rhs_eff = torch.empty_like(x)
+    label = {"cg": "CG", "bicgstab": "BICGSTAB", "jacobi": "JACOBI"}[method]
+    total, rep = 0, None
+    for _ in range(n_steps):
+        x = var()
+        N.check(N.lib().pa_axpy(N.dtype_code(x.dtype), x.numel(), c, x.data_ptr(), src.data_ptr(), rhs_eff.data_ptr(),
+                                N.current_stream(x.device)))
+        rep = _run(method, var, rhs_eff, eqs, config, mesh, implicit_ddt=True)
+        total += rep.itr
+        var.update_time()
+        if rep.status == N.MAXIT:
+            break
+    if rep is None:
+        return _write_report(0, 0.0, True)
+    out = _finish(rep, config, label, method == "bicgstab")
+    out["itr"] = total if n_steps > 1 else out["itr"]
+    return out
 
 
 def _apply_bc_otf(var: Field, mesh: Mesh) -> Field:

@@ -13,7 +13,7 @@ from torch import Tensor
 from pyapes_b200 import _lower as L
 from pyapes_b200 import _native as N
 from pyapes_b200.solver.fdm import Operators
-from pyapes_b200.solver.linalg import ReportType, euler_explicit, solve
+from pyapes_b200.solver.linalg import ReportType, euler_explicit, euler_implicit, solve
 from pyapes_b200.solver.tools import SolverConfig
 from pyapes_b200.solver.types import OPStype
 from pyapes_b200.variables import Field
@@ -54,7 +54,11 @@ class Solver:
         )
         assert self.config is not None, "Solver: config is missing!"
         if self.eqs[0]["name"].lower() == "ddt":
-            self.report = euler_explicit(self.var, self.rhs, self.eqs, self.config["fdm"], self.var.mesh)
+            # time stepping: method "euler" = explicit Euler steps; a linear-solver name = implicit
+            # Euler, one solve per step
+            method = str(self.config["fdm"].get("method", "euler")).lower()
+            step = euler_explicit if method == "euler" else euler_implicit
+            self.report = step(self.var, self.rhs, self.eqs, self.config["fdm"], self.var.mesh)
         else:
             self.report = solve(self.var, self.rhs, _Aop, self.eqs, self.config["fdm"], self.var.mesh)
         return self.report
@@ -81,8 +85,15 @@ def _Aop(target: Field, eqs: dict[int, OPStype]) -> Tensor:
     return out
 
 
-def L_lower_equation(eqs: dict[int, OPStype], target: Field):
-    """OPStype dicts -> pa_equation (spatial operators only, in key order)."""
+def inv_dt_of(eqs: dict[int, OPStype], dtype) -> float:
+    """1/dt of the leading Ddt entry, rounded once in the field dtype."""
+    return float(torch.ones(1, dtype=dtype)[0] / float(eqs[0]["param"][0]))
+
+
+def L_lower_equation(eqs: dict[int, OPStype], target: Field, implicit_ddt: bool = False):
+    """OPStype dicts -> pa_equation: the spatial operators in key order; with `implicit_ddt` the
+    leading Ddt becomes a diagonal star operator (1/dt)*phi appended LAST, where the reference's
+    `_Aop` adds the time-derivative term (ops.py:133-134,151-152)."""
     if target.dim != 1:
         raise NotImplementedError(
             "pyapes_b200: only scalar fields (Field.dim == 1) are on the CUDA path (SURVEY.md §0 item 5)"
@@ -126,5 +137,15 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field):
         k += 1
     if k == 0:
         raise ValueError("pyapes_b200: equation has no spatial operator")
+    if implicit_ddt and eqs[0]["name"].lower() == "ddt":
+        if k >= N.PA_MAX_OPS:
+            raise NotImplementedError(f"pyapes_b200: at most {N.PA_MAX_OPS - 1} spatial operators next to ddt")
+        op = N.Op()
+        op.kind, op.sign, op.has_param, op.param = N.OP_STAR, 1.0, 0, 1.0
+        c = inv_dt_of(eqs, dtype)
+        for cls in range(3):
+            op.coef[2][cls][1] = c  # kernel axis 2 is active for every mesh dimension
+        eq.ops[k] = op
+        k += 1
     eq.nops = k
     return eq, keep

@@ -417,3 +417,66 @@ def test_cpu_field_fails_loudly():
     s.set_eq(FDM().laplacian(var) == 1.0)
     with pytest.raises(NativeError):
         s.solve()
+
+
+@pytest.mark.parametrize("method,shape,limiter", [
+    ("cg", [20, 18, 24], None),          # heat equation: ddt - nu*laplacian (SPD), 3-D
+    ("cg", [33, 40], None),              # 2-D
+    ("jacobi", [20, 18, 24], None),
+    ("bicgstab", [20, 18, 24], "upwind_fd"),  # transient advection-diffusion
+    ("bicgstab", [33, 40], "upwind"),
+])
+def test_implicit_euler_vs_oracle(method, shape, limiter):
+    """fdm.ddt with a linear-solver method = implicit Euler (not in the reference: its Ddt is a
+    stub; oracle = the definition in oracle.fd_oracle.implicit_euler_step)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    nd = len(shape)
+    kinds = (["dirichlet", "dirichlet", "neumann", "dirichlet", "dirichlet", "symmetry"])[: 2 * nd]
+    vals = ([0.0, 1.0, 0.5, 0.0, -0.25, None])[: 2 * nd]
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, DEV, "double")
+    var = Field("c", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    g = torch.Generator().manual_seed(99)
+    phi0 = torch.rand(1, *shape, generator=g, dtype=torch.float64)
+    src = torch.rand(1, *shape, generator=g, dtype=torch.float64)
+    var.set_var_tensor(phi0.to(DEV))
+    nu, u = 0.1, 1.0
+    dt = 5.0 * min(mesh._dx) ** 2 / nu  # 20x beyond the explicit stability limit
+    var.set_time(dt, 0.0)
+    lock = method == "bicgstab"
+    steps = 1 if lock else 3  # lockstep BiCGSTAB: one step of exactly max_it iterations
+    tol, max_it = (1e-30, 6) if lock else (1e-9, 4000)
+    fdm = FDM({"div": {"limiter": limiter or "none", "edge": False}})
+    solver = Solver({"fdm": {"method": method, "tol": tol, "max_it": max_it, "report": False, "n_steps": steps}})
+    rhs_d = src.to(DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if limiter:
+            solver.set_eq(fdm.ddt(var) + fdm.div(u, var) - fdm.laplacian(nu, var) == rhs_d)
+        else:
+            solver.set_eq(fdm.ddt(var) - fdm.laplacian(nu, var) == rhs_d)
+        rep = solver.solve()
+    assert var.t == pytest.approx(steps * dt)
+
+    xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
+    bcs = [O.FaceBC(f, k, v) for f, k, v in zip(O.FACES, kinds, vals)]
+    terms = ([O.Term("div", 1.0, u, limiter)] if limiter else []) + [O.Term("laplacian", -1.0, nu), O.Term("ddt", 1.0, dt)]
+    x = phi0.clone()
+    eq = O.Equation(terms, dx, xs, bcs).build(x)
+    rhs_o = eq.adjust_rhs(x, src.clone())
+    assert torch.equal(solver.rhs.cpu(), rhs_o)
+    total = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(steps):
+            x, rep_o, _ = O.implicit_euler_step(eq, x, rhs_o, dt, method, tol, max_it)
+            total += rep_o["itr"]
+    scale = x.abs().max().item()
+    assert rep["itr"] == total, (rep, total)
+    err = (var().cpu() - x).abs().max().item()
+    assert err <= (1e-7 if lock else 1e-9) * scale, err

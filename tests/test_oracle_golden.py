@@ -146,3 +146,43 @@ def test_solver_fixtures(case):
     if "solution" in case:
         scale = case["solution"].abs().max().item() + 1e-300
         assert (sol - case["solution"]).abs().max().item() <= 1e-9 * scale
+
+
+def test_oracle_implicit_euler_matches_dense_solve():
+    """The oracle's implicit Euler step (no reference counterpart) against a dense linear solve
+    of (I/dt + A) x = rhs + x_old/dt on a tiny 2-D grid, A assembled column by column from the
+    oracle's own (reference-pinned) operator application."""
+    import warnings
+
+    from oracle import fd_oracle as O
+
+    shape = [7, 6]
+    xs, dx = O.make_axes([0.0, 0.0], [1.0, 1.0], shape)
+    kinds, vals = ["dirichlet", "dirichlet", "neumann", "dirichlet"], [0.0, 1.0, 0.5, -0.25]
+    bcs = [O.FaceBC(f, k, v) for f, k, v in zip(O.FACES, kinds, vals)]
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(1, *shape, generator=g, dtype=torch.float64)
+    src = torch.rand(1, *shape, generator=g, dtype=torch.float64)
+    dt, nu = 0.05, 0.3
+    eq = O.Equation([O.Term("laplacian", -1.0, nu), O.Term("ddt", 1.0, dt)], dx, xs, bcs).build(x0)
+    rhs = eq.adjust_rhs(x0, src.clone())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x1, rep, _ = O.implicit_euler_step(eq, x0, rhs, dt, "bicgstab", 1e-13, 500)
+    assert rep["converge"]
+    # dense system on the solver region; boundary cells hold their BC values (taken from x1)
+    sl = O.solver_region(2, bcs)
+    n = x0.numel()
+    idx = torch.zeros(shape, dtype=torch.bool)
+    idx[sl] = True
+    unknown = idx.flatten().nonzero().flatten()
+    A = torch.zeros(n, n, dtype=torch.float64)
+    for j in range(n):
+        e = torch.zeros(n, dtype=torch.float64)
+        e[j] = 1.0
+        A[:, j] = eq.aop(e.view(1, *shape)).flatten()
+    b = (rhs + x0 / dt).flatten()
+    known = (~idx.flatten()).nonzero().flatten()
+    xk = x1.flatten()[known]
+    sol = torch.linalg.solve(A[unknown][:, unknown], b[unknown] - A[unknown][:, known] @ xk)
+    assert torch.allclose(x1.flatten()[unknown], sol, rtol=1e-9, atol=1e-11)

@@ -79,3 +79,34 @@ def test_partition_covers_everything():
         assert sum(l["ohi0"] - l["olo0"] for l in lay) == n0
     with pytest.raises(ValueError):
         slab_layout(8, 0, 4)
+
+
+def test_periodic_slab_layout_and_region():
+    """Periodic x faces: every rank carries both ghost planes (ring), rank 0 starts at global -1,
+    the solver region covers every owned plane, and local_slice wraps around."""
+    sys.path.insert(0, ROOT)
+    from pyapes_b200 import _lower as L
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.parallel import SlabMesh, slab_layout
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    lay = [slab_layout(11, r, 2, periodic=True) for r in range(2)]
+    assert [(l["goff0"], l["olo0"], l["ohi0"], l["n0_local"]) for l in lay] == [(-1, 1, 7, 8), (5, 1, 6, 7)]
+    assert slab_layout(11, 0, 1, periodic=True)["n0_local"] == 11  # one rank: the kernels wrap themselves
+    kinds = ["periodic", "periodic", "neumann", "symmetry", "dirichlet", "dirichlet"]
+    vals = [None, None, 0.5, None, 0.0, 0.0]
+    glob = torch.arange(11, dtype=torch.float64).view(1, 11, 1, 1).expand(1, 11, 5, 6)
+    for r in range(2):
+        mesh = SlabMesh(Box[0:1, 0:1, 0:1], None, [11, 5, 6], r, 2, "cpu", periodic=True)
+        var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+        g = L.lower_grid(mesh.nx, var.bcs, mesh.slab)
+        assert (g.lo[0], g.hi[0]) == (g.olo0, g.ohi0) == (1, mesh.nx[0] - 1)
+        planes = mesh.local_slice(glob)[0, :, 0, 0].tolist()
+        assert planes == ([10.0, 0, 1, 2, 3, 4, 5, 6] if r == 0 else [5.0, 6, 7, 8, 9, 10, 0])
+        assert mesh.x[0][0].item() == pytest.approx((planes[0]) / 10.0)
+    # a periodic Field on a non-periodic slab (or the reverse) is refused when lowering
+    mesh = SlabMesh(Box[0:1, 0:1, 0:1], None, [11, 5, 6], 0, 2, "cpu")
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    with pytest.raises(ValueError):
+        L.lower_grid(mesh.nx, var.bcs, mesh.slab)
