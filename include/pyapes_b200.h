@@ -125,7 +125,11 @@ typedef struct {
    * IndexError for dim > 1), scaled by adv_const; for pa_grad_apply any non-zero value replaces
    * component a on the faces normal to axis a.  Uses dx[]. */
   int32_t edge;
-  int32_t reserved;
+  /* *_FIELD kinds: 1 = the advection field IS the unknown of the solve (nonlinear advection,
+   * fdm.div(var, var), fdm.py:306-312): the solvers read it from the current iterate, which moves
+   * every iteration as the reference rebinds var (linalg.py:122-125,253-256); `adv` is then only
+   * used by pa_stencil_apply / the initial state.  0 = `adv` is a fixed array. */
+  int32_t adv_is_iterate;
   double adv_const;
   /* optional per-index coefficient tables: coef_tab[axis] points to n[axis]*3 device values
    * [Ap, Ac, Am] per index along that kernel axis, used instead of coef[axis][cls][] — the

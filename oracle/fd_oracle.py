@@ -463,6 +463,13 @@ class Equation:
     xs: list[Tensor]
     bcs: list[FaceBC]
     rz: bool = False  # axisymmetric (r, z) mesh: Cylinder geometry
+    # nonlinear advection, Term("div", param="self") == fdm.div(var, var): the Div coefficients are
+    # rebuilt from the LIVE unknown on every application (fdm.py:306-312); the solvers below move
+    # `live` where the reference rebinds var (linalg.py:122-125, 236-238, 253-256)
+    live: Any = field(default=None, repr=False)
+
+    def set_live(self, x: Tensor) -> None:
+        self.live = x
 
     def build(self, phi: Tensor) -> "Equation":
         rz_xs = self.xs if self.rz else None
@@ -472,7 +479,11 @@ class Equation:
             elif t.kind == "grad":
                 t.coeffs = grad_coeffs(phi, self.dx, self.bcs)
             elif t.kind == "div":
-                t.coeffs = div_coeffs(t.param, phi, self.dx, self.bcs, t.limiter, rz_xs)
+                if isinstance(t.param, str):  # "self": built per application in aop()
+                    self.live = phi
+                    t.coeffs = None
+                else:
+                    t.coeffs = div_coeffs(t.param, phi, self.dx, self.bcs, t.limiter, rz_xs)
             elif t.kind == "ddt":
                 # implicit Euler: the linear part of (phi - phi_old)/dt, as a multiplication by
                 # 1/dt rounded in the field dtype (NOT in the reference, see implicit_euler_step)
@@ -491,7 +502,8 @@ class Equation:
             elif t.kind == "grad":
                 rhs += grad_rhs_adjust(phi, self.dx, self.bcs)
             else:
-                rhs += div_rhs_adjust(t.param, phi, self.dx, self.bcs, t.limiter)
+                u = phi if isinstance(t.param, str) else t.param
+                rhs += div_rhs_adjust(u, phi, self.dx, self.bcs, t.limiter)
         return rhs
 
     def aop(self, phi: Tensor) -> Tensor:
@@ -506,7 +518,10 @@ class Equation:
                     ax = ax * t.param
                 ax = (ax * t.sign).view(phi.size())  # only legal in 1-D (ops.py:145-147)
             else:
-                ax = apply_scalar_op(t.coeffs, phi)
+                coeffs = t.coeffs
+                if t.kind == "div" and isinstance(t.param, str):
+                    coeffs = div_coeffs(self.live, phi, self.dx, self.bcs, t.limiter, self.xs if self.rz else None)
+                ax = apply_scalar_op(coeffs, phi)
                 if t.kind == "laplacian" and t.param is not None:
                     ax = ax * t.param
                 ax = ax * t.sign
@@ -556,6 +571,7 @@ def cg(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int):
     sl = solver_region(x.dim() - 1, eq.bcs)
     tol, itr = 1.0, 0
     apply_bcs(x, eq.xs, eq.bcs)
+    eq.set_live(x)
     Ad = torch.zeros_like(rhs)
     r = torch.zeros_like(x)
     r[0][sl] = rhs[0][sl] - eq.aop(x)[0][sl]
@@ -567,6 +583,7 @@ def cg(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int):
         alpha = _nan_to_num(torch.sum(r * r, dim=axes) / torch.sum(d * Ad, dim=axes))
         x = x + alpha * d
         apply_bcs(x, eq.xs, eq.bcs)
+        eq.set_live(x)
         beta_denom = torch.sum(r * r, dim=axes)
         r -= alpha * Ad
         tol = tolerance_check(x, x_old)
@@ -585,6 +602,7 @@ def bicgstab(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int
     sl = solver_region(x.dim() - 1, eq.bcs)
     itr = 0
     apply_bcs(x, eq.xs, eq.bcs)
+    eq.set_live(x)
     r0 = torch.zeros_like(x)
     r0[0][sl] = rhs[0][sl] - eq.aop(x)[0][sl]
     r = r0.clone()
@@ -611,6 +629,7 @@ def bicgstab(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int
         if tol <= tolerance:
             x = x + alpha * p
             apply_bcs(x, eq.xs, eq.bcs)
+            eq.set_live(x)
             finished = True
             continue
         t[0][sl] = eq.aop(s)[0][sl]
@@ -618,6 +637,7 @@ def bicgstab(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int
         rho_next = -omega * torch.sum(r0 * t, dim=axes)
         x = x + alpha * p + s * omega
         apply_bcs(x, eq.xs, eq.bcs)
+        eq.set_live(x)
         r = s - omega * t
         tol = tolerance_check(s, omega * t)
         if tol <= tolerance:
@@ -638,6 +658,7 @@ def jacobi(eq: Equation, x: Tensor, rhs: Tensor, tolerance: float, max_it: int):
     x_old = x
     while tol > tolerance:
         x_old = x.clone()
+        eq.set_live(x)
         ax = eq.aop(x)
         x = x.clone()
         x[0][sl] = x_old[0][sl] + (rhs[0][sl] - ax[0][sl]) / diag[0][sl]
@@ -654,6 +675,7 @@ def euler_step(eq: Equation, x: Tensor, rhs: Tensor | None, dt: float) -> Tensor
     """NOT in the reference (fdm.Ddt is a stub, fdm.py:315-353).  Explicit Euler
     (SURVEY.md §8a A16): phi_new[sl] = phi + dt*(rhs - Aop(phi)), then BCs."""
     sl = solver_region(x.dim() - 1, eq.bcs)
+    eq.set_live(x)
     ax = eq.aop(x)
     src = torch.zeros_like(x) if rhs is None else rhs
     new = x.clone()

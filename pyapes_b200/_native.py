@@ -59,7 +59,7 @@ class Op(C.Structure):
         ("zero_ap_hi", C.c_int32 * 3),
         ("param_field", C.c_void_p),
         ("edge", C.c_int32),
-        ("reserved", C.c_int32),
+        ("adv_is_iterate", C.c_int32),
         ("adv_const", C.c_double),
         ("coef_tab", C.c_void_p * 3),
     ]

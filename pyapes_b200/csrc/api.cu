@@ -608,7 +608,19 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     if (rcs != PA_OK) return rcs;
   }
   GridDev g = make_grid(*pg);
+  // nonlinear advection (pa_op.adv_is_iterate): the operator reads its advection speed from the
+  // current iterate, which ping-pongs between x and x_alt -> one equation per buffer
   EqDev<T> eq = make_eq<T>(*peq);
+  EqDev<T> eq_alt = eq;
+  bool nonlinear = false;
+  for (int k = 0; k < peq->nops; ++k)
+    if (peq->ops[k].kind != PA_OP_STAR && peq->ops[k].adv_is_iterate) {
+      eq.op[k].adv = x;
+      eq_alt.op[k].adv = x_alt;
+      nonlinear = true;
+    }
+  if (nonlinear && dist)
+    return fail(PA_ERR_UNSUPPORTED, "multi-GPU: nonlinear advection div(var, var) on slabs is not built");
   int nvec = method_nvec(method);
   if (ws_size < ws_bytes(g.cells, sizeof(T), nvec))
     return fail(PA_ERR_ARG, "workspace too small (see pa_solver_workspace_bytes)");
@@ -715,13 +727,14 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   }
 
   auto iteration = [&](T* cur, T* nxt) {
+    const EqDev<T>& e = (cur == x) ? eq : eq_alt;
     if (method == PA_METHOD_CG)
-      cg_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
+      cg_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
                       use_tma ? &tmap : nullptr, dist);
     else if (method == PA_METHOD_BICGSTAB)
-      bicgstab_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, pw, dist);
+      bicgstab_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, pw, dist);
     else
-      jacobi_iteration<T>(L, g, eq, nfaces, faces, w, cur, nxt, rhs, pw, dist);
+      jacobi_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, rhs, pw, dist);
   };
 
   const long long max_iters = (method == PA_METHOD_BICGSTAB)
@@ -1065,13 +1078,21 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   int rcs = solver_stream(caller, &s);
   if (rcs != PA_OK) return rcs;
   GridDev g = make_grid(*pg);
-  EqDev<T> eq = make_eq<T>(*peq);
+  EqDev<T> eq_a = make_eq<T>(*peq);
+  EqDev<T> eq_b = eq_a;  // nonlinear advection: the speed is the field being advanced (see run_solver)
+  for (int k = 0; k < peq->nops; ++k)
+    if (peq->ops[k].kind != PA_OP_STAR && peq->ops[k].adv_is_iterate) {
+      if (dist) return fail(PA_ERR_UNSUPPORTED, "multi-GPU: nonlinear advection div(var, var) on slabs is not built");
+      eq_a.op[k].adv = a;
+      eq_b.op[k].adv = b;
+    }
   Launcher L{s};
   const bool tma = pw_eligible<T>(g, *peq, nfaces, faces);
   TilePlan tile;
   if (tma) pw_tile_plan<T>(g, tile);
   const bool stat = static_shell(nfaces, faces) != 0;
   auto one = [&](T* cur, T* nxt, bool bcs) {
+    const EqDev<T>& eq = (cur == a) ? eq_a : eq_b;
     bool done = false;
     if (tma)
       done = launch_star_tma<T, PW_EULER>(s, g, eq, tile, cur, rhs, nxt, nullptr, (T)dt, nullptr, nullptr, ST_NONE);

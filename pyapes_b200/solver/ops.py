@@ -113,6 +113,7 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field, implicit_ddt: bool 
             raise NotImplementedError(f"pyapes_b200: at most {N.PA_MAX_OPS} spatial operators per equation")
         coeffs = e["A_coeffs"]
         param = None
+        nonlinear = False
         if name in ("laplacian", "grad"):
             param = e["param"][0]
             if name == "grad" and nd != 1:
@@ -123,15 +124,14 @@ def L_lower_equation(eqs: dict[int, OPStype], target: Field, implicit_ddt: bool 
         elif name == "div":
             var_j, cfg = e["param"]
             if isinstance(var_j, Field):
-                if var_j is target:
-                    raise NotImplementedError(
-                        "pyapes_b200: nonlinear advection div(var, var) is not built yet (SURVEY.md §8(f) item 3)"
-                    )
                 from pyapes_b200.solver.fdc import FDC
 
                 coeffs = FDC(cfg).div.build_A_coeffs(var_j, target, cfg)  # live field (fdm.py:309-312)
+                nonlinear = var_j is target  # div(var, var): the coefficients follow the iterate
         op, kp = L.lower_op(coeffs, nd, dtype, sign=float(e["sign"]), param=param, field_shape=target().shape,
                             field_device=target().device)
+        if name == "div" and nonlinear:
+            op.adv_is_iterate = 1
         eq.ops[k] = op
         keep.append(kp)
         k += 1
