@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the hot path: 3-D fp64 matrix-free CG on a Poisson problem (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--iters 50] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--iters 200] [--impl reference]
 
 A *step* is one `solver.solve()` of `--iters` CG iterations (tol = 1e-30 so the count is
 fixed) on an n^3 Dirichlet Poisson problem with a seeded random RHS.
@@ -80,12 +80,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
@@ -93,7 +94,8 @@ class ClockSampler:
                 pass
         busy = [v for v in sm if v > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": statistics.median(pw) if pw else None}
 
 
 def make_problem(n, device, rank=0, world=1, dtype="double"):
@@ -307,11 +309,15 @@ def run_ours(args):
 
     # --- end to end (host buffers) ------------------------------------------------------------
     run_e2e(2)
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
     barrier()
     e0.record()
     run_e2e(args.steps)
     e1.record()
     barrier()
+    clocks_e2e = sampler2.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -359,7 +365,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_v, "unit": "GLUP/s", "cores": cpu_thr, "kind": "port",
                          "sample": f"{args.cpu_n}^3 Dirichlet Poisson, {cpu_it} CG iterations, oracle (torch CPU fp64), {cpu_s:.1f} s"},
         "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": int(rhs_h.numel() * 8),
-                "d2h_bytes_per_step": int(out_h.numel() * 8)},
+                "d2h_bytes_per_step": int(out_h.numel() * 8), "clocks": clocks_e2e},
         "gpu_launches": int(launches_timed),
         "clocks": clocks,
     }
@@ -374,7 +380,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=512, help="grid points per axis per GPU")
-    ap.add_argument("--iters", type=int, default=50, help="CG iterations per step")
+    # the throughput run is a fixed-count solve with max_it = 200
+    ap.add_argument("--iters", type=int, default=200, help="CG iterations per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-n", type=int, default=256, help="grid of the bounded CPU sample (reference arm)")
     ap.add_argument("--cpu-iters", type=int, default=20, help="CG iterations of the CPU sample (~10-30 s)")

@@ -726,8 +726,17 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     return PA_OK;
   }
 
+  // fused TMA CG kernels with an implicit-Euler term: operator 0 + diagonal shift (plan_tma)
+  EqDev<T> eq_cg = eq;
+  if (use_tma && peq->nops == 2) {
+    double c = 0.0;
+    diagonal_op(peq->ops[1], &c);
+    eq_cg.nops = 1;
+    eq_cg.op[0].has_shift = 1;
+    eq_cg.op[0].shift = (T)c;
+  }
   auto iteration = [&](T* cur, T* nxt) {
-    const EqDev<T>& e = (cur == x) ? eq : eq_alt;
+    const EqDev<T>& e = use_tma ? eq_cg : ((cur == x) ? eq : eq_alt);
     if (method == PA_METHOD_CG)
       cg_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, tiled, plan, cur == x ? 0 : 1, nullptr,
                       use_tma ? &tmap : nullptr, dist);
@@ -762,7 +771,11 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   long long it = 0;
   int rc = PA_OK;
   while (true) {
+    // never queue more iterations than max_it allows (each queued iteration past `done` is a
+    // train of no-op launches)
     long long chunk = check_every;
+    const long long left = max_iters + 1 - it;
+    if (left < chunk) chunk = left > 2 ? left + (left & 1) : 2;
     for (long long k = 0; k < chunk; k += 2) {
       if (gexec) {
         cudaError_t e = cudaGraphLaunch(gexec, stream);

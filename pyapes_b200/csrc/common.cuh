@@ -63,6 +63,10 @@ struct OpDev {
   int edge;
   T adv_const;
   const T* coef_tab[3];
+  // fused CG kernels only: a second, purely diagonal operator c*phi (the implicit-Euler term
+  // (1/dt)*phi that `ddt` appends) folded into this one:  A(phi) = (0 + star(phi)) + shift*phi
+  int has_shift;
+  T shift;
 };
 
 template <typename T>
@@ -95,6 +99,8 @@ inline EqDev<T> make_eq(const pa_equation& e) {
     o.edge = s.edge;
     o.adv_const = (T)s.adv_const;
     for (int a = 0; a < 3; ++a) o.coef_tab[a] = (const T*)s.coef_tab[a];
+    o.has_shift = 0;
+    o.shift = (T)0;
   }
   return d;
 }

@@ -210,12 +210,29 @@ inline bool plan_tma_k(const GridDev& g, const T* x, const T* x_alt, const T* r,
          make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) && make_map<T>(&tp.d_halo[1], d1, g, C::BOXZ, C::BOXY);
 }
 
+// a STAR operator that is c*phi and nothing else, with sign +1 and no parameter: the form in
+// which the host layer lowers the implicit-Euler term (pyapes_b200/solver/ops.py)
+inline bool diagonal_op(const pa_op& o, double* c) {
+  if (o.kind != PA_OP_STAR || o.param_field != nullptr || o.edge != 0 || o.has_param || o.sign != 1.0) return false;
+  for (int a = 0; a < 3; ++a) {
+    if (o.coef_tab[a]) return false;
+    for (int cls = 0; cls < 3; ++cls)
+      for (int k = 0; k < 3; ++k) {
+        const bool centre = (a == 2 && k == 1);
+        if (!centre && o.coef[a][cls][k] != 0.0) return false;
+        if (centre && o.coef[a][cls][k] != o.coef[2][0][1]) return false;
+      }
+  }
+  if (c) *c = o.coef[2][0][1];
+  return true;
+}
+
 template <typename T>
 inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces,
                      const T* x, const T* x_alt, const T* r, const T* d0, const T* d1, TmaPlan& tp) {
   const pa_op& o = eq.ops[0];
-  if (eq.nops != 1 || o.kind != PA_OP_STAR || o.param_field != nullptr || o.edge != 0 || o.coef_tab[0] ||
-      o.coef_tab[1] || o.coef_tab[2])
+  if (!(eq.nops == 1 || (eq.nops == 2 && diagonal_op(eq.ops[1], nullptr))) || o.kind != PA_OP_STAR ||
+      o.param_field != nullptr || o.edge != 0 || o.coef_tab[0] || o.coef_tab[1] || o.coef_tab[2])
     return false;
   if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;  // 1-D meshes stay on the generic kernels
   for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
@@ -299,7 +316,11 @@ __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, con
   }
 }
 
-// the star operator on the thread's cells (same arithmetic order as eval_equation)
+// the star operator on the thread's cells: same bits as eval_equation, with two exact shortcuts --
+// the accumulator starts from the first axis' sum instead of 0 + sum (they differ only in the sign
+// of an all-zero sum, erased by the `0 + acc` below), and (acc * param) * sign is one
+// multiplication by param*sign (sign = +-1; rounding is symmetric), skipped when it is exactly 1.
+// Kernel axis 0 is always active on this path (plan_tma).
 template <typename T, typename K, bool LEAN, typename F>
 __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K>& c, const T (&cx)[3],
                                            bool actx, const T (&vm)[K::RY][VecOf<T>::N],
@@ -307,6 +328,8 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
                                            const T (&up)[VecOf<T>::N], const T (&dn)[VecOf<T>::N],
                                            const T (&zl)[K::RY], const T (&zr)[K::RY], F emit) {
   constexpr int VEC = VecOf<T>::N;
+  const T scale = o.has_param ? o.param * o.sign : o.sign;
+  const bool use_scale = scale != (T)1;
 #pragma unroll
   for (int k = 0; k < K::RY; ++k) {
     const int cy = LEAN ? 0 : c.cly[k];
@@ -320,12 +343,12 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
       const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
       const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
       const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
-      T acc = (T)0;
-      if (actx) {
+      T acc;
+      {
         T s = cx[0] * vp[k][e];
         s = s + cx[1] * v0;
         s = s + cx[2] * vm[k][e];
-        acc = acc + s;
+        acc = s;
       }
       if (!K::FLAT) {
         T s = yap * yp;
@@ -339,9 +362,9 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
         s = s + zam * zm;
         acc = acc + s;
       }
-      if (o.has_param) acc = acc * o.param;
-      acc = acc * o.sign;
-      const T res = (T)0 + acc;
+      if (use_scale) acc = acc * scale;
+      T res = (T)0 + acc;
+      if (o.has_shift) res = res + o.shift * v0;  // + the diagonal operator, last (ops.py:151-152)
       emit(k, e, res);
     }
   }
@@ -488,7 +511,9 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start, derived by pointer arithmetic so the compiler keeps the shared
+  // address space (LDS instead of generic LD)
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
   unsigned char* stages = base;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_B);
   uint64_t* empty = full + C::S;
@@ -672,7 +697,9 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start, derived by pointer arithmetic so the compiler keeps the shared
+  // address space (LDS instead of generic LD)
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
   unsigned char* stages = base;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_A);
   uint64_t* empty = full + C::S;

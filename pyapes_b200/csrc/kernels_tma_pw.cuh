@@ -32,15 +32,97 @@ struct PwPlan {
   int has_aux;
 };
 
-// sum over operators of sign*param*(star), reference order (ops.py:130-149, fdc.py:103-108)
+// ---- exact shortcuts ------------------------------------------------------------------------
+// Every shortcut below returns the SAME bits as the reference's operation sequence:
+//  * the per-operator accumulator starts from the first axis' sum instead of 0 + sum: the two only
+//    differ in the sign of an all-zero sum, which the `0 + acc` of the operator sum erases;
+//  * (acc * param) * sign == acc * (param * sign) because sign is +-1 (rounding is symmetric), and a
+//    factor of exactly 1 is skipped;
+//  * x / d with d constant over a plane: q = x * RN(1/d) followed by two FMA residual corrections
+//    is the correctly rounded quotient (Markstein: a correctly rounded reciprocal + a faithful
+//    quotient estimate), as long as nothing under/overflows -- operands outside a safe exponent
+//    window (and 0, Inf, NaN) take the plain division.
+template <typename T>
+struct OpScale {
+  T scale;
+  bool use;
+};
+
+template <typename T>
+__device__ __forceinline__ OpScale<T> op_scale(const OpDev<T>& o) {
+  OpScale<T> r;
+  r.scale = o.has_param ? o.param * o.sign : o.sign;
+  r.use = r.scale != (T)1;
+  return r;
+}
+
+__device__ __forceinline__ bool exp_window(double v, int lo, int hi) {  // 2^lo <= |v| < 2^hi
+  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  return (e - (unsigned)(1023 + lo)) < (unsigned)(hi - lo);
+}
+__device__ __forceinline__ bool exp_window(float v, int lo, int hi) {
+  const unsigned e = ((unsigned)__float_as_int(v) >> 23) & 0xffu;
+  return (e - (unsigned)(127 + lo)) < (unsigned)(hi - lo);
+}
+template <typename T>
+struct DivWin;
+template <>
+struct DivWin<double> {
+  static constexpr int NUM = 600, DEN = 300;
+};
+template <>
+struct DivWin<float> {
+  static constexpr int NUM = 60, DEN = 30;
+};
+
+// a / d given rcp = RN(1/d); `den_ok` = d inside its exponent window (uniform per plane)
+template <typename T>
+__device__ __forceinline__ T div_rcp(T a, T d, T rcp, bool den_ok) {
+  if (den_ok && exp_window(a, -DivWin<T>::NUM, DivWin<T>::NUM)) {
+    T q = a * rcp;
+    T e = fma(-d, q, a);
+    q = fma(e, rcp, q);
+    e = fma(-d, q, a);
+    return fma(e, rcp, q);
+  }
+  return a / d;
+}
+
+// diagonal of the operator sum for one coefficient-class triple (Jacobi)
+template <typename T, typename K, int NOPS>
+__device__ __forceinline__ T star_diag(const EqDev<T>& eq, int clx, int cy, int cz) {
+  T diag = (T)0;
+  const int nops = NOPS > 0 ? NOPS : eq.nops;
+#pragma unroll
+  for (int q = 0; q < nops; ++q) {
+    const OpDev<T>& o = eq.op[q];
+    T dacc = (T)0;
+    dacc = dacc + o.coef[0][clx][1];
+    if (!K::FLAT) dacc = dacc + o.coef[1][cy][1];
+    dacc = dacc + o.coef[2][cz][1];
+    if (o.has_param) dacc = dacc * o.param;
+    dacc = dacc * o.sign;
+    diag = diag + dacc;
+  }
+  return diag;
+}
+
+// sum over operators of sign*param*(star), reference order (ops.py:130-149, fdc.py:103-108).
+// Kernel axis 0 is always active here (pw_eligible: 3-D meshes, and 2-D meshes as FLAT tiles).
 template <typename T, typename K, bool LEAN, int NOPS, typename F>
 __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<T, K>& c, int clx,
-                                              bool actx, const T (&vm)[K::RY][VecOf<T>::N],
+                                              const T (&vm)[K::RY][VecOf<T>::N],
                                               const T (&vc)[K::RY][VecOf<T>::N],
                                               const T (&vp)[K::RY][VecOf<T>::N], const T (&up)[VecOf<T>::N],
                                               const T (&dn)[VecOf<T>::N], const T (&zl)[K::RY],
                                               const T (&zr)[K::RY], F emit) {
   constexpr int VEC = VecOf<T>::N;
+  constexpr int MAXO = NOPS > 0 ? NOPS : kMaxOps;
+  const int nops = NOPS > 0 ? NOPS : eq.nops;  // compile-time count: unrolled, constant operands
+  OpScale<T> sc[MAXO];
+#pragma unroll
+  for (int q = 0; q < MAXO; ++q)
+    if (q < nops) sc[q] = op_scale<T>(eq.op[q]);
 #pragma unroll
   for (int k = 0; k < K::RY; ++k) {
     const int cy = LEAN ? 0 : c.cly[k];
@@ -52,43 +134,34 @@ __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<
       const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
       const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
       const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
-      T res = (T)0, diag = (T)0;
-      const int nops = NOPS > 0 ? NOPS : eq.nops;  // compile-time count: unrolled, constant operands
+      T res = (T)0;
 #pragma unroll
-      for (int q = 0; q < nops; ++q) {
+      for (int q = 0; q < MAXO; ++q) {
+        if (q >= nops) break;
         const OpDev<T>& o = eq.op[q];
-        T acc = (T)0, dacc = (T)0;
-        if (actx) {
+        T acc;
+        {
           T s = o.coef[0][clx][0] * vp[k][e];
           s = s + o.coef[0][clx][1] * v0;
           s = s + o.coef[0][clx][2] * vm[k][e];
-          acc = acc + s;
-          dacc = dacc + o.coef[0][clx][1];
+          acc = s;
         }
         if (!K::FLAT) {
           T s = o.coef[1][cy][0] * yp;
           s = s + o.coef[1][cy][1] * v0;
           s = s + o.coef[1][cy][2] * ym;
           acc = acc + s;
-          dacc = dacc + o.coef[1][cy][1];
         }
         {
           T s = o.coef[2][cz][0] * zp;
           s = s + o.coef[2][cz][1] * v0;
           s = s + o.coef[2][cz][2] * zm;
           acc = acc + s;
-          dacc = dacc + o.coef[2][cz][1];
         }
-        if (o.has_param) {
-          acc = acc * o.param;
-          dacc = dacc * o.param;
-        }
-        acc = acc * o.sign;
-        dacc = dacc * o.sign;
+        if (sc[q].use) acc = acc * sc[q].scale;
         res = res + acc;
-        diag = diag + dacc;
       }
-      emit(k, e, res, diag);
+      emit(k, e, res);
     }
   }
 }
@@ -140,7 +213,9 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
     const bool xown = x >= g.olo0 && x < g.ohi0;
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
-    T ax[K::RY][VEC], dg[K::RY][VEC];
+    T ax[K::RY][VEC];
+    T dgl = (T)1, rcl = (T)1;  // LEAN Jacobi: one diagonal (and its reciprocal) per plane
+    bool den_ok = false;
     if (xreg) {
       T up[VEC], dn[VEC], zl[K::RY], zr[K::RY];
       if (!K::FLAT) {
@@ -155,11 +230,14 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
         zl[k] = h[k * C::BOXZ - 1];
         zr[k] = h[k * C::BOXZ + VEC];
       }
-      const int clx = actx ? coef_class(g, 0, x) : 0;
-      star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T v, T d) {
-        ax[k][e] = v;
-        dg[k][e] = d;
-      });
+      const int clx = coef_class(g, 0, x);
+      star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, vm, vc, vp, up, dn, zl, zr,
+                                      [&](int k, int e, T v) { ax[k][e] = v; });
+      if (MODE == PW_JACOBI && LEAN) {
+        dgl = star_diag<T, K, NOPS>(eq, clx, 0, 0);
+        rcl = (T)1 / dgl;
+        den_ok = exp_window(dgl, -DivWin<T>::DEN, DivWin<T>::DEN);
+      }
     }
 #pragma unroll
     for (int k = 0; k < K::RY; ++k) {
@@ -185,7 +263,10 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           T xn = xc;
           if (in) {
             const T res = av[e] - ax[k][e];
-            xn = xc + res / dg[k][e];
+            if (LEAN)
+              xn = xc + div_rcp<T>(res, dgl, rcl, den_ok);
+            else
+              xn = xc + res / star_diag<T, K, NOPS>(eq, coef_class(g, 0, x), c.cly[k], c.clz[e]);
           }
           o[e] = xn;
           if (xown && !xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
@@ -263,7 +344,9 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   extern __shared__ unsigned char smem_dyn[];
   if (st != nullptr && st->done) return;
   if (MODE == PW_APPLY_T && st->finished_flag) return;
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start, derived by pointer arithmetic so the compiler keeps the shared
+  // address space (LDS instead of generic LD)
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
   unsigned char* stages = base;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE);
   uint64_t* empty = full + C::S;

@@ -61,6 +61,9 @@ class Operators:
             self._rhs = other()
         else:
             self._rhs = torch.zeros_like(self.var()) + other
+            # remember that this tensor is a constant fill (valid while nobody writes to it: any
+            # in-place write bumps `_version`); the explicit Euler path skips reading an all-zero RHS
+            self._rhs._pa_const = (float(other), self._rhs._version)  # type: ignore[attr-defined]
         assert self._rhs.shape == self.var().shape, (
             f"FDM Operators: RHS shape {self._rhs.shape} does not match {self.var().shape}!"
         )

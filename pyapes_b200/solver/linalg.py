@@ -148,6 +148,9 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
     dt = float(eqs[0]["param"][0])
     n_steps = int(config.get("n_steps", 1))
     rhs_ptr = None
+    tag = getattr(rhs, "_pa_const", None)
+    if tag is not None and tag[0] == 0.0 and tag[1] == rhs._version:
+        rhs = None  # `== 0.0`: a zero source is not read at all (pa_euler_steps: rhs may be NULL)
     if rhs is not None:
         rhs_c = rhs if rhs.is_contiguous() else rhs.contiguous()
         rhs_ptr = rhs_c.data_ptr()
