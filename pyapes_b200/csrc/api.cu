@@ -42,6 +42,12 @@ namespace pa {
                                                       SolverState*, double*, int);
 PA_EXTERN(double)
 PA_EXTERN(float)
+extern template bool launch_bi_st_tma<double>(cudaStream_t, const GridDev&, const EqDev<double>&, const TilePlan&,
+                                              const double*, const double*, const double*, double*, double*,
+                                              SolverState*, double*, int);
+extern template bool launch_bi_st_tma<float>(cudaStream_t, const GridDev&, const EqDev<float>&, const TilePlan&,
+                                             const float*, const float*, const float*, float*, float*, SolverState*,
+                                             double*, int);
 #undef PA_EXTERN
 
 static thread_local std::string g_err;
@@ -519,39 +525,57 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
     L.count += 2;
   };
   const int ST_V = dist ? ST_NONE : ST_BI_V, ST_S = dist ? ST_NONE : ST_BI_S, ST_T = dist ? ST_NONE : ST_BI_T;
-  if (stream_ok)
-    k_bi_p_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r + off, p + off, v + off, w.st);
-  else
-    k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
-  if (dist) {
-    dist_halo_exchange<T>(*dist, p, plane, g.olo0, g.ohi0, L.s);
-    ++L.count;
-  }
+  // (p = r + beta (p - omega v) of this iteration was produced by the previous iteration's fused
+  //  x/r/p update, or by bicgstab_first_p before the loop; 17 words per cell and iteration)
   if (pw)
     L.ok &= launch_star_tma<T, PW_APPLY_V>(L.s, g, eq, *pw, p, r0, v, nullptr, (T)0, w.st, w.partials, ST_V);
   else
     k_bi_apply<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, p, v, r0, w.st, w.partials, ST_V);
   reduce(1, ST_BI_V);
-  if (stream_ok)
-    k_bi_s_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r + off, v + off, s + off, w.st, w.partials, ST_S);
-  else
-    k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_S);
-  reduce(1, ST_BI_S);
-  if (dist) {
-    dist_halo_exchange<T>(*dist, s, plane, g.olo0, g.ohi0, L.s);
+  // second half step.  TMA engine + streaming x update: s = r - alpha v is never stored -- the fused
+  // kernel forms it on the fly (with halos) for t = A(s) and the x update recomputes it
+  // (R r,v,r0 W t | R x,p,r,t,v W x,r,p: with v = A(p) 15 words per iteration).
+  const bool fuse_st = pw != nullptr && stream_ok;
+  if (fuse_st) {
+    if (dist) {  // the stencil of s needs the neighbours' boundary planes of r and v
+      dist_halo_exchange<T>(*dist, v, plane, g.olo0, g.ohi0, L.s);
+      ++L.count;
+    }
+    L.ok &= launch_bi_st_tma<T>(L.s, g, eq, *pw, r, v, r0, t, nullptr, w.st, w.partials, dist ? ST_NONE : ST_BI_ST);
+    reduce(4, ST_BI_ST);
+    k_bi_x_stream<T, true><<<nb, kBlock, 0, L.s>>>(nvec, cur + off, nxt + off, p + off, s + off, t + off, v + off,
+                                                   r + off, w.st, w.partials);
+    L.count += 3;
+    if (dist) {
+      dist_halo_exchange<T>(*dist, r, plane, g.olo0, g.ohi0, L.s);
+      ++L.count;
+    }
+  } else {
+    if (stream_ok)
+      k_bi_s_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, r + off, v + off, s + off, w.st, w.partials, ST_S);
+    else
+      k_bi_s<T><<<nb, kBlock, 0, L.s>>>(g, r, v, s, w.st, w.partials, ST_S);
+    reduce(1, ST_BI_S);
+    if (dist) {
+      dist_halo_exchange<T>(*dist, s, plane, g.olo0, g.ohi0, L.s);
+      ++L.count;
+    }
+    if (pw)
+      L.ok &= launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_T);
+    else
+      k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_T);
+    reduce(3, ST_BI_T);
+    if (stream_ok)
+      k_bi_x_stream<T, false><<<nb, kBlock, 0, L.s>>>(nvec, cur + off, nxt + off, p + off, s + off, t + off, v + off,
+                                                      r + off, w.st, w.partials);
+    else
+      k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, v, r, w.st, w.partials);
+    L.count += 4;
+  }
+  if (dist) {  // ghost planes of the new p for the next iteration's v = A(p)
+    dist_halo_exchange<T>(*dist, p, plane, g.olo0, g.ohi0, L.s);
     ++L.count;
   }
-  if (pw)
-    L.ok &= launch_star_tma<T, PW_APPLY_T>(L.s, g, eq, *pw, s, r0, t, nullptr, (T)0, w.st, w.partials, ST_T);
-  else
-    k_bi_apply<T, 1><<<nb, kBlock, 0, L.s>>>(g, eq, s, t, r0, w.st, w.partials, ST_T);
-  reduce(3, ST_BI_T);
-  if (stream_ok)
-    k_bi_x_stream<T><<<nb, kBlock, 0, L.s>>>(nvec, cur + off, nxt + off, p + off, s + off, t + off, r + off, w.st,
-                                             w.partials);
-  else
-    k_bi_x<T><<<nb, kBlock, 0, L.s>>>(g, cur, nxt, p, s, t, r, w.st, w.partials);
-  L.count += 5;
   launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
   if (dist) {
     dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
@@ -559,6 +583,28 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   }
   k_finalize<T><<<1, 1, 0, L.s>>>(ST_BI_FIN, w.st);
   ++L.count;
+}
+
+// p of the first iteration: p = r + beta (p - omega v) with p = v = 0 (linalg.py:217)
+template <typename T>
+static void bicgstab_first_p(Launcher& L, const GridDev& g, const Workspace& w, const Dist* dist) {
+  T* r = (T*)w.vec[1];
+  T* p = (T*)w.vec[2];
+  T* v = (T*)w.vec[3];
+  constexpr int SV = StreamVec<T>::N;
+  const long long plane = (long long)g.n[1] * g.n[2];
+  const long long off = (long long)g.olo0 * plane;
+  const long long nown = (long long)(g.ohi0 - g.olo0) * plane;
+  const int nb = grid_blocks(g.cells);
+  if ((nown % SV == 0) && (off % SV == 0))
+    k_bi_p_stream<T><<<nb, kBlock, 0, L.s>>>(nown / SV, r + off, p + off, v + off, w.st);
+  else
+    k_bi_p<T><<<nb, kBlock, 0, L.s>>>(g, r, p, v, w.st);
+  ++L.count;
+  if (dist) {
+    dist_halo_exchange<T>(*dist, p, plane, g.olo0, g.ohi0, L.s);
+    ++L.count;
+  }
 }
 
 // Multi-GPU: the sweep reads x with its ghost planes (valid on entry), then the new iterate's
@@ -706,8 +752,10 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     if (dist) {
       dist_allreduce(*dist, &w.st->sum[R_A], 1, stream);
       k_finalize<T><<<1, 1, 0, stream>>>(ST_BI_INIT, w.st);
-      L.count += 2;
+      dist_halo_exchange<T>(*dist, r, plane, g.olo0, g.ohi0, stream);  // the fused s/t kernel reads r with halos
+      L.count += 3;
     }
+    bicgstab_first_p<T>(L, g, w, dist);
   } else if (dist) {  // Jacobi: the first sweep reads x with its ghost planes
     dist_halo_exchange<T>(*dist, x, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, stream);
     ++L.count;

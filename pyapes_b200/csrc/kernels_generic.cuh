@@ -18,6 +18,7 @@ enum Stage {
   ST_BI_V,
   ST_BI_S,
   ST_BI_T,
+  ST_BI_ST,    // fused s/t half step: sums |s|^2, t.s, t.t, r0.t
   ST_BI_X,     // leaves raw sums for ST_BI_FIN
   ST_BI_FIN,
   ST_JA_UPD,
@@ -98,12 +99,35 @@ __device__ void finalize_stage(int stage, SolverState* st) {
       }
       st->finished_flag = ((double)tol <= st->tolerance) ? 1 : 0;
     } break;
+    case ST_BI_ST: {  // ST_BI_S then ST_BI_T on the sums of the fused kernel (k_bi_st_tma)
+      T tol = (T)sqrt(sum[R_A]);
+      st->tol = (double)tol;
+      if (isnan(tol) || isinf(tol)) {
+        st->done = 1;
+        st->status = PA_BAD_TOL;
+        break;
+      }
+      st->finished_flag = ((double)tol <= st->tolerance) ? 1 : 0;
+      if (st->finished_flag) break;
+      T w = (T)sum[R_B] / (T)sum[R_C];
+      w = nan_to_num0<T>(w);
+      sc[S_OMEGA] = (double)w;
+      sc[S_RHO_NEXT] = (double)((-w) * (T)sum[R_SHELL]);
+      T beta = (T)sc[S_RHO_NEXT] / (T)sc[S_RHO] * (T)sc[S_ALPHA] / (T)sc[S_OMEGA];
+      sc[S_BETA] = (double)beta;
+      sc[S_RHO] = sc[S_RHO_NEXT];
+    } break;
     case ST_BI_T: {  // omega, rho_next                                     linalg.py:246-250
       if (st->finished_flag) break;  // early exit taken after the first half step (linalg.py:235-240)
       T w = (T)sum[R_A] / (T)sum[R_B];
       w = nan_to_num0<T>(w);
       sc[S_OMEGA] = (double)w;
       sc[S_RHO_NEXT] = (double)((-w) * (T)sum[R_C]);
+      // head of the next iteration (linalg.py:212-214): every input is known here already, and the
+      // fused x/r/p update of this iteration needs beta for p = r_new + beta (p - omega v)
+      T beta = (T)sc[S_RHO_NEXT] / (T)sc[S_RHO] * (T)sc[S_ALPHA] / (T)sc[S_OMEGA];
+      sc[S_BETA] = (double)beta;
+      sc[S_RHO] = sc[S_RHO_NEXT];
     } break;
     case ST_BI_FIN: {
       if (st->finished_flag) {  // early exit path: `finished = True; continue`
@@ -126,10 +150,6 @@ __device__ void finalize_stage(int stage, SolverState* st) {
         st->done = 1;
         st->status = PA_CONVERGED;
       }
-      // head of the next iteration                                     linalg.py:212-214
-      T beta = (T)sc[S_RHO_NEXT] / (T)sc[S_RHO] * (T)sc[S_ALPHA] / (T)sc[S_OMEGA];
-      sc[S_BETA] = (double)beta;
-      sc[S_RHO] = sc[S_RHO_NEXT];
     } break;
     case ST_JA_FIN: {
       T tol = (T)sqrt(sum[R_B] + sum[R_SHELL]);
@@ -543,14 +563,15 @@ __global__ void __launch_bounds__(kBlock) k_bi_s(GridDev g, const T* __restrict_
 }
 
 // x_new = x + alpha p (+ s omega) ; r = s - omega t ; ||r||^2   (linalg.py:236, 253-262)
+// and, fused, the head of the NEXT iteration: p = r_new + beta (p - omega v)   (linalg.py:217)
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_bi_x(GridDev g, const T* __restrict__ x,
-                                                 T* __restrict__ x_new, const T* __restrict__ p,
+                                                 T* __restrict__ x_new, T* __restrict__ p,
                                                  const T* __restrict__ s, const T* __restrict__ t,
-                                                 T* __restrict__ r, SolverState* st,
+                                                 const T* __restrict__ v, T* __restrict__ r, SolverState* st,
                                                  double* partials) {
   if (st->done) return;
-  const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA];
+  const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA], beta = (T)st->scal[S_BETA];
   const bool early = st->finished_flag != 0;
   double acc[1] = {0.0};
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.cells;
@@ -558,12 +579,15 @@ __global__ void __launch_bounds__(kBlock) k_bi_x(GridDev g, const T* __restrict_
     Cell c = decode(g, idx);
     T xn = x[idx];
     if (in_region(g, c)) {
-      xn = xn + alpha * p[idx];
+      const T pv = p[idx];
+      xn = xn + alpha * pv;
       if (!early) {
         T sv = s[idx];
         xn = xn + sv * omega;
         T rn = sv - omega * t[idx];
         r[idx] = rn;
+        T tt = pv - omega * v[idx];
+        p[idx] = rn + beta * tt;
         if (owned(g, c)) {
           T q = rn * rn;
           acc[0] += (double)q;
@@ -631,15 +655,17 @@ __global__ void __launch_bounds__(kBlock) k_bi_s_stream(long long nvec, const T*
   grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, stage});
 }
 
-template <typename T>
+// RS: s is not stored -- it is recomputed as r - alpha v from the (old) r, with the same operation
+// as the s-stage, so the bits are the same (the fused k_bi_st_tma path, 15 words per iteration)
+template <typename T, bool RS>
 __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T* __restrict__ x,
-                                                        T* __restrict__ x_new, const T* __restrict__ p,
+                                                        T* __restrict__ x_new, T* __restrict__ p,
                                                         const T* __restrict__ s, const T* __restrict__ t,
-                                                        T* __restrict__ r, SolverState* st,
-                                                        double* partials) {
+                                                        const T* __restrict__ v, T* __restrict__ r,
+                                                        SolverState* st, double* partials) {
   typedef typename StreamVec<T>::type V;
   if (st->done) return;
-  const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA];
+  const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA], beta = (T)st->scal[S_BETA];
   const bool early = st->finished_flag != 0;
   double acc[1] = {0.0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -649,17 +675,25 @@ __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T*
 #pragma unroll
       for (int e = 0; e < StreamVec<T>::N; ++e) xo.v[e] = xv.v[e] + alpha * pv.v[e];
     } else {
-      V sv = reinterpret_cast<const V*>(s)[i], tv = reinterpret_cast<const V*>(t)[i], ro;
+      V sv = reinterpret_cast<const V*>(RS ? r : s)[i], tv = reinterpret_cast<const V*>(t)[i],
+        vv = reinterpret_cast<const V*>(v)[i], ro, po;
+      if (RS) {
+#pragma unroll
+        for (int e = 0; e < StreamVec<T>::N; ++e) sv.v[e] = sv.v[e] - alpha * vv.v[e];  // linalg.py:230
+      }
 #pragma unroll
       for (int e = 0; e < StreamVec<T>::N; ++e) {
         T xn = xv.v[e] + alpha * pv.v[e];
         xo.v[e] = xn + sv.v[e] * omega;
         T rn = sv.v[e] - omega * tv.v[e];
         ro.v[e] = rn;
+        T tt = pv.v[e] - omega * vv.v[e];
+        po.v[e] = rn + beta * tt;  // next iteration's p (linalg.py:217), beta from ST_BI_T
         T q = rn * rn;
         acc[0] += (double)q;
       }
       reinterpret_cast<V*>(r)[i] = ro;
+      reinterpret_cast<V*>(p)[i] = po;
     }
     reinterpret_cast<V*>(x_new)[i] = xo;
   }

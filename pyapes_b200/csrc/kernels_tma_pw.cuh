@@ -398,6 +398,210 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   grid_reduce<3>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 3>{st, R_A, stage});
 }
 
+// =========================================================================================
+// BiCGSTAB second half step, fused:  s = r - alpha v  (never stored unless `s_out`),  t = A(s),
+// sums |s|^2, t.s, t.t, r0.t  -- two halo inputs (r, v) combined on the fly like CG phase A, r0 as
+// the own-tile input.  Traffic: R r, R v, R r0, W t = 4 words per cell (s-stage + T-apply: 6).
+// =========================================================================================
+template <typename T, typename K>
+struct Pw2Cfg : TmaCfg<T, K> {
+  typedef TmaCfg<T, K> B;
+  static constexpr int STAGE = 2 * B::HALO_SLOT + B::OWN_SLOT;  // r halo, v halo, r0 own
+  static constexpr size_t SMEM = (size_t)B::S * STAGE + B::BAR_BYTES + 128;
+};
+
+template <typename T, typename K, bool LEAN, int NOPS>
+__device__ __forceinline__ void pw2_consumer(const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
+                                             T* __restrict__ t_out, T* __restrict__ s_out, T alpha,
+                                             unsigned char* stages, uint64_t* full, uint64_t* empty, int y0,
+                                             int z0, int x0, int x1, double (&acc_out)[4]) {
+  typedef Pw2Cfg<T, K> C;
+  constexpr int VEC = C::VEC;
+  ConsCtx<T, K> c;
+  cons_setup<T, K>(g, c, y0, z0);
+  const long long n12 = (long long)g.n[1] * g.n[2];
+  T* tp_ = t_out + (long long)x0 * n12 + c.goff;
+  T* sp_ = s_out ? s_out + (long long)x0 * n12 + c.goff : nullptr;
+
+  auto rt = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE) + c.hoff; };
+  auto vt = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE + C::HALO_SLOT) + c.hoff; };
+  auto aux = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE + 2 * C::HALO_SLOT); };
+  // s = r - alpha v on the thread's own cells of the plane in stage s   (linalg.py:230)
+  auto own_s = [&](int s, T (&o)[K::RY][VEC]) {
+    const T* rp = rt(s);
+    const T* vp = vt(s);
+#pragma unroll
+    for (int k = 0; k < K::RY; ++k) {
+      T a[VEC], b[VEC];
+      lds_vec<T>(rp + k * C::BOXZ, a);
+      lds_vec<T>(vp + k * C::BOXZ, b);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[k][e] = a[e] - alpha * b[e];
+    }
+  };
+  auto release = [&](int s) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&empty[s]);
+  };
+
+  T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  mbar_wait(&full[0], 0);
+  own_s(0, A);
+  release(0);
+  mbar_wait(&full[1 % C::S], 0);
+  own_s(1 % C::S, B);
+
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
+    const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
+    mbar_wait(&full[sn], (i / C::S) & 1);
+    own_s(sn, vp);
+    const bool xreg = x >= g.lo[0] && x < g.hi[0];
+    const bool xown = x >= g.olo0 && x < g.ohi0;
+    T ax[K::RY][VEC];
+    if (xreg) {
+      const T* rp = rt(sc);
+      const T* vq = vt(sc);
+      T up[VEC], dn[VEC], zl[K::RY], zr[K::RY];
+      if (!K::FLAT) {
+        T a[VEC], b[VEC];
+        lds_vec<T>(rp - C::BOXZ, a);
+        lds_vec<T>(vq - C::BOXZ, b);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) up[e] = a[e] - alpha * b[e];
+        lds_vec<T>(rp + K::RY * C::BOXZ, a);
+        lds_vec<T>(vq + K::RY * C::BOXZ, b);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) dn[e] = a[e] - alpha * b[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) up[e] = dn[e] = (T)0;
+      }
+#pragma unroll
+      for (int k = 0; k < K::RY; ++k) {
+        zl[k] = rp[k * C::BOXZ - 1] - alpha * vq[k * C::BOXZ - 1];
+        zr[k] = rp[k * C::BOXZ + VEC] - alpha * vq[k * C::BOXZ + VEC];
+      }
+      star_cells_eq<T, K, LEAN, NOPS>(eq, c, coef_class(g, 0, x), vm, vc, vp, up, dn, zl, zr,
+                                      [&](int k, int e, T v) { ax[k][e] = v; });
+    }
+#pragma unroll
+    for (int k = 0; k < K::RY; ++k) {
+      T r0v[VEC], o[VEC];
+      lds_vec<T>(aux(sc) + c.ooff + k * C::OBOXZ, r0v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const bool in = xreg && (LEAN || ((c.inreg >> (k * VEC + e)) & 1u));
+        const T sv = vc[k][e];
+        const T a = in ? ax[k][e] : (T)0;
+        o[e] = a;
+        if (xown && (LEAN || ((c.valid >> (k * VEC + e)) & 1u))) {  // s == 0 outside the region
+          const T q = sv * sv;
+          a0 += (double)q;
+        }
+        if (in && xown) {
+          const T q1 = a * sv, q2 = a * a, q3 = r0v[e] * a;
+          a1 += (double)q1;
+          a2 += (double)q2;
+          a3 += (double)q3;
+        }
+      }
+      stg_row<T, K, LEAN>(tp_ + (long long)k * g.n[2], c, k, o);
+      if (sp_) stg_row<T, K, LEAN>(sp_ + (long long)k * g.n[2], c, k, vc[k]);
+    }
+    tp_ += n12;
+    if (sp_) sp_ += n12;
+    release(sc);
+  };
+
+  int x = x0, i = 2;
+  if (LEAN) {
+    while (true) {
+      step(A, B, Cc, x, i);
+      if (++x >= x1) break;
+      ++i;
+      step(B, Cc, A, x, i);
+      if (++x >= x1) break;
+      ++i;
+      step(Cc, A, B, x, i);
+      if (++x >= x1) break;
+      ++i;
+    }
+  } else {
+    for (; x < x1; ++x, ++i) {
+      step(A, B, Cc, x, i);
+#pragma unroll
+      for (int k = 0; k < K::RY; ++k)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          A[k][e] = B[k][e];
+          B[k][e] = Cc[k][e];
+        }
+    }
+  }
+  acc_out[0] = a0;
+  acc_out[1] = a1;
+  acc_out[2] = a2;
+  acc_out[3] = a3;
+}
+
+template <typename T, typename K, int NOPS>
+__global__ void __launch_bounds__(Pw2Cfg<T, K>::THREADS, 2)
+k_bi_st_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
+            const __grid_constant__ CUtensorMap tm_r0, TilePlan p, GridDev g, EqDev<T> eq, T* __restrict__ t_out,
+            T* __restrict__ s_out, SolverState* st, double* partials, int stage) {
+  typedef Pw2Cfg<T, K> C;
+  extern __shared__ unsigned char smem_dyn[];
+  if (st->done) return;
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  unsigned char* stages = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE);
+  uint64_t* empty = full + C::S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
+  const int x0 = blockIdx.z * p.cx, x1 = min(x0 + p.cx, g.n[0]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], C::CWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (warp == C::CWARPS) {
+    if (lane == 0) {
+      const int n = x1 - x0 + 2;
+      for (int i = 0; i < n; ++i) {
+        const int pl = x0 - 1 + i;
+        const int s = i & (C::S - 1);
+        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
+        const bool inner = (pl >= x0 && pl < x1);
+        mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES + (inner ? C::OWN_BYTES : 0)));
+        unsigned char* sb = stages + (size_t)s * C::STAGE;
+        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+        for (int b = 0; b < C::NB; ++b) {
+          const int zb = z0 + b * C::OBOXZ;
+          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, &tm_v, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          if (inner) tma_load_3d(sb + 2 * C::HALO_SLOT + b * C::OBOX_SLOT, &tm_r0, zb, y0, xw, &full[s]);
+        }
+      }
+    }
+  } else {
+    const T alpha = (T)st->scal[S_ALPHA];
+    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
+    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    if (full_tile && !edge)
+      pw2_consumer<T, K, true, NOPS>(p, g, eq, t_out, s_out, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+    else
+      pw2_consumer<T, K, false, NOPS>(p, g, eq, t_out, s_out, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+  }
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  grid_reduce<4>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 4>{st, R_A, stage});
+}
+
 // ---- host ------------------------------------------------------------------------------------
 template <typename T>
 inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces) {
@@ -460,6 +664,47 @@ static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& 
   else
     launch_star_tma_n<T, K, MODE, 0>(s, tm_in, tm_aux, g, eq, tile, aux != nullptr, out, out2, dt, st, partials, stage);
   return true;
+}
+
+template <typename T, typename K, int NOPS>
+static void launch_bi_st_n(cudaStream_t s, const CUtensorMap& tm_r, const CUtensorMap& tm_v, const CUtensorMap& tm_r0,
+                           const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, T* t_out, T* s_out,
+                           SolverState* st, double* partials, int stage) {
+  typedef Pw2Cfg<T, K> C;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_bi_st_tma<T, K, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    attr = true;
+  }
+  dim3 grid(tile.tiles_z, tile.tiles_y, tile.chunks);
+  k_bi_st_tma<T, K, NOPS><<<grid, C::THREADS, C::SMEM, s>>>(tm_r, tm_v, tm_r0, tile, g, eq, t_out, s_out, st, partials,
+                                                           stage);
+}
+
+template <typename T, typename K>
+static bool launch_bi_st_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, const T* r,
+                           const T* v, const T* r0, T* t_out, T* s_out, SolverState* st, double* partials,
+                           int stage) {
+  typedef Pw2Cfg<T, K> C;
+  CUtensorMap tm_r, tm_v, tm_r0;
+  if (!make_map<T>(&tm_r, r, g, C::BOXZ, C::BOXY) || !make_map<T>(&tm_v, v, g, C::BOXZ, C::BOXY) ||
+      !make_map<T>(&tm_r0, r0, g, C::OBOXZ, C::TY))
+    return false;
+  if (eq.nops == 1)
+    launch_bi_st_n<T, K, 1>(s, tm_r, tm_v, tm_r0, g, eq, tile, t_out, s_out, st, partials, stage);
+  else if (eq.nops == 2)
+    launch_bi_st_n<T, K, 2>(s, tm_r, tm_v, tm_r0, g, eq, tile, t_out, s_out, st, partials, stage);
+  else
+    launch_bi_st_n<T, K, 0>(s, tm_r, tm_v, tm_r0, g, eq, tile, t_out, s_out, st, partials, stage);
+  return true;
+}
+
+// BiCGSTAB s/t half step (k_bi_st_tma); s_out may be null (s is then recomputed by the x update)
+template <typename T>
+bool launch_bi_st_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, const T* r,
+                      const T* v, const T* r0, T* t_out, T* s_out, SolverState* st, double* partials, int stage) {
+  return tma_flat(g) ? launch_bi_st_k<T, KFlat>(s, g, eq, tile, r, v, r0, t_out, s_out, st, partials, stage)
+                     : launch_bi_st_k<T, KStd>(s, g, eq, tile, r, v, r0, t_out, s_out, st, partials, stage);
 }
 
 template <typename T, int MODE>

@@ -10,4 +10,6 @@ PA_INST(PW_EULER)
 PA_INST(PW_APPLY_V)
 PA_INST(PW_APPLY_T)
 #undef PA_INST
+template bool launch_bi_st_tma<float>(cudaStream_t, const GridDev&, const EqDev<float>&, const TilePlan&, const float*,
+                                   const float*, const float*, float*, float*, SolverState*, double*, int);
 }  // namespace pa

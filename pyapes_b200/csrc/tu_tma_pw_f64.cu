@@ -10,4 +10,6 @@ PA_INST(PW_EULER)
 PA_INST(PW_APPLY_V)
 PA_INST(PW_APPLY_T)
 #undef PA_INST
+template bool launch_bi_st_tma<double>(cudaStream_t, const GridDev&, const EqDev<double>&, const TilePlan&, const double*,
+                                   const double*, const double*, double*, double*, SolverState*, double*, int);
 }  // namespace pa
