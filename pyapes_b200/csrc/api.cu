@@ -687,6 +687,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
   if (dist) {
     if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+    nccl_first_error() = ncclSuccess;
     plan.dist = tmap.tile.dist = 1;
     plan.fuse_fin = tmap.tile.fuse_fin = 0;
   }
@@ -853,6 +854,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
+  if (dist && nccl_first_error() != ncclSuccess)
+    return fail(PA_ERR_NCCL, std::string("NCCL: ") + nccl_api().GetErrorString(nccl_first_error()));
   if (rc != PA_OK) return rc;
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(PA_ERR_CUDA, cudaGetErrorString(le));
@@ -1165,6 +1168,7 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   };
   if (dist) {
     if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+    nccl_first_error() = ncclSuccess;
     if (dist->ring) bc_scratch((size_t)2 * g.n[1] * g.n[2] * sizeof(T));  // before any capture
     if (nsteps > 0) dist_halo_exchange<T>(*dist, a, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, s);
   }
@@ -1200,6 +1204,9 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   }
   PA_CUDA(cudaStreamSynchronize(s));
   PA_CUDA(cudaGetLastError());
+  if (dist && nccl_first_error() != ncclSuccess)
+    return fail(PA_ERR_NCCL, std::string("NCCL: ") + nccl_api().GetErrorString(nccl_first_error()));
+  if (!L.ok) return fail(PA_ERR_CUDA, "device scratch allocation failed (slab-periodic boundary condition)");
   *result_in_b = (cur == b) ? 1 : 0;
   return PA_OK;
 }

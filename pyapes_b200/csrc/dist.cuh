@@ -70,9 +70,20 @@ struct Dist {
   int ring = 0;  // axis 0 is periodic: rank 0 and rank P-1 are neighbours (wrap-around ghost planes)
 };
 
+// First NCCL failure of the current solve (the collectives are enqueued from deep inside the
+// iteration builders; the drivers check this once per solve and report PA_ERR_NCCL).
+static inline ncclResult_t& nccl_first_error() {
+  static thread_local ncclResult_t rc = ncclSuccess;
+  return rc;
+}
+static inline ncclResult_t nccl_note(ncclResult_t rc) {
+  if (rc != ncclSuccess && nccl_first_error() == ncclSuccess) nccl_first_error() = rc;
+  return rc;
+}
+
 // sum-all-reduce `count` doubles in place (device memory)
 static inline ncclResult_t dist_allreduce(const Dist& d, double* buf, int count, cudaStream_t s) {
-  return nccl_api().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, d.comm, s);
+  return nccl_note(nccl_api().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, d.comm, s));
 }
 
 // exchange the boundary planes of a slab-decomposed vector: first/last OWNED plane -> the
@@ -88,23 +99,23 @@ static inline ncclResult_t dist_halo_exchange(const Dist& d, T* v, long long pla
   const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
   const int lower = d.rank > 0 ? d.rank - 1 : (d.ring ? d.nranks - 1 : -1);
   const int upper = d.rank < d.nranks - 1 ? d.rank + 1 : (d.ring ? 0 : -1);
-  ncclResult_t rc = a.GroupStart();
+  ncclResult_t rc = nccl_note(a.GroupStart());
   if (rc != ncclSuccess) return rc;
-  if (lower >= 0) a.Send(v + (long long)olo0 * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s);
-  if (upper >= 0) a.Recv(v + (long long)ohi0 * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s);
-  if (upper >= 0) a.Send(v + (long long)(ohi0 - 1) * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s);
-  if (lower >= 0) a.Recv(v + (long long)(olo0 - 1) * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s);
-  return a.GroupEnd();
+  if (lower >= 0) nccl_note(a.Send(v + (long long)olo0 * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s));
+  if (upper >= 0) nccl_note(a.Recv(v + (long long)ohi0 * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s));
+  if (upper >= 0) nccl_note(a.Send(v + (long long)(ohi0 - 1) * plane_elems, (size_t)plane_elems, dt, upper, d.comm, s));
+  if (lower >= 0) nccl_note(a.Recv(v + (long long)(olo0 - 1) * plane_elems, (size_t)plane_elems, dt, lower, d.comm, s));
+  return nccl_note(a.GroupEnd());
 }
 
 // point-to-point helpers of the slab-periodic boundary condition (api.cu launch_bcs)
 template <typename T>
 static inline ncclResult_t dist_send(const Dist& d, const T* p, long long n, int peer, cudaStream_t s) {
-  return nccl_api().Send(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s);
+  return nccl_note(nccl_api().Send(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s));
 }
 template <typename T>
 static inline ncclResult_t dist_recv(const Dist& d, T* p, long long n, int peer, cudaStream_t s) {
-  return nccl_api().Recv(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s);
+  return nccl_note(nccl_api().Recv(p, (size_t)n, sizeof(T) == 8 ? ncclFloat64 : ncclFloat32, peer, d.comm, s));
 }
 
 }  // namespace pa
