@@ -643,13 +643,15 @@ __global__ void __launch_bounds__(kBlock) k_bi_s_stream(long long nvec, const T*
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     V a = reinterpret_cast<const V*>(r)[i], c = reinterpret_cast<const V*>(v)[i], o;
+    T part = (T)0;  // one 16-byte vector: summed in T, added once (fp64: 2 values; fp32: 4, one conversion)
 #pragma unroll
     for (int e = 0; e < StreamVec<T>::N; ++e) {
       T sv = a.v[e] - alpha * c.v[e];
       o.v[e] = sv;
       T q = sv * sv;
-      acc[0] += (double)q;
+      part += q;
     }
+    acc[0] += (double)part;
     reinterpret_cast<V*>(s)[i] = o;
   }
   grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, stage});
@@ -681,6 +683,7 @@ __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T*
 #pragma unroll
         for (int e = 0; e < StreamVec<T>::N; ++e) sv.v[e] = sv.v[e] - alpha * vv.v[e];  // linalg.py:230
       }
+      T part = (T)0;
 #pragma unroll
       for (int e = 0; e < StreamVec<T>::N; ++e) {
         T xn = xv.v[e] + alpha * pv.v[e];
@@ -690,8 +693,9 @@ __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T*
         T tt = pv.v[e] - omega * vv.v[e];
         po.v[e] = rn + beta * tt;  // next iteration's p (linalg.py:217), beta from ST_BI_T
         T q = rn * rn;
-        acc[0] += (double)q;
+        part += q;
       }
+      acc[0] += (double)part;
       reinterpret_cast<V*>(r)[i] = ro;
       reinterpret_cast<V*>(p)[i] = po;
     }

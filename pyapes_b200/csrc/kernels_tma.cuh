@@ -292,6 +292,28 @@ __device__ __forceinline__ void cons_setup(const GridDev& g, ConsCtx<T, K>& c, i
   for (int e = 0; e < C::VEC; ++e) c.clz[e] = (zg + e < g.n[2]) ? coef_class(g, 2, zg + e) : 0;
 }
 
+// Per-step partial sums.  fp64: added straight into the double accumulator (unchanged order).
+// fp32: the products of one plane-step (<= 8 cells) are first summed in float and converted once --
+// the F2F conversions (quarter rate) were 2 per cell in phase B; torch's own fp32 sums accumulate in
+// float as well, and reductions are not part of the bit-exact contract.
+template <typename T>
+struct StepSum;
+template <>
+struct StepSum<double> {
+  double& acc;
+  __device__ __forceinline__ explicit StepSum(double& a) : acc(a) {}
+  __device__ __forceinline__ void add(double q) { acc += q; }
+  __device__ __forceinline__ void flush() {}
+};
+template <>
+struct StepSum<float> {
+  double& acc;
+  float part = 0.f;
+  __device__ __forceinline__ explicit StepSum(double& a) : acc(a) {}
+  __device__ __forceinline__ void add(float q) { part += q; }
+  __device__ __forceinline__ void flush() { acc += (double)part; }
+};
+
 template <typename T>
 __device__ __forceinline__ void lds_vec(const T* p, T (&v)[VecOf<T>::N]) {
   typedef typename VecOf<T>::type V;
@@ -429,6 +451,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
     const bool xown = x >= g.olo0 && x < g.ohi0;
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
+    StepSum<T> s0(a0), s1(a1);
     if (xreg) {
       T ad[K::RY][VEC];
       {
@@ -465,12 +488,12 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
           if (xown) {
             if (in) {
               const T q = t * t;
-              a0 += (double)q;
+              s0.add(q);
             }
             if (!xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
               const T df = xn[e] - xv[e];
               const T q2 = df * df;
-              a1 += (double)q2;
+              s1.add(q2);
             }
           }
         }
@@ -485,6 +508,8 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
         stg_row<T, K, LEAN>(xo + (long long)k * g.n[2], c, k, xv);
       }
     }
+    s0.flush();
+    s1.flush();
     xo += n12;
     ro += n12;
     release(sc);
@@ -640,6 +665,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       if (x + 1 < x1) write_d(vp);
     }
     const bool xin = x >= g.lo[0] && x < g.hi[0] && x >= g.olo0 && x < g.ohi0;
+    StepSum<T> sd(acc);
     if (xin) {
       // halo neighbours of the centre plane: recomputed from the staged raw r, d
       const T* rp = rt(sc);
@@ -670,10 +696,11 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       star_cells<T, K, LEAN>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, [&](int k, int e, T ad) {
         if (LEAN || ((c.valid >> (k * VEC + e)) & 1u)) {
           const T q = vc[k][e] * ad;
-          acc += (double)q;
+          sd.add(q);
         }
       });
     }
+    sd.flush();
     release(sc);
   };
 

@@ -214,6 +214,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
     T ax[K::RY][VEC];
+    StepSum<T> s0(a0), s1(a1), s2(a2);
     T dgl = (T)1, rcl = (T)1;  // LEAN Jacobi: one diagonal (and its reciprocal) per plane
     bool den_ok = false;
     if (xreg) {
@@ -257,7 +258,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           o[e] = res;
           if (in && xown) {
             const T q = res * res;
-            a0 += (double)q;
+            s0.add(q);
           }
         } else if (MODE == PW_JACOBI) {
           T xn = xc;
@@ -272,7 +273,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           if (xown && !xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
             const T df = xn - xc;
             const T q = df * df;
-            a1 += (double)q;
+            s1.add(q);
           }
         } else if (MODE == PW_EULER) {
           T xn = xc;
@@ -287,12 +288,12 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           if (in && xown) {
             if (MODE == PW_APPLY_V) {
               const T q = av[e] * a;
-              a0 += (double)q;
+              s0.add(q);
             } else {
               const T q0 = a * xc, q1 = a * a, q2 = av[e] * a;
-              a0 += (double)q0;
-              a1 += (double)q1;
-              a2 += (double)q2;
+              s0.add(q0);
+              s1.add(q1);
+              s2.add(q2);
             }
           }
         }
@@ -300,6 +301,9 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
       stg_row<T, K, LEAN>(op_ + (long long)k * g.n[2], c, k, o);
       if (MODE == PW_RESID && op2_) stg_row<T, K, LEAN>(op2_ + (long long)k * g.n[2], c, k, o);
     }
+    s0.flush();
+    s1.flush();
+    s2.flush();
     op_ += n12;
     if (op2_) op2_ += n12;
     release(sc);
@@ -459,6 +463,7 @@ __device__ __forceinline__ void pw2_consumer(const TilePlan& p, const GridDev& g
     const bool xreg = x >= g.lo[0] && x < g.hi[0];
     const bool xown = x >= g.olo0 && x < g.ohi0;
     T ax[K::RY][VEC];
+    StepSum<T> s0(a0), s1(a1), s2(a2), s3(a3);
     if (xreg) {
       const T* rp = rt(sc);
       const T* vq = vt(sc);
@@ -497,18 +502,22 @@ __device__ __forceinline__ void pw2_consumer(const TilePlan& p, const GridDev& g
         o[e] = a;
         if (xown && (LEAN || ((c.valid >> (k * VEC + e)) & 1u))) {  // s == 0 outside the region
           const T q = sv * sv;
-          a0 += (double)q;
+          s0.add(q);
         }
         if (in && xown) {
           const T q1 = a * sv, q2 = a * a, q3 = r0v[e] * a;
-          a1 += (double)q1;
-          a2 += (double)q2;
-          a3 += (double)q3;
+          s1.add(q1);
+          s2.add(q2);
+          s3.add(q3);
         }
       }
       stg_row<T, K, LEAN>(tp_ + (long long)k * g.n[2], c, k, o);
       if (sp_) stg_row<T, K, LEAN>(sp_ + (long long)k * g.n[2], c, k, vc[k]);
     }
+    s0.flush();
+    s1.flush();
+    s2.flush();
+    s3.flush();
     tp_ += n12;
     if (sp_) sp_ += n12;
     release(sc);

@@ -244,3 +244,51 @@ def test_implicit_euler_cg_shifted_tma_kernels_256():
     lhs = (x - phi_bc) / dt - nu * lap
     sl = (slice(2, -2),) * 3
     assert (lhs - rhs[0])[sl].abs().max().item() <= 1e-6 * rhs.abs().max().item() * max(1.0, 1.0 / dt)
+
+
+def test_more_than_2_pow_31_cells():
+    """Maximum sizes: 1296 x 1290 x 1292 = 2.16e9 cells (> 2^31, 17 GB per fp64 vector).  The fused
+    TMA CG kernels and the generic kernels must agree after 3 iterations (64-bit cell indexing in every
+    kernel, TMA coordinates, chunk planning), and one BiCGSTAB / Jacobi / Euler step stays finite."""
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~140 GB of free HBM")
+    n = [1296, 1290, 1292]
+    assert n[0] * n[1] * n[2] > 2**31
+    g = torch.Generator(device=DEV).manual_seed(11)
+    rhs = torch.rand((1, *n), generator=g, dtype=torch.float64, device=DEV)
+    ref = {}
+    for variant in (0, 1):
+        mesh, var = _problem(n)
+        s = Solver({"fdm": {"method": "cg", "tol": 1e-30, "max_it": 2, "report": False, "variant": variant}})
+        s.set_eq(FDM().laplacian(1.0, var) == rhs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rep = s.solve()
+        assert rep["itr"] == 3
+        x = var()
+        # checksums over the two halves of the array (the upper half lies beyond 2^31 bytes * 4)
+        half = n[0] // 2
+        ref[variant] = (rep["tol"], x[:, :half].sum().item(), x[:, half:].sum().item(), x[0, -2, -2, -2].item(),
+                        x.abs().max().item())
+        del s, var, mesh, x
+        torch.cuda.empty_cache()
+    a, b = ref[0], ref[1]
+    assert abs(a[0] - b[0]) <= 1e-9 * b[0]
+    for i in (1, 2):
+        assert abs(a[i] - b[i]) <= 1e-9 * abs(b[i]) + 1e-12
+    assert a[3] == pytest.approx(b[3], rel=1e-10) and a[4] == pytest.approx(b[4], rel=1e-10)
+    for method in ("bicgstab", "jacobi"):
+        mesh, var = _problem(n)
+        s = Solver({"fdm": {"method": method, "tol": 1e-300, "max_it": 2, "report": False}})
+        s.set_eq(FDM().laplacian(1.0, var) == rhs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s.solve()
+        x = var()
+        assert torch.isfinite(x[0, -3:]).all() and x[0, -2, 1:-1, 1:-1].abs().max().item() > 0.0
+        del s, var, mesh, x
+        torch.cuda.empty_cache()
