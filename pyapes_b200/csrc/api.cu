@@ -694,7 +694,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
 
   TilePlan pwtile;
   const bool pw_ok = cfg->variant != 1 && pw_eligible<T>(g, *peq, nfaces, faces);
-  if (pw_ok) pw_tile_plan<T>(g, pwtile);
+  if (pw_ok) pw_tile_plan<T>(g, pwtile, nfaces, faces);
   const TilePlan* pw = pw_ok ? &pwtile : nullptr;
 
   k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
@@ -1153,7 +1153,7 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   Launcher L{s};
   const bool tma = pw_eligible<T>(g, *peq, nfaces, faces);
   TilePlan tile;
-  if (tma) pw_tile_plan<T>(g, tile);
+  if (tma) pw_tile_plan<T>(g, tile, nfaces, faces);
   const bool stat = static_shell(nfaces, faces) != 0;
   auto one = [&](T* cur, T* nxt, bool bcs) {
     const EqDev<T>& eq = (cur == a) ? eq_a : eq_b;

@@ -47,6 +47,12 @@ struct TilePlan {
   // to chunk0 + z, the rest to chunk_hi0 + (z - chunk_split);
   // accum = 1 adds this launch's sums to the ones an earlier sub-launch stored
   int chunk0, chunk_split, chunk_hi0, accum;
+  // TMA kernels, periodic faces on kernel axes 1/2: the boxes cannot wrap (out-of-bounds halo cells
+  // arrive as zeros), so boundary tiles read the wrapped halo row / column straight from the global
+  // arrays behind the halo tensor maps
+  int wrap;
+  const void* src0;
+  const void* src1;
 };
 
 template <typename T>
@@ -135,6 +141,8 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.chunk0 = 0;
   p.chunk_split = 1 << 30;
   p.chunk_hi0 = 0;
+  p.wrap = 0;
+  p.src0 = p.src1 = nullptr;
   p.accum = 0;
   return true;
 }

@@ -159,6 +159,8 @@ struct TmaPlan {
   CUtensorMap x_own[2];     // x, x_alt  (phase B reads the current iterate)
   CUtensorMap r_own, r_halo;
   CUtensorMap d_halo[2];    // the two d buffers
+  const void* r_ptr;        // raw arrays behind r_halo / d_halo (wrap-around reads, TilePlan::src*)
+  const void* d_ptr[2];
 };
 
 // wave-aware chunking along axis 0 (shared by the CG and the star-engine plans)
@@ -191,6 +193,8 @@ inline void tma_chunks(const GridDev& g, int tiles, TilePlan& p) {
   p.chunk0 = 0;
   p.chunk_split = 1 << 30;
   p.chunk_hi0 = 0;
+  p.wrap = 0;
+  p.src0 = p.src1 = nullptr;
   p.accum = 0;
 }
 
@@ -208,9 +212,31 @@ inline bool plan_tma_k(const GridDev& g, const T* x, const T* x_alt, const T* r,
   p.tiles_y = C::FLAT ? 1 : (g.n[1] + C::TY - 1) / C::TY;
   p.tiles_z = (g.n[2] + C::TZ - 1) / C::TZ;
   tma_chunks(g, p.tiles_y * p.tiles_z, p);
+  tp.r_ptr = r;
+  tp.d_ptr[0] = d0;
+  tp.d_ptr[1] = d1;
   return make_map<T>(&tp.x_own[0], x, g, C::OBOXZ, C::TY) && make_map<T>(&tp.x_own[1], x_alt, g, C::OBOXZ, C::TY) &&
          make_map<T>(&tp.r_own, r, g, C::OBOXZ, C::TY) && make_map<T>(&tp.r_halo, r, g, C::BOXZ, C::BOXY) &&
          make_map<T>(&tp.d_halo[0], d0, g, C::BOXZ, C::BOXY) && make_map<T>(&tp.d_halo[1], d1, g, C::BOXZ, C::BOXY);
+}
+
+// Periodic faces on kernel axes 1/2: a TMA box cannot wrap around, so boundary tiles fetch the
+// wrapped halo row / column from global memory (wrap_halo); that needs whole tiles along the axis.
+template <typename T>
+inline bool tma_wrap_ok(const GridDev& g, int nfaces, const pa_face_bc* faces, int* wrap) {
+  *wrap = 0;
+  const bool flat = tma_flat(g);
+  for (int f = 0; f < nfaces; ++f) {
+    if (faces[f].kind != PA_BC_PERIODIC || faces[f].axis == 0) continue;
+    if (faces[f].axis == 1) {
+      if (flat || g.n[1] % TmaCfg<T, KStd>::TY != 0) return false;
+    } else {
+      const int tz = flat ? TmaCfg<T, KFlat>::TZ : TmaCfg<T, KStd>::TZ;
+      if (g.n[2] % tz != 0) return false;
+    }
+    *wrap = 1;
+  }
+  return true;
 }
 
 // a STAR operator that is c*phi and nothing else, with sign +1 and no parameter: the form in
@@ -238,10 +264,12 @@ inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const 
       o.param_field != nullptr || o.edge != 0 || o.coef_tab[0] || o.coef_tab[1] || o.coef_tab[2])
     return false;
   if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;  // 1-D meshes stay on the generic kernels
-  for (int f = 0; f < nfaces; ++f)  // wrap-around on axes 1/2 is not expressible as a TMA box
-    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
-  return tma_flat(g) ? plan_tma_k<T, KFlat>(g, x, x_alt, r, d0, d1, tp)
-                     : plan_tma_k<T, KStd>(g, x, x_alt, r, d0, d1, tp);
+  int wrap = 0;
+  if (!tma_wrap_ok<T>(g, nfaces, faces, &wrap)) return false;
+  const bool ok = tma_flat(g) ? plan_tma_k<T, KFlat>(g, x, x_alt, r, d0, d1, tp)
+                              : plan_tma_k<T, KStd>(g, x, x_alt, r, d0, d1, tp);
+  tp.tile.wrap = wrap;
+  return ok;
 }
 
 // ---- consumer-side geometry -----------------------------------------------------------------------
@@ -253,6 +281,7 @@ struct ConsCtx {
   long long goff;  // element offset of (own row 0, element 0) inside a global plane
   unsigned valid, inreg, nonshell;  // bit k*VEC+e   (GENERAL path)
   int cly[K::RY], clz[VecOf<T>::N];
+  int yb, zg;  // global (axis 1, axis 2) index of the thread's first cell
 };
 
 template <typename T, typename K>
@@ -270,6 +299,8 @@ __device__ __forceinline__ void cons_setup(const GridDev& g, ConsCtx<T, K>& c, i
     c.ooff = (wy * K::RY) * C::OBOXZ + col;
   }
   const int yb = y0 + wy * K::RY, zg = z0 + col;
+  c.yb = yb;
+  c.zg = zg;
   c.goff = (long long)yb * g.n[2] + zg;
   c.valid = c.inreg = c.nonshell = 0u;
 #pragma unroll
@@ -338,6 +369,35 @@ __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, con
 #pragma unroll
     for (int e = 0; e < N; ++e)
       if ((m >> e) & 1u) p[e] = v[e];
+  }
+}
+
+// Wrap-around halos of plane x for periodic kernel axes 1/2 (boundary tiles only; tma_wrap_ok
+// guarantees whole tiles).  `val(i)` returns the stencilled quantity at linear index i from global
+// memory, computed exactly like the staged one.  A row/column is wrapped when the first/last index of
+// the axis is inside the solver region (mesh/tools.py:7-20 opens the slicer on periodic sides).
+template <typename T, typename K, typename F>
+__device__ __forceinline__ void wrap_halo(const GridDev& g, const ConsCtx<T, K>& c, int x, T (&up)[VecOf<T>::N],
+                                          T (&dn)[VecOf<T>::N], T (&zl)[K::RY], T (&zr)[K::RY], F val) {
+  constexpr int VEC = VecOf<T>::N;
+  const long long base = (long long)x * g.n[1] * g.n[2];
+  if (!K::FLAT) {
+    if (c.yb == 0 && g.lo[1] == 0) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) up[e] = val(base + (long long)(g.n[1] - 1) * g.n[2] + c.zg + e);
+    }
+    if (c.yb + K::RY == g.n[1] && g.hi[1] == g.n[1]) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dn[e] = val(base + c.zg + e);
+    }
+  }
+  if (c.zg == 0 && g.lo[2] == 0) {
+#pragma unroll
+    for (int k = 0; k < K::RY; ++k) zl[k] = val(base + (long long)(c.yb + k) * g.n[2] + g.n[2] - 1);
+  }
+  if (c.zg + VEC == g.n[2] && g.hi[2] == g.n[2]) {
+#pragma unroll
+    for (int k = 0; k < K::RY; ++k) zr[k] = val(base + (long long)(c.yb + k) * g.n[2]);
   }
 }
 
@@ -467,6 +527,10 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
         for (int k = 0; k < K::RY; ++k) {
           zl[k] = h[k * C::BOXZ - 1];
           zr[k] = h[k * C::BOXZ + VEC];
+        }
+        if (!LEAN && p.wrap) {
+          const T* dg = static_cast<const T*>(p.src0);
+          wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return dg[i]; });
         }
         const int clx = actx ? coef_class(g, 0, x) : 0;
         const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
@@ -690,6 +754,11 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
         zl[k] = rp[k * C::BOXZ - 1] + beta * dp[k * C::BOXZ - 1];
         zr[k] = rp[k * C::BOXZ + VEC] + beta * dp[k * C::BOXZ + VEC];
       }
+      if (!LEAN && p.wrap) {
+        const T* rg = static_cast<const T*>(p.src0);
+        const T* dg = static_cast<const T*>(p.src1);
+        wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return rg[i] + beta * dg[i]; });
+      }
       const int clx = actx ? coef_class(g, 0, x) : 0;
       const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
       // d == 0 outside the solver region: d*Ad needs no region mask, only array bounds
@@ -796,7 +865,10 @@ static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     attr = true;
   }
   dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
-  k_cg_phaseA_tma<T, K><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tp.tile, g, eq.op[0],
+  TilePlan tile = tp.tile;
+  tile.src0 = tp.r_ptr;
+  tile.src1 = tp.d_ptr[parity];
+  k_cg_phaseA_tma<T, K><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tile, g, eq.op[0],
                                                            d_new, st, partials);
 }
 
@@ -820,6 +892,7 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
   }
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
   TilePlan tile = tp.tile;
+  tile.src0 = tp.d_ptr[1 - parity];
   int nz = tile.chunks;
   // the boundary sub-launch must produce the first and the last OWNED plane (they leave with the
   // halo exchange while the interior sub-launch runs): every chunk up to the one holding plane

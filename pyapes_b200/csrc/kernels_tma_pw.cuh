@@ -231,6 +231,10 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
         zl[k] = h[k * C::BOXZ - 1];
         zr[k] = h[k * C::BOXZ + VEC];
       }
+      if (!LEAN && p.wrap) {
+        const T* ing = static_cast<const T*>(p.src0);
+        wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return ing[i]; });
+      }
       const int clx = coef_class(g, 0, x);
       star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, vm, vc, vp, up, dn, zl, zr,
                                       [&](int k, int e, T v) { ax[k][e] = v; });
@@ -487,6 +491,11 @@ __device__ __forceinline__ void pw2_consumer(const TilePlan& p, const GridDev& g
         zl[k] = rp[k * C::BOXZ - 1] - alpha * vq[k * C::BOXZ - 1];
         zr[k] = rp[k * C::BOXZ + VEC] - alpha * vq[k * C::BOXZ + VEC];
       }
+      if (!LEAN && p.wrap) {
+        const T* rg = static_cast<const T*>(p.src0);
+        const T* vg = static_cast<const T*>(p.src1);
+        wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return rg[i] - alpha * vg[i]; });
+      }
       star_cells_eq<T, K, LEAN, NOPS>(eq, c, coef_class(g, 0, x), vm, vc, vp, up, dn, zl, zr,
                                       [&](int k, int e, T v) { ax[k][e] = v; });
     }
@@ -625,13 +634,13 @@ inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, con
   if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;
   if (g.n[2] % VEC != 0 || g.n[2] < 2 * VEC) return false;
   if (g.act[1] && g.n[1] < 4) return false;
-  for (int f = 0; f < nfaces; ++f)
-    if (faces[f].kind == PA_BC_PERIODIC && faces[f].axis != 0) return false;
+  int wrap = 0;
+  if (!tma_wrap_ok<T>(g, nfaces, faces, &wrap)) return false;
   return encode_tiled_fn() != nullptr;
 }
 
 template <typename T>
-inline void pw_tile_plan(const GridDev& g, TilePlan& p) {
+inline void pw_tile_plan(const GridDev& g, TilePlan& p, int nfaces = 0, const pa_face_bc* faces = nullptr) {
   const bool flat = tma_flat(g);
   const int ty = flat ? 1 : PwCfg<T, KStd>::TY;
   const int tz = flat ? PwCfg<T, KFlat>::TZ : PwCfg<T, KStd>::TZ;
@@ -639,6 +648,7 @@ inline void pw_tile_plan(const GridDev& g, TilePlan& p) {
   p.tiles_y = flat ? 1 : (g.n[1] + ty - 1) / ty;
   p.tiles_z = (g.n[2] + tz - 1) / tz;
   tma_chunks(g, p.tiles_y * p.tiles_z, p);
+  tma_wrap_ok<T>(g, nfaces, faces, &p.wrap);
 }
 
 // One launch of the engine.  `in` is the stencilled field, `aux` rhs / r0 (may be null).
@@ -658,10 +668,12 @@ static void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CU
 }
 
 template <typename T, typename K, int MODE>
-static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile,
+static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile_in,
                               const T* in, const T* aux, T* out, T* out2, T dt, SolverState* st,
                               double* partials, int stage) {
   typedef PwCfg<T, K> C;
+  TilePlan tile = tile_in;
+  tile.src0 = in;  // wrap-around reads of periodic axes 1/2
   CUtensorMap tm_in, tm_aux;
   if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
   if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::OBOXZ, C::TY)) return false;
@@ -691,10 +703,13 @@ static void launch_bi_st_n(cudaStream_t s, const CUtensorMap& tm_r, const CUtens
 }
 
 template <typename T, typename K>
-static bool launch_bi_st_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, const T* r,
+static bool launch_bi_st_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile_in, const T* r,
                            const T* v, const T* r0, T* t_out, T* s_out, SolverState* st, double* partials,
                            int stage) {
   typedef Pw2Cfg<T, K> C;
+  TilePlan tile = tile_in;
+  tile.src0 = r;
+  tile.src1 = v;
   CUtensorMap tm_r, tm_v, tm_r0;
   if (!make_map<T>(&tm_r, r, g, C::BOXZ, C::BOXY) || !make_map<T>(&tm_v, v, g, C::BOXZ, C::BOXY) ||
       !make_map<T>(&tm_r0, r0, g, C::OBOXZ, C::TY))
