@@ -166,8 +166,10 @@ typedef struct {
   int32_t max_it;
   int32_t check_every; /* iterations between host polls of the device-side done flag (0 = default) */
   int32_t use_graph;   /* capture the iteration in a CUDA graph */
-  int32_t variant;     /* 0 = auto (TMA-staged fused kernels, else register-tiled, else generic),
-                          1 = generic kernels, 2 = register-tiled kernels (no TMA) */
+  int32_t variant;     /* 0 = auto (small grids: persistent kernel; TMA-staged fused kernels, else
+                          register-tiled, else generic), 1 = generic kernels, 2 = register-tiled kernels
+                          (no TMA), 3 = CG as one persistent cooperative kernel (small grids, every
+                          face Dirichlet), 4 = like 0 but never the persistent kernel */
 } pa_solver_cfg;
 
 const char* pa_last_error(void);

@@ -10,6 +10,7 @@
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
 #include "kernels_tma_pw.cuh"
+#include "kernels_small.cuh"
 #include "dist.cuh"
 
 namespace pa {
@@ -108,6 +109,11 @@ static int check_faces(int nfaces, const pa_face_bc* faces) {
   }
   return PA_OK;
 }
+
+// auto-selection threshold of the persistent small-grid CG kernel (cells); see DESIGN.md §4
+// measured (tools/bench_small.py): 9.7-10.9 us per iteration against 16.2 us for the fused kernels up to
+// 256^2 / 32^3, break-even near 110 k cells
+constexpr long long kSmallCgCells = 80000;
 
 static inline int grid_blocks(long long cells) {
   long long b = (cells + kBlock - 1) / kBlock;
@@ -678,11 +684,12 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   bool tiled = false;
   TmaPlan tmap;
   bool use_tma = false;
-  if (method == PA_METHOD_CG && cfg->variant == 0) {
+  const bool auto_fused = cfg->variant == 0 || cfg->variant == 4;  // 4: fused kernels, never the persistent one
+  if (method == PA_METHOD_CG && auto_fused) {
     use_tma = plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], tmap);
     if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
   }
-  if (method == PA_METHOD_CG && !use_tma && (cfg->variant == 0 || cfg->variant == 2))
+  if (method == PA_METHOD_CG && !use_tma && (auto_fused || cfg->variant == 2))
     tiled = plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
   if (dist) {
@@ -773,6 +780,39 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     rep->result_in_alt = 0;
     rep->launches = L.count;
     return PA_OK;
+  }
+
+  // Small grids: the whole CG solve as ONE persistent cooperative kernel (kernels_small.cuh) -- the
+  // iteration of the fused kernels is launch-bound there.  variant 3 forces it, auto (0) takes it
+  // below kSmallCgCells.
+  if (method == PA_METHOD_CG && !dist && !nonlinear && static_shell(nfaces, faces) &&
+      (cfg->variant == 3 || (cfg->variant == 0 && g.cells <= kSmallCgCells))) {
+    const int maxb = small_cg_max_blocks<T>();
+    if (maxb > 0) {
+      long long want = (g.cells + kSmallBlock - 1) / kSmallBlock;
+      int blocks = (int)(want < maxb ? want : maxb);
+      if (blocks > kMaxPartials) blocks = kMaxPartials;
+      T* r = (T*)w.vec[0];
+      T* d = (T*)w.vec[1];
+      double* partA = w.partials;
+      double* partB = w.partials + 2 * kMaxPartials;
+      PA_CUDA(cudaMemcpyAsync(x_alt, x, vbytes, cudaMemcpyDeviceToDevice, stream));  // the static shell
+      void* args[] = {(void*)&g, (void*)&eq, (void*)&x, (void*)&x_alt, (void*)&r, (void*)&d, (void*)&w.st,
+                      (void*)&partA, (void*)&partB};
+      PA_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_persistent<T>, dim3(blocks), dim3(kSmallBlock), args, 0,
+                                          stream));
+      L.count += 2;
+      SolverState* hs = nullptr;
+      int rcp = poll_state(stream, w.st, &hs);
+      if (rcp != PA_OK) return rcp;
+      PA_CUDA(cudaGetLastError());
+      if (!hs->done) return fail(PA_ERR_CUDA, "persistent CG kernel returned without latching `done`");
+      fill_report(rep, hs, L.count);
+      int swaps = hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0);
+      rep->result_in_alt = swaps & 1;
+      return PA_OK;
+    }
+    if (cfg->variant == 3) return fail(PA_ERR_UNSUPPORTED, "cooperative launch is not available on this device");
   }
 
   // fused TMA CG kernels with an implicit-Euler term: operator 0 + diagonal shift (plan_tma)

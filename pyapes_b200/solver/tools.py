@@ -13,7 +13,7 @@ class FDMSolverConfig(TypedDict, total=False):
     # optional knobs of this implementation (ignored by the reference)
     check_every: int  # iterations between host polls of the device-side convergence latch
     use_graph: bool   # replay the iteration as a CUDA graph
-    variant: int      # 0 tiled fused kernels when applicable, 1 generic kernels
+    variant: int      # 0 auto, 1 generic kernels, 2 register-tiled, 3 persistent small-grid CG, 4 fused (TMA) only
     n_steps: int      # explicit Euler: time steps per solve()
 
 

@@ -215,7 +215,7 @@ def _run_solver_case(case, **extra):
 
 
 @pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["auto_tma", "generic", "tiled"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["auto", "generic", "tiled", "persistent", "fused_tma"])
 def test_solver_fixtures(case, variant):
     """Parity bar per solver:
     CG        — iteration count EXACT, final tol to 1e-10 absolute, solution to 1e-9 relative.
@@ -264,7 +264,7 @@ def test_solver_fixtures(case, variant):
         assert dsol <= max(20 * case["sens_dsol"], 1e-9 * smax), (dsol, case["sens_dsol"])
 
 
-@pytest.mark.parametrize("method", ["cg", "bicgstab", "jacobi"])
+@pytest.mark.parametrize("method", ["cg", "cg_fused", "bicgstab", "jacobi"])
 @pytest.mark.parametrize("bcname", ["dirichlet", "mixed"])
 def test_solvers_vs_oracle_48(method, bcname):
     """Seeded 3-D case at a size the oracle finishes in seconds, compared with the oracle run
@@ -277,6 +277,9 @@ def test_solvers_vs_oracle_48(method, bcname):
     from pyapes_b200.variables.bcs import mixed_bcs
 
     n = [40, 36, 48]
+    # 69 k cells: `cg` takes the persistent small-grid kernel (auto), `cg_fused` forces the TMA kernels
+    variant = 4 if method == "cg_fused" else 0
+    method = "cg" if method == "cg_fused" else method
     if bcname == "dirichlet":
         kinds, vals = ["dirichlet"] * 6, [0.0, 0.25, 0.0, 0.0, -0.5, 0.0]
     else:
@@ -291,7 +294,7 @@ def test_solvers_vs_oracle_48(method, bcname):
     var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
     g = torch.Generator().manual_seed(99)
     rhs_h = torch.rand(1, *n, generator=g, dtype=torch.float64) - 0.5
-    solver = Solver({"fdm": {"method": method, "tol": tol, "max_it": max_it, "report": False}})
+    solver = Solver({"fdm": {"method": method, "tol": tol, "max_it": max_it, "report": False, "variant": variant}})
     solver.set_eq(FDM().laplacian(1.0, var) == rhs_h.to(DEV))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
