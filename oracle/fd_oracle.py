@@ -10,8 +10,11 @@ Field/Mesh objects.  It keeps the reference's *operation order* so that, on the 
 it is bit-identical to the reference on CPU.  That is pinned by `tests/test_oracle_golden.py`
 against fixtures produced by the real reference (`tests/golden/make_golden.py`).
 Parity status: PINNED for Laplacian/Grad/Div apply, rhs adjustment, BC application, CG and
-BiCGSTAB.  `jacobi` and `euler_step` have NO counterpart in the reference (SURVEY.md §0 items
-1-2): they are defined here from reference primitives and are "parity unpinned".
+BiCGSTAB, edge=True one-sided stencils, jacobian/hessian, the axisymmetric (rz) operators and
+nonlinear advection `div(var, var)` (tests/golden/{ops,solvers,edges,rz_ops,nonlinear}.pt, all
+produced by the real reference).  `jacobi`, `euler_step` and `implicit_euler_step` have NO
+counterpart in the reference (fdm.Ddt is a stub): they are defined here from
+reference primitives and are "parity unpinned" (the implicit step is checked against a dense solve).
 
 Citations are `file:line` in /root/reference (pyapes v0.2.13).
 
