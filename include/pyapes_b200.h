@@ -246,6 +246,17 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
                      size_t ws_bytes, void* comm, int rank, int nranks, pa_report* report,
                      void* stream);
 
+/* --- peer-memory mailboxes for the fused all-reduces (optional; without them the solvers use
+ *     ncclAllReduce).  Every rank: pa_p2p_local_handle() -> 64-byte CUDA IPC handle of its mailbox;
+ *     the host layer all-gathers the handles; pa_p2p_attach(all handles, rank, nranks) maps the peers
+ *     (NVLink peer access).  From then on the slab-decomposed CG sums d.Ad and {r.r, |dx|^2} over the
+ *     ranks INSIDE the kernels that produce them (one thread per rank writes its partial sums into every
+ *     peer's mailbox and adds the others' in rank order) and finalizes the scalar stage there. */
+int pa_p2p_local_handle(void* out64);
+int pa_p2p_attach(const void* handles, int rank, int nranks);
+int pa_p2p_enabled(void);
+int pa_p2p_disable(void); /* every rank must agree: the host layer disables all if one rank failed to attach */
+
 /* --- any of the three solvers on a slab (method = PA_METHOD_*); pa_cg_solve_dist is the CG case.
  *     BiCGSTAB: p and s get their ghost planes by one send/recv pair each before the operator
  *     application that reads them, and {r0.v}, {|s|^2}, {t.s, t.t, r0.t}, {|r|^2} are all-reduced

@@ -224,7 +224,7 @@ static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_
 
 template <typename T>
 static void launch_shell(Launcher& L, const GridDev& g, const T* a, const T* b, SolverState* st,
-                         double* partials, int stage) {
+                         double* partials, int stage, P2PDev p2p = P2PDev{nullptr, 0, 0, 0, 0}) {
   long long m = 1;
   for (int ax = 0; ax < 3; ++ax) {
     int bb = (ax == 0) ? 1 : 0, cc = (ax == 2) ? 1 : 2;
@@ -234,11 +234,14 @@ static void launch_shell(Launcher& L, const GridDev& g, const T* a, const T* b, 
   int bx = (int)((m + kBlock - 1) / kBlock);
   if (bx > 128) bx = 128;
   dim3 grid(bx, 6);
-  k_shell_norm<T><<<grid, kBlock, 0, L.s>>>(g, a, b, st, partials, stage);
+  k_shell_norm<T><<<grid, kBlock, 0, L.s>>>(g, a, b, st, partials, stage, p2p);
   ++L.count;
 }
 
-__global__ void k_state_init(SolverState* st, double tolerance, int max_it) {
+__global__ void k_state_init(SolverState* st, double tolerance, int max_it, unsigned long long epoch = 1ull) {
+  st->epoch = epoch;
+  st->halo_count = 0u;
+  st->halo_target = 0u;
   for (int i = 0; i < 8; ++i) {
     st->sum[i] = 0.0;
     st->scal[i] = 0.0;
@@ -340,11 +343,37 @@ struct CommLane {
 static CommLane* comm_lane() {
   static CommLane lane;
   if (!lane.s) {
-    if (cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int lo = 0, hi = 0;  // highest priority: its few CTAs must not queue behind the compute kernel's
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&lane.s, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&lane.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&lane.join, cudaEventDisableTiming);
   }
   return &lane;
+}
+
+// ---- peer-memory mailboxes (common.cuh P2PDev) ------------------------------------------------
+// Process-wide: one communicator per process.  `epoch` is the number of peer all-reduces completed so
+// far; it is identical on every rank because all ranks run the same solves with bitwise identical
+// scalars (and therefore the same iteration counts).
+struct P2PCtx {
+  unsigned long long* local = nullptr;       // this rank's mailbox (device memory, exported by IPC)
+  unsigned long long** peers_dev = nullptr;  // device array [nranks] of mapped mailboxes
+  int rank = 0, nranks = 0;
+  unsigned long long epoch = 0;
+  bool ready = false;
+};
+static P2PCtx g_p2p;
+constexpr size_t kMailboxBytes = 2 * 16 * 8 * sizeof(unsigned long long);
+
+static P2PDev p2p_dev(const Dist* dist) {
+  P2PDev d{nullptr, 0, 0, 0, 0};
+  if (dist && g_p2p.ready && g_p2p.nranks == dist->nranks && g_p2p.rank == dist->rank && dist->nranks <= 16) {
+    d.peers = g_p2p.peers_dev;
+    d.me = g_p2p.rank;
+    d.nranks = g_p2p.nranks;
+  }
+  return d;
 }
 
 // ---- CG -----------------------------------------------------------------------------------
@@ -363,11 +392,13 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
   T* r = (T*)w.vec[0];
   T* d = (T*)w.vec[1];
   int nb = grid_blocks(g.cells);
+  // slabs + peer mailboxes: the all-reduces and scalar stages run inside the fused kernels
+  const bool p2p = tma != nullptr && tma->tile.p2p.peers != nullptr;
   if (tma) {
     T* d_new = (T*)w.vec[2 - parity];
     launch_cg_phaseA_tma<T>(L.s, *tma, g, eq, parity, d_new, w.st, w.partials);
     ++L.count;
-    if (dist) {
+    if (dist && !p2p) {
       dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
       k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_DAD, w.st);
       L.count += 2;
@@ -375,14 +406,19 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     mark(1);
     CommLane* lane = (dist && tma_interior_chunks(*tma, g) >= 4) ? comm_lane() : nullptr;  // enough interior work to hide it
     if (lane) {
-      // overlap: boundary chunks first, their r planes go out on the comm stream while the
-      // interior chunks run
-      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, 1);
+      // overlap: ONE phase B launch whose boundary chunks are scheduled first and count themselves
+      // in; on the (high-priority) communication stream k_wait_halo waits for that count, then their r
+      // planes go out while the interior chunks are still running.  (A split into two launches cost
+      // a wave: 1.7 + 5.2 -> 2 + 6 waves instead of 6.9 -> 7.)
+      // (phase B is enqueued BEFORE the waiting kernel: outside graph capture the host may block
+      //  inside the NCCL enqueue, and a spinning k_wait_halo must never wait for a kernel that the
+      //  host has not been able to submit yet)
       cudaEventRecord(lane->fork, L.s);
+      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, 3);
       cudaStreamWaitEvent(lane->s, lane->fork, 0);
+      k_wait_halo<<<1, 1, 0, lane->s>>>(w.st, tma_boundary_ctas(*tma, g));
       dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, lane->s);
       cudaEventRecord(lane->join, lane->s);
-      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, 2);
       L.count += 3;
       overlapped = true;
     } else {
@@ -424,17 +460,24 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
     }
   } else {
     // multi-GPU: boundary planes of the new r to the neighbours' ghosts, then the three sums
-    if (static_shell(nfaces, faces)) {
-      cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
+    const bool stat = static_shell(nfaces, faces) != 0;
+    if (stat) {
+      if (!p2p) cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
     } else {
       launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
-      launch_shell<T>(L, g, nxt, cur, w.st, w.partials, ST_NONE);
+      P2PDev pp = p2p ? tma->tile.p2p : P2PDev{nullptr, 0, 0, 0, 0};
+      pp.slot0 = R_A;
+      pp.count = 4;
+      launch_shell<T>(L, g, nxt, cur, w.st, w.partials, p2p ? ST_CG_FIN : ST_NONE, pp);
     }
     if (!overlapped) dist_halo_exchange<T>(*dist, r, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
-    dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
-    k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_FIN, w.st);
+    if (!p2p) {  // (p2p, static shell: phase B has already reduced and finalized)
+      dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
+      k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_FIN, w.st);
+      L.count += 2;
+    }
     if (overlapped) cudaStreamWaitEvent(L.s, comm_lane()->join, 0);  // r ghosts before the next phase A
-    L.count += 3;
+    ++L.count;
   }
   mark(3);
 }
@@ -697,6 +740,10 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     nccl_first_error() = ncclSuccess;
     plan.dist = tmap.tile.dist = 1;
     plan.fuse_fin = tmap.tile.fuse_fin = 0;
+    if (use_tma && cfg->variant != 4) {  // (variant 4 on slabs: keep the NCCL all-reduces, for A/B runs)
+      tmap.tile.p2p = p2p_dev(dist);
+      if (tmap.tile.p2p.peers != nullptr) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+    }
   }
 
   TilePlan pwtile;
@@ -704,7 +751,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (pw_ok) pw_tile_plan<T>(g, pwtile, nfaces, faces);
   const TilePlan* pw = pw_ok ? &pwtile : nullptr;
 
-  k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it);
+  k_state_init<<<1, 1, 0, stream>>>(w.st, cfg->tol, cfg->max_it, g_p2p.epoch + 1ull);
   ++L.count;
   if (dist && dist->ring) bc_scratch((size_t)2 * g.n[1] * g.n[2] * sizeof(T));  // before any capture
   launch_bcs<T>(L, g, nfaces, faces, x, nullptr, dist);
@@ -906,6 +953,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     dist_halo_exchange<T>(*dist, x_alt, plane, g.olo0, g.ohi0, stream);
     PA_CUDA(cudaStreamSynchronize(stream));
   }
+  if (dist && tmap.tile.p2p.peers != nullptr) g_p2p.epoch = h->epoch - 1ull;
   fill_report(rep, h, L.count);
   // iterations completed with an update == number of ping-pong swaps
   int swaps = h->itr;
@@ -1100,6 +1148,57 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
                                    (const T*)rhs, cfg, ws, ws_bytes_, report, (cudaStream_t)stream,
                                    nranks > 1 ? &d : nullptr));
+}
+
+int pa_p2p_local_handle(void* out64) {
+  PA_REQUIRE_DEVICE();
+  if (!out64) return fail(PA_ERR_ARG, "null argument");
+  if (!g_p2p.local) {
+    PA_CUDA(cudaMalloc((void**)&g_p2p.local, kMailboxBytes));
+    PA_CUDA(cudaMemset(g_p2p.local, 0, kMailboxBytes));
+    PA_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  PA_CUDA(cudaIpcGetMemHandle(&h, g_p2p.local));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &h, sizeof(h));
+  return PA_OK;
+}
+
+int pa_p2p_attach(const void* handles, int rank, int nranks) {
+  PA_REQUIRE_DEVICE();
+  if (!handles || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || !g_p2p.local)
+    return fail(PA_ERR_ARG, "bad argument (call pa_p2p_local_handle first; at most 16 ranks)");
+  std::vector<unsigned long long*> ptrs((size_t)nranks, nullptr);
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) {
+      ptrs[p] = g_p2p.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)p, sizeof(h));
+    void* mapped = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PA_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    ptrs[p] = (unsigned long long*)mapped;
+  }
+  if (!g_p2p.peers_dev) PA_CUDA(cudaMalloc((void**)&g_p2p.peers_dev, 16 * sizeof(unsigned long long*)));
+  PA_CUDA(cudaMemcpy(g_p2p.peers_dev, ptrs.data(), (size_t)nranks * sizeof(unsigned long long*),
+                     cudaMemcpyHostToDevice));
+  g_p2p.rank = rank;
+  g_p2p.nranks = nranks;
+  g_p2p.epoch = 0;
+  g_p2p.ready = true;
+  return PA_OK;
+}
+
+int pa_p2p_enabled(void) { return g_p2p.ready ? 1 : 0; }
+int pa_p2p_disable(void) {
+  g_p2p.ready = false;
+  return PA_OK;
 }
 
 int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,

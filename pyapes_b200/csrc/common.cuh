@@ -249,7 +249,48 @@ struct SolverState {
   int finished_flag;  // bicgstab's `finished`
   int pad;
   unsigned int ticket[8];
+  unsigned long long epoch;  // sequence number of the next peer-memory all-reduce (p2p_allreduce)
+  unsigned int halo_count;   // boundary CTAs of phase B that have written their planes (monotonic)
+  unsigned int halo_target;  // value halo_count reaches when the current iteration's are all done
 };
+
+// ---- all-reduce over NVLink peer memory -----------------------------------------------------
+// One process per GPU; every rank owns a small mailbox in device memory that its peers map through
+// CUDA IPC (api.cu pa_p2p_*).  A reduction is executed by ONE thread per rank -- the thread that has
+// just finished the grid-wide reduction of a fused kernel -- so the sum over ranks and the scalar
+// stage that consumes it happen inside the kernel that produced the local sum: no NCCL launch, no
+// finalize launch.  Mailbox of the receiver: [slot 2][source rank 16][8 words]; words 0..3 carry the
+// values, word 7 the epoch.  Epochs increase monotonically over the life of the process, a rank can
+// be at most one reduction ahead of the slowest one, so two slots never collide.  Every rank adds the
+// contributions in rank order: the result is bitwise identical everywhere.
+struct P2PDev {
+  unsigned long long* const* peers;  // device array [nranks]: mailbox of every rank (peers[me] is local)
+  int me, nranks;
+  int slot0, count;                  // which SolverState::sum entries are reduced
+};
+
+__device__ __forceinline__ void p2p_allreduce(const P2PDev& pp, unsigned long long epoch, double* vals) {
+  const int slot = (int)(epoch & 1ull);
+  const int off = (slot * 16 + pp.me) * 8;
+  for (int p = 0; p < pp.nranks; ++p) {
+    volatile unsigned long long* dst = pp.peers[p] + off;
+    for (int k = 0; k < pp.count; ++k) dst[k] = (unsigned long long)__double_as_longlong(vals[k]);
+  }
+  __threadfence_system();
+  for (int p = 0; p < pp.nranks; ++p) {
+    volatile unsigned long long* dst = pp.peers[p] + off;
+    dst[7] = epoch;
+  }
+  double tot[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int q = 0; q < pp.nranks; ++q) {
+    volatile unsigned long long* src = pp.peers[pp.me] + (slot * 16 + q) * 8;
+    while (src[7] != epoch) {
+    }
+    __threadfence_system();
+    for (int k = 0; k < pp.count; ++k) tot[k] += __longlong_as_double((long long)src[k]);
+  }
+  for (int k = 0; k < pp.count; ++k) vals[k] = tot[k];
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -186,9 +186,17 @@ struct StoreSums {
   int slot0;
   int stage;  // ST_NONE: just store
   int accum = 0;  // add to what an earlier sub-launch stored
+  P2PDev p2p = {nullptr, 0, 0, 0, 0};  // multi-GPU: sum over ranks through peer memory before `stage`
   __device__ void operator()(double (&acc)[NS]) const {
 #pragma unroll
     for (int s = 0; s < NS; ++s) st->sum[slot0 + s] = accum ? st->sum[slot0 + s] + acc[s] : acc[s];
+    if (p2p.peers != nullptr) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int k = 0; k < p2p.count; ++k) v[k] = st->sum[p2p.slot0 + k];
+      p2p_allreduce(p2p, st->epoch, v);
+      for (int k = 0; k < p2p.count; ++k) st->sum[p2p.slot0 + k] = v[k];
+      st->epoch += 1ull;
+    }
     if (stage != ST_NONE) finalize_stage<T>(stage, st);
   }
 };
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(kBlock) k_bc_face(GridDev g, FaceDev<T> f, T* 
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_shell_norm(GridDev g, const T* __restrict__ a,
                                                        const T* __restrict__ b, SolverState* st,
-                                                       double* partials, int stage) {
+                                                       double* partials, int stage, P2PDev p2p) {
   if (st->done) return;
   double v[1] = {0.0};
   const int face = blockIdx.y, ax = face >> 1, up = face & 1;
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(kBlock) k_shell_norm(GridDev g, const T* __res
   }
   int nblocks = gridDim.x * gridDim.y;
   int bid = blockIdx.y * gridDim.x + blockIdx.x;
-  grid_reduce<1>(v, partials, nblocks, bid, &st->ticket[3], StoreSums<T, 1>{st, R_SHELL, stage});
+  grid_reduce<1>(v, partials, nblocks, bid, &st->ticket[3], StoreSums<T, 1>{st, R_SHELL, stage, 0, p2p});
 }
 
 // ---------------------------------------------------------------------------------------

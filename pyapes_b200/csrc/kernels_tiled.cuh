@@ -43,17 +43,28 @@ struct TilePlan {
   int fuse_fin;                      // phase B also finalizes the iteration (static shell)
   int ry;                            // rows per thread of the instantiation to launch (2 or 4)
   int dist;                          // multi-GPU: leave raw sums for the NCCL all-reduce
-  // sub-launch over a subset of the chunks (halo-exchange overlap): blockIdx.z < chunk_split maps
-  // to chunk0 + z, the rest to chunk_hi0 + (z - chunk_split);
+  // blockIdx.z -> chunk (halo-exchange overlap on slabs): the first b_lo launch slots are the lowest
+  // chunks, the next b_hi the highest ones, the rest continue from chunk0 -- so the chunks that hold the
+  // first / last owned plane can run first (tile_chunk()).  signal_halo: those boundary CTAs count
+  // themselves in SolverState::halo_count when their planes are written (k_wait_halo).
   // accum = 1 adds this launch's sums to the ones an earlier sub-launch stored
-  int chunk0, chunk_split, chunk_hi0, accum;
+  int chunk0, b_lo, b_hi, signal_halo, accum;
   // TMA kernels, periodic faces on kernel axes 1/2: the boxes cannot wrap (out-of-bounds halo cells
   // arrive as zeros), so boundary tiles read the wrapped halo row / column straight from the global
   // arrays behind the halo tensor maps
   int wrap;
   const void* src0;
   const void* src1;
+  // multi-GPU, TMA CG kernels: all-reduce over peer memory inside the kernel (common.cuh P2PDev);
+  // peers == nullptr -> raw sums are left for the NCCL all-reduce + k_finalize pair
+  P2PDev p2p;
 };
+
+__device__ __forceinline__ int tile_chunk(const TilePlan& p, int z) {
+  if (z < p.b_lo) return z;
+  if (z < p.b_lo + p.b_hi) return p.chunks - p.b_hi + (z - p.b_lo);
+  return p.chunk0 + (z - p.b_lo - p.b_hi);
+}
 
 template <typename T>
 struct VecOf;
@@ -139,10 +150,10 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.fuse_fin = 0;
   p.dist = 0;
   p.chunk0 = 0;
-  p.chunk_split = 1 << 30;
-  p.chunk_hi0 = 0;
+  p.b_lo = p.b_hi = p.signal_halo = 0;
   p.wrap = 0;
   p.src0 = p.src1 = nullptr;
+  p.p2p = P2PDev{nullptr, 0, 0, 0, 0};
   p.accum = 0;
   return true;
 }

@@ -191,10 +191,10 @@ inline void tma_chunks(const GridDev& g, int tiles, TilePlan& p) {
   p.fuse_fin = 0;
   p.dist = 0;
   p.chunk0 = 0;
-  p.chunk_split = 1 << 30;
-  p.chunk_hi0 = 0;
+  p.b_lo = p.b_hi = p.signal_halo = 0;
   p.wrap = 0;
   p.src0 = p.src1 = nullptr;
+  p.p2p = P2PDev{nullptr, 0, 0, 0, 0};
   p.accum = 0;
 }
 
@@ -612,7 +612,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
   const int zc = (int)blockIdx.z;
-  const int x0 = (zc < p.chunk_split ? p.chunk0 + zc : p.chunk_hi0 + (zc - p.chunk_split)) * p.cx;
+  const int x0 = tile_chunk(p, zc) * p.cx;
   const int x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
@@ -656,11 +656,23 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
     else
       tmaB_consumer<T, K, false>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
   }
+  if (p.signal_halo && zc < p.b_lo + p.b_hi) {
+    // a boundary chunk: its r planes may leave for the neighbour rank as soon as every such CTA is
+    // done (k_wait_halo on the communication stream) while the interior chunks still run
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&st->halo_count, 1u);
+  }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (p.fuse_fin) {
+    // static shell: this launch also finalizes the iteration; on slabs the two sums first go
+    // through the peer-memory all-reduce (p.p2p), single GPU: p.p2p.peers == nullptr
     if (threadIdx.x == 0) st->sum[R_SHELL] = 0.0;
-    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_CG_FIN});
+    P2PDev pp = p.p2p;
+    pp.slot0 = R_A;
+    pp.count = 2;
+    grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_CG_FIN, p.accum, pp});
   } else {
     grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_NONE, p.accum});
   }
@@ -805,7 +817,7 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
   const int zc = (int)blockIdx.z;
-  const int x0 = (zc < p.chunk_split ? p.chunk0 + zc : p.chunk_hi0 + (zc - p.chunk_split)) * p.cx;
+  const int x0 = tile_chunk(p, zc) * p.cx;
   const int x1 = min(x0 + p.cx, g.n[0]);
   const bool actx = g.act[0] != 0;
   if (threadIdx.x == 0) {
@@ -846,7 +858,30 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, p.dist ? ST_NONE : ST_CG_DAD});
+  {
+    P2PDev pp = p.p2p;  // slabs: d.Ad summed over the ranks right here when the peer mailboxes exist
+    pp.slot0 = R_A;
+    pp.count = 1;
+    const int stage = (p.dist && pp.peers == nullptr) ? ST_NONE : ST_CG_DAD;
+    grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, stage, 0, pp});
+  }
+}
+
+// Communication-stream side of the single-launch overlap: wait until every boundary CTA of the phase B
+// that is running on the main stream has written its planes.  One thread; returns at once after `done`.
+static __global__ void k_wait_halo(SolverState* st, unsigned int nboundary) {
+  if (st->done) return;
+  const unsigned int target = st->halo_target + nboundary;
+  st->halo_target = target;
+  while (*(volatile unsigned int*)&st->halo_count < target) {
+  }
+  __threadfence();
+}
+
+// number of boundary CTAs of a sub == 3 launch
+inline unsigned int tma_boundary_ctas(const TmaPlan& tp, const GridDev& g) {
+  const int c_lo = g.olo0 / tp.tile.cx, c_hi = (g.ohi0 - 1) / tp.tile.cx;
+  return (unsigned int)((c_lo + 1 + tp.tile.chunks - c_hi) * tp.tile.tiles_y * tp.tile.tiles_z);
 }
 
 // chunks left to the interior sub-launch when phase B is split around the halo exchange
@@ -899,14 +934,19 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
   // olo0 and from the one holding plane ohi0-1 on
   const int c_lo = g.olo0 / tile.cx, c_hi = (g.ohi0 - 1) / tile.cx;
   if (sub == 1) {
-    tile.chunk0 = 0;
-    tile.chunk_split = c_lo + 1;
-    tile.chunk_hi0 = c_hi;
-    nz = (c_lo + 1) + (tile.chunks - c_hi);
+    tile.b_lo = c_lo + 1;
+    tile.b_hi = tile.chunks - c_hi;
+    nz = tile.b_lo + tile.b_hi;
+    tile.fuse_fin = 0;  // the interior sub-launch adds its sums and finalizes
   } else if (sub == 2) {  // interior chunks, sums added to the boundary launch's
     tile.chunk0 = c_lo + 1;
     tile.accum = 1;
     nz = c_hi - c_lo - 1;
+  } else if (sub == 3) {  // ONE launch, boundary chunks first, each of their CTAs signals completion
+    tile.b_lo = c_lo + 1;
+    tile.b_hi = tile.chunks - c_hi;
+    tile.chunk0 = tile.b_lo;
+    tile.signal_halo = 1;
   }
   dim3 grid(tile.tiles_z, tile.tiles_y, nz);
   k_cg_phaseB_tma<T, K><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,

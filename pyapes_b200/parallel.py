@@ -111,7 +111,37 @@ def get_comm(device) -> C.c_void_p:
     torch.cuda.set_device(device)
     N.check(lib.pa_comm_create(idbuf, rank, world, C.byref(comm)))
     _COMM["comm"] = comm
+    _attach_peer_mailboxes(lib, rank, world, device, on_gpu)
     return comm
+
+
+def _attach_peer_mailboxes(lib, rank: int, world: int, device, on_gpu: bool) -> None:
+    """Exchange the CUDA IPC handles of the per-rank mailboxes so that the CG kernels can all-reduce
+    their dot products over NVLink peer memory inside the kernel (csrc/common.cuh p2p_allreduce).
+    Falls back to ncclAllReduce (with a warning) if any rank cannot export or map a mailbox."""
+    import os
+    import warnings
+
+    import torch.distributed as dist
+
+    if world < 2 or os.environ.get("PA_NO_P2P"):
+        return
+    mine = (C.c_ubyte * 64)()
+    ok = lib.pa_p2p_local_handle(mine) == 0
+    t = torch.tensor(list(mine) + [1 if ok else 0], dtype=torch.uint8, device=device if on_gpu else "cpu")
+    allt = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    rows = [bytes(a.cpu().tolist()) for a in allt]
+    good = all(r[64] == 1 for r in rows)
+    if good:
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(r[:64] for r in rows))
+        good = lib.pa_p2p_attach(blob, rank, world) == 0
+    flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=device if on_gpu else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank attached, or nobody uses the mailboxes
+    if int(flag.item()) != 1:
+        lib.pa_p2p_disable()
+        warnings.warn("pyapes_b200: peer mailboxes unavailable, CG scalars go through ncclAllReduce")
+    _COMM["p2p"] = int(flag.item()) == 1
 
 
 def destroy_comm() -> None:
