@@ -567,13 +567,27 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
   const long long nown = (long long)(g.ohi0 - g.olo0) * plane;
   const bool stream_ok = (nown % SV == 0) && (off % SV == 0);
   const long long nvec = nown / SV;
+  // (the choice must be the same on every rank: plane % SV is, stream_ok alone is not -- the owned
+  //  range starts at a different plane on rank 0)
+  const bool p2p_on = dist && pw != nullptr && (plane % SV == 0) && p2p_dev(dist).peers != nullptr;
   auto reduce = [&](int count, int stage) {  // rank-sum of the raw sums, then the scalar stage
-    if (!dist) return;
+    if (!dist || p2p_on) return;
     dist_allreduce(*dist, &w.st->sum[R_A], count, L.s);
     k_finalize<T><<<1, 1, 0, L.s>>>(stage, w.st);
     L.count += 2;
   };
-  const int ST_V = dist ? ST_NONE : ST_BI_V, ST_S = dist ? ST_NONE : ST_BI_S, ST_T = dist ? ST_NONE : ST_BI_T;
+  // slabs with peer mailboxes, TMA + streaming path: every reduction is summed over the ranks inside
+  // the kernel that produces it (common.cuh p2p_allreduce)
+  const P2PDev P = p2p_on ? p2p_dev(dist) : P2PDev{nullptr, 0, 0, 0, 0};
+  const bool p2p = P.peers != nullptr;
+  TilePlan pwr;
+  if (pw) {
+    pwr = *pw;
+    pwr.p2p = P;
+    pw = &pwr;
+  }
+  const bool nccl = dist && !p2p;
+  const int ST_V = nccl ? ST_NONE : ST_BI_V, ST_S = nccl ? ST_NONE : ST_BI_S, ST_T = nccl ? ST_NONE : ST_BI_T;
   // (p = r + beta (p - omega v) of this iteration was produced by the previous iteration's fused
   //  x/r/p update, or by bicgstab_first_p before the loop; 17 words per cell and iteration)
   if (pw)
@@ -590,10 +604,10 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
       dist_halo_exchange<T>(*dist, v, plane, g.olo0, g.ohi0, L.s);
       ++L.count;
     }
-    L.ok &= launch_bi_st_tma<T>(L.s, g, eq, *pw, r, v, r0, t, nullptr, w.st, w.partials, dist ? ST_NONE : ST_BI_ST);
+    L.ok &= launch_bi_st_tma<T>(L.s, g, eq, *pw, r, v, r0, t, nullptr, w.st, w.partials, nccl ? ST_NONE : ST_BI_ST);
     reduce(4, ST_BI_ST);
     k_bi_x_stream<T, true><<<nb, kBlock, 0, L.s>>>(nvec, cur + off, nxt + off, p + off, s + off, t + off, v + off,
-                                                   r + off, w.st, w.partials);
+                                                   r + off, w.st, w.partials, P);
     L.count += 3;
     if (dist) {
       dist_halo_exchange<T>(*dist, r, plane, g.olo0, g.ohi0, L.s);
@@ -626,7 +640,7 @@ static void bicgstab_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq
     ++L.count;
   }
   launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
-  if (dist) {
+  if (nccl) {  // (peer mailboxes: |r|^2 was summed over the ranks inside the x update)
     dist_allreduce(*dist, &w.st->sum[R_A], 1, L.s);
     ++L.count;
   }
@@ -664,13 +678,24 @@ static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, 
                              const T* rhs, const TilePlan* pw = nullptr, const Dist* dist = nullptr) {
   int nb = grid_blocks(g.cells);
   const bool stat = static_shell(nfaces, faces) != 0;
+  const P2PDev P = (dist && pw != nullptr) ? p2p_dev(dist) : P2PDev{nullptr, 0, 0, 0, 0};
+  const bool p2p = P.peers != nullptr;
   if (pw) {
-    // static shell: the sweep also finalizes the iteration (shell part of the norm is 0)
-    const bool fuse = stat && !dist;
-    L.ok &= launch_star_tma<T, PW_JACOBI>(L.s, g, eq, *pw, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
+    // static shell: the sweep also finalizes the iteration (shell part of the norm is 0); on slabs
+    // with peer mailboxes it first sums |dx|^2 over the ranks, inside the kernel
+    const bool fuse = stat && (!dist || p2p);
+    TilePlan pwr = *pw;
+    if (fuse) pwr.p2p = P;
+    L.ok &= launch_star_tma<T, PW_JACOBI>(L.s, g, eq, pwr, cur, rhs, nxt, nullptr, (T)0, w.st, w.partials,
                                           fuse ? ST_JA_FIN : ST_NONE);
     ++L.count;
-    if (fuse) return;
+    if (fuse) {
+      if (dist) {
+        dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
+        ++L.count;
+      }
+      return;
+    }
   } else {
     k_pointwise_update<T, 0><<<nb, kBlock, 0, L.s>>>(g, eq, cur, nxt, rhs, (T)0, w.st, w.partials);
     ++L.count;
@@ -679,13 +704,19 @@ static void jacobi_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, 
     cudaMemsetAsync(&w.st->sum[R_SHELL], 0, sizeof(double), L.s);
   } else {
     launch_bcs<T>(L, g, nfaces, faces, nxt, w.st, dist);
-    launch_shell<T>(L, g, nxt, cur, w.st, w.partials, dist ? ST_NONE : ST_JA_FIN);
+    P2PDev pp = P;  // non-static shell on slabs: the shell norm is the last sum -> reduce all four here
+    pp.slot0 = R_A;
+    pp.count = 4;
+    launch_shell<T>(L, g, nxt, cur, w.st, w.partials, (dist && !p2p) ? ST_NONE : ST_JA_FIN, pp);
   }
   if (dist) {
     dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
-    dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
-    k_finalize<T><<<1, 1, 0, L.s>>>(ST_JA_FIN, w.st);
-    L.count += 3;
+    ++L.count;
+    if (!p2p || stat) {  // (stat && p2p returned above; this is the NCCL path)
+      dist_allreduce(*dist, &w.st->sum[R_A], 4, L.s);
+      k_finalize<T><<<1, 1, 0, L.s>>>(ST_JA_FIN, w.st);
+      L.count += 2;
+    }
   }
 }
 
@@ -953,7 +984,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     dist_halo_exchange<T>(*dist, x_alt, plane, g.olo0, g.ohi0, stream);
     PA_CUDA(cudaStreamSynchronize(stream));
   }
-  if (dist && tmap.tile.p2p.peers != nullptr) g_p2p.epoch = h->epoch - 1ull;
+  if (dist && g_p2p.ready) g_p2p.epoch = h->epoch - 1ull;  // unchanged if no reduction used the mailboxes
   fill_report(rep, h, L.count);
   // iterations completed with an update == number of ping-pong swaps
   int swaps = h->itr;

@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T*
                                                         T* __restrict__ x_new, T* __restrict__ p,
                                                         const T* __restrict__ s, const T* __restrict__ t,
                                                         const T* __restrict__ v, T* __restrict__ r,
-                                                        SolverState* st, double* partials) {
+                                                        SolverState* st, double* partials,
+                                                        P2PDev p2p = P2PDev{nullptr, 0, 0, 0, 0}) {
   typedef typename StreamVec<T>::type V;
   if (st->done) return;
   const T alpha = (T)st->scal[S_ALPHA], omega = (T)st->scal[S_OMEGA], beta = (T)st->scal[S_BETA];
@@ -709,7 +710,9 @@ __global__ void __launch_bounds__(kBlock) k_bi_x_stream(long long nvec, const T*
     }
     reinterpret_cast<V*>(x_new)[i] = xo;
   }
-  grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_NONE});
+  p2p.slot0 = R_A;
+  p2p.count = 1;
+  grid_reduce<1>(acc, partials, gridDim.x, blockIdx.x, &st->ticket[0], StoreSums<T, 1>{st, R_A, ST_NONE, 0, p2p});
 }
 
 // ---------------------------------------------------------------------------------------

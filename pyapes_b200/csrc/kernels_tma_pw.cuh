@@ -403,7 +403,10 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   if (MODE == PW_EULER) return;  // no reductions
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  grid_reduce<3>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 3>{st, R_A, stage});
+  P2PDev pp = p.p2p;  // slabs: the host sets p.p2p when this launch sums over the ranks itself
+  pp.slot0 = R_A;
+  pp.count = 3;
+  grid_reduce<3>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 3>{st, R_A, stage, 0, pp});
 }
 
 // =========================================================================================
@@ -617,7 +620,10 @@ k_bi_st_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CU
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  grid_reduce<4>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 4>{st, R_A, stage});
+  P2PDev pp = p.p2p;
+  pp.slot0 = R_A;
+  pp.count = 4;
+  grid_reduce<4>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 4>{st, R_A, stage, 0, pp});
 }
 
 // ---- host ------------------------------------------------------------------------------------
