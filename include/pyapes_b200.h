@@ -150,7 +150,9 @@ typedef enum {
   PA_RUNNING = 0,
   PA_CONVERGED = 1,   /* loop left through its condition */
   PA_MAXIT = 2,       /* "Maximum iteration reached!" RuntimeWarning (linalg.py:146-150,268-271) */
-  PA_BAD_TOL = 3      /* "Invalid tolerance detected!" RuntimeError (linalg.py:334-336) */
+  PA_BAD_TOL = 3,     /* "Invalid tolerance detected!" RuntimeError (linalg.py:334-336) */
+  PA_PEER_LOST = 4    /* device-side only (multi-GPU): a peer rank never joined a fused all-reduce within
+                         the watchdog time; the entry point returns PA_ERR_NCCL, never this status */
 } pa_solve_status;
 
 typedef struct {

@@ -977,6 +977,10 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (rc != PA_OK) return rc;
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(PA_ERR_CUDA, cudaGetErrorString(le));
+  if (h->status == PA_PEER_LOST) {
+    g_p2p.ready = false;  // the mailboxes are in an unknown state: never use them again
+    return fail(PA_ERR_NCCL, "multi-GPU: a peer rank did not join a fused all-reduce within 60 s (peer-memory watchdog)");
+  }
   if (dist && method == PA_METHOD_BICGSTAB) {
     // the axpy stages only touched owned planes: refresh the ghost planes of both iterates
     const long long plane = (long long)g.n[1] * g.n[2];

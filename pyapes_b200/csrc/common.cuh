@@ -269,7 +269,18 @@ struct P2PDev {
   int slot0, count;                  // which SolverState::sum entries are reduced
 };
 
-__device__ __forceinline__ void p2p_allreduce(const P2PDev& pp, unsigned long long epoch, double* vals) {
+// Watchdog of the flag wait: a peer that never arrives (crashed rank, a rank that left the solve on an
+// error) must not leave this GPU spinning for ever.  After kP2PTimeoutNs the reduction gives up and
+// returns false; the caller latches `done` with status PA_PEER_LOST and the host reports PA_ERR_NCCL.
+constexpr unsigned long long kP2PTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ bool p2p_allreduce(const P2PDev& pp, unsigned long long epoch, double* vals) {
   const int slot = (int)(epoch & 1ull);
   const int off = (slot * 16 + pp.me) * 8;
   for (int p = 0; p < pp.nranks; ++p) {
@@ -282,14 +293,22 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& pp, unsigned long lo
     dst[7] = epoch;
   }
   double tot[4] = {0.0, 0.0, 0.0, 0.0};
+  unsigned long long t0 = 0ull;  // the clock is only read once a wait has lasted a while
   for (int q = 0; q < pp.nranks; ++q) {
     volatile unsigned long long* src = pp.peers[pp.me] + (slot * 16 + q) * 8;
+    unsigned int spins = 0;
     while (src[7] != epoch) {
+      if ((++spins & 0xfffu) == 0u) {
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > kP2PTimeoutNs) return false;
+      }
     }
     __threadfence_system();
     for (int k = 0; k < pp.count; ++k) tot[k] += __longlong_as_double((long long)src[k]);
   }
   for (int k = 0; k < pp.count; ++k) vals[k] = tot[k];
+  return true;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -193,7 +193,11 @@ struct StoreSums {
     if (p2p.peers != nullptr) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int k = 0; k < p2p.count; ++k) v[k] = st->sum[p2p.slot0 + k];
-      p2p_allreduce(p2p, st->epoch, v);
+      if (!p2p_allreduce(p2p, st->epoch, v)) {  // a peer never arrived (watchdog, common.cuh)
+        st->done = 1;
+        st->status = PA_PEER_LOST;
+        return;
+      }
       for (int k = 0; k < p2p.count; ++k) st->sum[p2p.slot0 + k] = v[k];
       st->epoch += 1ull;
     }

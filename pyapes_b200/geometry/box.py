@@ -3,6 +3,8 @@ from __future__ import annotations
 
 from .basis import GeoBounder, Geometry, bound_edge_and_corner
 
+BOX_DIM = [1, 2, 3]  # dimensions a Box may have (box.py:9)
+
 
 class Box(Geometry, metaclass=GeoBounder):
     """`Box([0, 0, 0], [1, 1, 1])` or `Box[0:1, 0:1, 0:1]`; bounds are stored as floats."""

@@ -216,3 +216,32 @@ class Mesh:
             bwd = g - torch.roll(g, 1, idx)
             out.append((fwd.clamp_min(0.0) + bwd.clamp_min(0.0)) / 2)
         return out
+
+
+def get_box_mask(x: list[Tensor], dx: Tensor, obj: dict, mask: Tensor, dim: int) -> Tensor:
+    """Mark the nodes a face description covers (reference: pyapes/mesh/_mesh.py:375-399).
+
+    `obj` is one entry of `Geometry.config`: `x_p` the corner the face starts at, `e_x` its extent
+    per axis.  Along every axis the marked range starts at the node nearest to `x_p` and holds
+    `ceil(e_x / dx) + 1` nodes."""
+    region = []
+    for axis in range(dim):
+        nodes = x[axis]
+        corner = torch.as_tensor(obj["x_p"][axis], dtype=nodes.dtype, device=nodes.device)
+        extent = torch.as_tensor(obj["e_x"][axis], dtype=nodes.dtype, device=nodes.device)
+        first = int(torch.argmin((nodes - corner).abs()))
+        count = int(torch.ceil(extent / dx[axis])) + 1
+        region.append(slice(first, first + count))
+    mask[tuple(region)] = True
+    return mask
+
+
+def boundary_mask(mesh: Mesh) -> tuple[dict, dict]:
+    """`(domain face masks, obstacle masks)` as the reference builds them in `Mesh.__init__`
+    (pyapes/mesh/_mesh.py:321-372).  `Mesh.d_mask` holds the same domain masks lazily; obstacles are
+    rejected by `Mesh`, so the second dictionary is always empty."""
+    faces: dict[str, Tensor] = {}
+    for desc in mesh.domain.config.values():
+        blank = torch.zeros(*mesh.nx, dtype=torch.bool, device=mesh.device)
+        faces[str(desc["face"])] = get_box_mask(mesh.x, mesh.dx, desc, blank, mesh.dim)
+    return faces, {}

@@ -33,6 +33,12 @@ class DiscretizerConfigType(TypedDict, total=False):
     ddt: DdtConfigType
 
 
+# signatures of `OPStype["adjust_rhs"]` (types.py:41-42): `(var) -> Tensor` and, for Div,
+# `(var_j, var_i, config) -> Tensor`
+GEN_RHS = Callable[[Any], Tensor]
+DIV_RHS = Callable[[Any, Any, DiscretizerConfigType], Tensor]
+
+
 class OPStype(TypedDict):
     """One operator of an equation (types.py:44-70).  `A_coeffs` is a compact coefficient
     descriptor (pyapes_b200._lower.StarCoeffs / FieldCoeffs) instead of 15 full-size tensors."""

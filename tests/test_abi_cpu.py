@@ -127,3 +127,39 @@ def test_derivative_containers():
     assert h["zx"] is h.xz
     with pytest.raises(KeyError):
         Hess(rr=x, zz=z)["xx"]
+
+
+def test_mask_helpers_and_burgers_fixture():
+    """Module-level helpers of the reference that user code imports next to `Mesh`
+    (pyapes/mesh/_mesh.py:321-399, pyapes/testing/burgers.py, pyapes/geometry/box.py:9)."""
+    from math import pi
+
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.geometry.box import BOX_DIM
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.mesh._mesh import boundary_mask, get_box_mask
+    from pyapes_b200.testing.burgers import burger_exact_nd
+
+    assert BOX_DIM == [1, 2, 3]
+    for box, spacing in [(Box[0:1], [11]), (Box[0:1, 0:2], [7, 9]), (Box[0:1, 0:1, 0:1], [0.1, 0.1, 0.25])]:
+        mesh = Mesh(box, None, spacing, "cpu", "double")
+        faces, obstacles = boundary_mask(mesh)
+        assert obstacles == {} and list(faces) == list(mesh.d_mask)
+        for name, mask in faces.items():
+            assert mask.dtype == torch.bool and torch.equal(mask, mesh.d_mask[name])
+            assert int(mask.sum()) == mesh.N // mesh.nx[mesh.d_mask_dim(name)]
+    # an interior block: nearest node to the corner, ceil(extent / dx) + 1 nodes per axis
+    mesh = Mesh(Box[0:1, 0:1], None, [11, 11], "cpu", "double")
+    blank = torch.zeros(11, 11, dtype=torch.bool)
+    got = get_box_mask(mesh.x, mesh.dx, {"x_p": [0.2, 0.5], "e_x": [0.25, 0.0], "face": "q"}, blank, 2)
+    want = torch.zeros(11, 11, dtype=torch.bool)
+    want[2:6, 5:6] = True
+    assert torch.equal(got, want)
+    # Burgers: the exact profile is 2*pi-periodic in the two-Gaussian approximation and equals 4 where
+    # phi_x vanishes (x = pi at t = 0)
+    mesh = Mesh(Box[0 : 2 * pi], None, [101], "cpu", "double")
+    u0 = burger_exact_nd(mesh, 0.1, 0.0)
+    assert u0.shape == mesh.X.shape and abs(u0[50].item() - 4.0) < 1e-12
+    assert abs(u0[0].item() - u0[-1].item()) < 1e-12
+    with pytest.raises(NotImplementedError):
+        burger_exact_nd(Mesh(Box[0:1, 0:1], None, [5, 5], "cpu", "double"), 0.1, 0.0)
