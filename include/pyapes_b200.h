@@ -251,9 +251,12 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
 /* --- peer-memory mailboxes for the fused all-reduces (optional; without them the solvers use
  *     ncclAllReduce).  Every rank: pa_p2p_local_handle() -> 64-byte CUDA IPC handle of its mailbox;
  *     the host layer all-gathers the handles; pa_p2p_attach(all handles, rank, nranks) maps the peers
- *     (NVLink peer access).  From then on the slab-decomposed CG sums d.Ad and {r.r, |dx|^2} over the
+ *     (NVLink peer access).  From then on the slab-decomposed solvers sum their dot products over the
  *     ranks INSIDE the kernels that produce them (one thread per rank writes its partial sums into every
- *     peer's mailbox and adds the others' in rank order) and finalizes the scalar stage there. */
+ *     peer's mailbox and adds the others' in rank order) and finalize the scalar stage there: CG
+ *     {d.Ad}, {r.r, |dx|^2}; BiCGSTAB {r0.v}, {|s|^2, t.s, t.t, r0.t}, {|r|^2}; Jacobi {|dx|^2}.
+ *     A peer that does not arrive within 60 s ends the solve with PA_ERR_NCCL (device-side watchdog)
+ *     and disables the mailboxes. */
 int pa_p2p_local_handle(void* out64);
 int pa_p2p_attach(const void* handles, int rank, int nranks);
 int pa_p2p_enabled(void);
