@@ -120,18 +120,54 @@ def host_rhs(n, rank=0, pin=True):
     return rhs.pin_memory() if pin and torch.cuda.is_available() else rhs
 
 
+_CPU_THREADS = None
+
+
+def cpu_threads():
+    """Thread count of the CPU arm: every core this process may run on (torchrun pins
+    OMP_NUM_THREADS=1, so it is set explicitly) -- unless fewer threads are FASTER on this host
+    (a container whose CPU quota is below its visible core count makes the OpenMP team thrash:
+    measured here, 8 visible cores, 30x slower with 8 threads than with 1).  Picked once by timing
+    the oracle's stencil application on a 64^3 sample at {all, 1/2, 1/4, 1} of the visible cores."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    import torch
+
+    from oracle import fd_oracle as O
+
+    try:
+        avail = max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        avail = max(1, os.cpu_count() or 1)
+    n = 64
+    xs, dx = O.make_axes([0, 0, 0], [1, 1, 1], [n] * 3)
+    bcs = [O.FaceBC(f, "dirichlet", 0.0) for f in O.FACES]
+    phi = torch.rand(1, n, n, n, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    eq = O.Equation([O.Term("laplacian", 1.0, 1.0)], dx, xs, bcs).build(phi)
+    best, best_t = avail, float("inf")
+    for thr in sorted({avail, max(1, avail // 2), max(1, avail // 4), 1}, reverse=True):
+        torch.set_num_threads(thr)
+        eq.aop(phi)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            eq.aop(phi)
+        dt = time.perf_counter() - t0
+        if dt < 0.9 * best_t:  # prefer more threads unless fewer are clearly faster
+            best, best_t = thr, dt
+    _CPU_THREADS = best
+    return best
+
+
 def cpu_baseline(n_cpu=256, iters=20):
     """Oracle port of the reference's CPU torch algorithm (roll + full coefficient tensors),
-    all host threads, bounded sample.  Returns (GLUP/s, seconds, threads)."""
+    all usable host threads (cpu_threads), bounded sample.  Returns (GLUP/s, seconds, threads, itr)."""
     import torch
 
     from oracle import fd_oracle as O
 
     torch.set_default_dtype(torch.float64)
-    try:  # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
+    torch.set_num_threads(cpu_threads())
     xs, dx = O.make_axes([0, 0, 0], [1, 1, 1], [n_cpu] * 3)
     bcs = [O.FaceBC(f, "dirichlet", 0.0) for f in O.FACES]
     x0 = torch.zeros(1, n_cpu, n_cpu, n_cpu, dtype=torch.float64)
