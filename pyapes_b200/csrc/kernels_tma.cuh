@@ -458,7 +458,11 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
 // =========================================================================================
 // phase B
 // =========================================================================================
-template <typename T, typename K, bool LEAN>
+// WRAP: the launch has periodic faces on kernel axes 1/2 (TilePlan::wrap).  A template parameter of the
+// KERNEL, so that the edge tiles of non-periodic problems (30 % of the tiles at 512^2 planes) do not carry
+// the wrapped-halo loads, their branches and the registers they pin: as a run-time branch they cost the
+// general path 22 % more instructions and 9 spill reloads per plane, and phase B 7 % at 512^3.
+template <typename T, typename K, bool LEAN, bool WRAP = false>
 __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ x_new, T* __restrict__ r, T alpha,
                                               unsigned char* stages, uint64_t* full, uint64_t* empty,
@@ -528,7 +532,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
           zl[k] = h[k * C::BOXZ - 1];
           zr[k] = h[k * C::BOXZ + VEC];
         }
-        if (!LEAN && p.wrap) {
+        if (WRAP) {
           const T* dg = static_cast<const T*>(p.src0);
           wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return dg[i]; });
         }
@@ -595,7 +599,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
   acc_out[1] = a1;
 }
 
-template <typename T, typename K>
+template <typename T, typename K, bool WRAP>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_r, TilePlan p, GridDev g, OpDev<T> o,
@@ -654,7 +658,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
     if (full_tile && !edge)
       tmaB_consumer<T, K, true>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
     else
-      tmaB_consumer<T, K, false>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+      tmaB_consumer<T, K, false, WRAP>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
   }
   if (p.signal_halo && zc < p.b_lo + p.b_hi) {
     // a boundary chunk: its r planes may leave for the neighbour rank as soon as every such CTA is
@@ -681,7 +685,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
 // =========================================================================================
 // phase A
 // =========================================================================================
-template <typename T, typename K, bool LEAN>
+template <typename T, typename K, bool LEAN, bool WRAP = false>
 __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ d_new, T beta, unsigned char* stages,
                                               uint64_t* full, uint64_t* empty, int y0, int z0, int x0,
@@ -766,7 +770,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
         zl[k] = rp[k * C::BOXZ - 1] + beta * dp[k * C::BOXZ - 1];
         zr[k] = rp[k * C::BOXZ + VEC] + beta * dp[k * C::BOXZ + VEC];
       }
-      if (!LEAN && p.wrap) {
+      if (WRAP) {
         const T* rg = static_cast<const T*>(p.src0);
         const T* dg = static_cast<const T*>(p.src1);
         wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return rg[i] + beta * dg[i]; });
@@ -800,7 +804,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
   acc_out = acc;
 }
 
-template <typename T, typename K>
+template <typename T, typename K, bool WRAP>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_d,
                 TilePlan p, GridDev g, OpDev<T> o, T* __restrict__ d_new, SolverState* st,
@@ -854,7 +858,7 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
     if (full_tile && !edge)
       tmaA_consumer<T, K, true>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
     else
-      tmaA_consumer<T, K, false>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+      tmaA_consumer<T, K, false, WRAP>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
   }
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -890,39 +894,46 @@ inline int tma_interior_chunks(const TmaPlan& tp, const GridDev& g) {
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-template <typename T, typename K>
+template <typename T, typename K, bool WRAP>
 static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* d_new, SolverState* st, double* partials) {
   typedef TmaCfg<T, K> C;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseA_tma<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
+    cudaFuncSetAttribute(k_cg_phaseA_tma<T, K, WRAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
     attr = true;
   }
   dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
   TilePlan tile = tp.tile;
   tile.src0 = tp.r_ptr;
   tile.src1 = tp.d_ptr[parity];
-  k_cg_phaseA_tma<T, K><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tile, g, eq.op[0],
+  k_cg_phaseA_tma<T, K, WRAP><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tile, g, eq.op[0],
                                                            d_new, st, partials);
 }
 
 template <typename T>
 void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                           int parity, T* d_new, SolverState* st, double* partials) {
-  if (tma_flat(g))
-    launch_cg_phaseA_tma_k<T, KFlat>(s, tp, g, eq, parity, d_new, st, partials);
-  else
-    launch_cg_phaseA_tma_k<T, KStd>(s, tp, g, eq, parity, d_new, st, partials);
+  if (tma_flat(g)) {
+    if (tp.tile.wrap)
+      launch_cg_phaseA_tma_k<T, KFlat, true>(s, tp, g, eq, parity, d_new, st, partials);
+    else
+      launch_cg_phaseA_tma_k<T, KFlat, false>(s, tp, g, eq, parity, d_new, st, partials);
+  } else {
+    if (tp.tile.wrap)
+      launch_cg_phaseA_tma_k<T, KStd, true>(s, tp, g, eq, parity, d_new, st, partials);
+    else
+      launch_cg_phaseA_tma_k<T, KStd, false>(s, tp, g, eq, parity, d_new, st, partials);
+  }
 }
 
-template <typename T, typename K>
+template <typename T, typename K, bool WRAP>
 static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* x_new, T* r, SolverState* st, double* partials, int sub) {
   typedef TmaCfg<T, K> C;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
+    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;
   }
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
@@ -949,17 +960,24 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     tile.signal_halo = 1;
   }
   dim3 grid(tile.tiles_z, tile.tiles_y, nz);
-  k_cg_phaseB_tma<T, K><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
+  k_cg_phaseB_tma<T, K, WRAP><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
                                                            g, eq.op[0], x_new, r, st, partials);
 }
 
 template <typename T>
 void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                           int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
-  if (tma_flat(g))
-    launch_cg_phaseB_tma_k<T, KFlat>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-  else
-    launch_cg_phaseB_tma_k<T, KStd>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+  if (tma_flat(g)) {
+    if (tp.tile.wrap)
+      launch_cg_phaseB_tma_k<T, KFlat, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+    else
+      launch_cg_phaseB_tma_k<T, KFlat, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+  } else {
+    if (tp.tile.wrap)
+      launch_cg_phaseB_tma_k<T, KStd, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+    else
+      launch_cg_phaseB_tma_k<T, KStd, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+  }
 }
 
 }  // namespace pa
