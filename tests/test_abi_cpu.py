@@ -163,3 +163,42 @@ def test_mask_helpers_and_burgers_fixture():
     assert abs(u0[0].item() - u0[-1].item()) < 1e-12
     with pytest.raises(NotImplementedError):
         burger_exact_nd(Mesh(Box[0:1, 0:1], None, [5, 5], "cpu", "double"), 0.1, 0.0)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/pyapes_b200.h must compile as C99 (and as C++) on its own, and a C
+    program must link against the library using nothing but that header."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("needs gcc")
+    lib_dir = os.path.join(ROOT, "pyapes_b200", "lib")
+    src = (
+        '#include "pyapes_b200.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "  pa_grid g; pa_report r; r.itr = 0; (void)g;\n"
+        '  const char* e = pa_last_error();\n'
+        '  printf("%d %d\\n", (int)sizeof(pa_grid), (int)(e != 0) + r.itr);\n'
+        "  return 0;\n"
+        "}\n"
+    )
+    with tempfile.TemporaryDirectory() as tmp:
+        c_file = os.path.join(tmp, "use_header.c")
+        with open(c_file, "w") as f:
+            f.write(src)
+        inc = os.path.join(ROOT, "include")
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", c_file],
+                       check=True)
+        subprocess.run([shutil.which("g++") or gcc, "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++",
+                        c_file], check=True)
+        exe = os.path.join(tmp, "use_header")
+        subprocess.run([gcc, "-std=c99", "-I", inc, c_file, "-o", exe, "-L", lib_dir, "-lpyapes_b200",
+                        f"-Wl,-rpath,{lib_dir}"], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+        from pyapes_b200 import _native as N
+
+        assert int(out[0]) == C.sizeof(N.Grid)
