@@ -1,5 +1,6 @@
 // C-ABI entry points + host-side iteration drivers.  See include/pyapes_b200.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -43,6 +44,15 @@ namespace pa {
                                                       SolverState*, double*, int);
 PA_EXTERN(double)
 PA_EXTERN(float)
+#define PA_EXTERN_APPLY(T)                                                                                     \
+  extern template bool launch_star_tma<T, PW_APPLY>(cudaStream_t, const GridDev&, const EqDev<T>&,             \
+                                                    const TilePlan&, const T*, const T*, T*, T*, T,            \
+                                                    SolverState*, double*, int);                               \
+  extern template bool launch_star_grad<T>(cudaStream_t, const GridDev&, const EqDev<T>&, const TilePlan&,     \
+                                           const T*, T*);
+PA_EXTERN_APPLY(double)
+PA_EXTERN_APPLY(float)
+#undef PA_EXTERN_APPLY
 extern template bool launch_bi_st_tma<double>(cudaStream_t, const GridDev&, const EqDev<double>&, const TilePlan&,
                                               const double*, const double*, const double*, double*, double*,
                                               SolverState*, double*, int);
@@ -997,12 +1007,40 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   return PA_OK;
 }
 
+// PA_APPLY_VARIANT=generic forces k_apply / k_grad (A/B runs of the two paths; read per call)
+static bool apply_force_generic() {
+  const char* e = getenv("PA_APPLY_VARIANT");
+  return e != nullptr && strcmp(e, "generic") == 0;
+}
+
+static inline dim3 shell_grid(const GridDev& g) {
+  long long m = 1;
+  for (int ax = 0; ax < 3; ++ax) {
+    int bb = (ax == 0) ? 1 : 0, cc = (ax == 2) ? 1 : 2;
+    long long nc = (long long)g.n[bb] * g.n[cc];
+    if (g.act[ax] && nc > m) m = nc;
+  }
+  long long bx = (m + kBlock - 1) / kBlock;
+  if (bx > kNumSMs * 4) bx = kNumSMs * 4;
+  return dim3((unsigned)bx, 6);
+}
+
+// ops._Aop / FDC().laplacian / .div: constant-coefficient stars go through the TMA star engine
+// (PW_APPLY, 2 words per cell); edge=True adds the shell pass with the one-sided face formulas.
 template <typename T>
 static int apply_impl(const pa_grid* pg, const pa_equation* peq, const T* phi, T* out,
                       cudaStream_t s) {
   GridDev g = make_grid(*pg);
   EqDev<T> eq = make_eq<T>(*peq);
-  k_apply<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, out);
+  if (!apply_force_generic() && apply_eligible<T>(g, *peq)) {
+    TilePlan tile;
+    apply_tile_plan<T>(g, tile);
+    if (!launch_star_tma<T, PW_APPLY>(s, g, eq, tile, phi, nullptr, out, nullptr, (T)0, nullptr, nullptr, ST_NONE))
+      return fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed (TMA tile descriptor)");
+    if (peq->ops[0].edge != 0) k_apply_shell<T, false><<<shell_grid(g), kBlock, 0, s>>>(g, eq, phi, out);
+  } else {
+    k_apply<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq, phi, out);
+  }
   PA_CUDA(cudaGetLastError());
   return PA_OK;
 }
@@ -1060,7 +1098,15 @@ static int grad_impl(const pa_grid* pg, const pa_op* op, const T* phi, T* out, c
   e.nops = 1;
   e.ops[0] = *op;
   EqDev<T> eq = make_eq<T>(e);
-  k_grad<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq.op[0], phi, out);
+  if (!apply_force_generic() && apply_eligible<T>(g, e)) {  // PW_GRAD, 1 + d words per cell
+    TilePlan tile;
+    apply_tile_plan<T>(g, tile);
+    if (!launch_star_grad<T>(s, g, eq, tile, phi, out))
+      return fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed (TMA tile descriptor)");
+    if (op->edge != 0) k_apply_shell<T, true><<<shell_grid(g), kBlock, 0, s>>>(g, eq, phi, out);
+  } else {
+    k_grad<T><<<grid_blocks(g.cells), kBlock, 0, s>>>(g, eq.op[0], phi, out);
+  }
   PA_CUDA(cudaGetLastError());
   return PA_OK;
 }

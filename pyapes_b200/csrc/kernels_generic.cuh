@@ -218,78 +218,124 @@ __device__ __forceinline__ T edge_first(const T* __restrict__ phi, long long idx
   return t;
 }
 
+// the operator sum at one cell incl. the edge=True face formulas
+template <typename T>
+__device__ __forceinline__ T apply_cell(const GridDev& g, const EqDev<T>& eq, const T* __restrict__ phi,
+                                        const Cell& c) {
+  const long long idx = c.idx;
+  T val = eval_equation<T>(g, eq, c, [&](long long j) { return phi[j]; });
+  const OpDev<T>& o = eq.op[0];
+  if (o.edge == 1) {
+    // edge=True Laplacian (fdc.py:223-258): replace by the one-sided second derivative along
+    // the face's axis; axes in order, so the last axis wins on shared edges
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (!g.act[a]) continue;
+      const int i = c.i[a], n = g.n[a];
+      if (i != 0 && i != n - 1) continue;
+      const long long st = stride_of(g, a) * (i == 0 ? 1 : -1);
+      T t = (T)2 * phi[idx];
+      t = t - (T)5 * phi[idx + st];
+      t = t + (T)4 * phi[idx + 2 * st];
+      t = t - phi[idx + 3 * st];
+      val = t / (o.dx[a] * o.dx[a]);
+    }
+  } else if (o.edge == 2) {
+    // edge=True Div on a 1-D mesh (fdc.py:290-348): the only active axis is kernel axis 2
+    const int i = c.i[2], n = g.n[2];
+    if (i == 0) {
+      T t = -edge_first<T>(phi, idx, 1, 1);
+      val = t / o.dx[2] * o.adv_const;
+    } else if (i == n - 1) {
+      T t = edge_first<T>(phi, idx, 1, -1);
+      val = t / o.dx[2] * o.adv_const;
+    }
+  }
+  return val;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_apply(GridDev g, EqDev<T> eq, const T* __restrict__ phi,
                                                   T* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.cells;
        idx += (long long)gridDim.x * blockDim.x) {
     Cell c = decode(g, idx);
-    T val = eval_equation<T>(g, eq, c, [&](long long j) { return phi[j]; });
-    const OpDev<T>& o = eq.op[0];
-    if (o.edge == 1) {
-      // edge=True Laplacian (fdc.py:223-258): replace by the one-sided second derivative along
-      // the face's axis; axes in order, so the last axis wins on shared edges
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (!g.act[a]) continue;
-        const int i = c.i[a], n = g.n[a];
-        if (i != 0 && i != n - 1) continue;
-        const long long st = stride_of(g, a) * (i == 0 ? 1 : -1);
-        T t = (T)2 * phi[idx];
-        t = t - (T)5 * phi[idx + st];
-        t = t + (T)4 * phi[idx + 2 * st];
-        t = t - phi[idx + 3 * st];
-        val = t / (o.dx[a] * o.dx[a]);
-      }
-    } else if (o.edge == 2) {
-      // edge=True Div on a 1-D mesh (fdc.py:290-348): the only active axis is kernel axis 2
-      const int i = c.i[2], n = g.n[2];
-      if (i == 0) {
-        T t = -edge_first<T>(phi, idx, 1, 1);
-        val = t / o.dx[2] * o.adv_const;
-      } else if (i == n - 1) {
-        T t = edge_first<T>(phi, idx, 1, -1);
-        val = t / o.dx[2] * o.adv_const;
-      }
-    }
-    out[idx] = val;
+    out[idx] = apply_cell<T>(g, eq, phi, c);
   }
 }
 
-// explicit gradient: one STAR operator, component per active axis (fdc.py:80-87)
+// explicit gradient at one cell: one STAR operator, component per active axis (fdc.py:80-87)
+template <typename T>
+__device__ __forceinline__ void grad_cell(const GridDev& g, const OpDev<T>& o, const T* __restrict__ phi,
+                                          T* __restrict__ out, const Cell& c) {
+  const long long idx = c.idx;
+  T vc = phi[idx];
+  int comp = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!g.act[a]) continue;
+    long long st = stride_of(g, a);
+    int i = c.i[a], n = g.n[a];
+    T vp = phi[(i + 1 == n) ? idx - (long long)(n - 1) * st : idx + st];
+    T vm = phi[(i == 0) ? idx + (long long)(n - 1) * st : idx - st];
+    int cls = coef_class(g, a, i);
+    const T* ct = o.coef_tab[a] != nullptr ? o.coef_tab[a] + 3 * i : &o.coef[a][cls][0];
+    T s = ct[0] * vp;
+    s = s + ct[1] * vc;
+    s = s + ct[2] * vm;
+    if (o.edge) {  // edge=True Grad (fdc.py:260-288)
+      if (i == 0)
+        s = -edge_first<T>(phi, idx, st, 1) / o.dx[a];
+      else if (i == n - 1)
+        s = edge_first<T>(phi, idx, st, -1) / o.dx[a];
+    }
+    if (o.param_field != nullptr)
+      s = s * o.param_field[idx];
+    else if (o.has_param)
+      s = s * o.param;
+    out[(long long)comp * g.cells + idx] = s;
+    ++comp;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_grad(GridDev g, OpDev<T> o, const T* __restrict__ phi,
                                                  T* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.cells;
        idx += (long long)gridDim.x * blockDim.x) {
     Cell c = decode(g, idx);
-    T vc = phi[idx];
-    int comp = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (!g.act[a]) continue;
-      long long st = stride_of(g, a);
-      int i = c.i[a], n = g.n[a];
-      T vp = phi[(i + 1 == n) ? idx - (long long)(n - 1) * st : idx + st];
-      T vm = phi[(i == 0) ? idx + (long long)(n - 1) * st : idx - st];
-      int cls = coef_class(g, a, i);
-      const T* ct = o.coef_tab[a] != nullptr ? o.coef_tab[a] + 3 * i : &o.coef[a][cls][0];
-      T s = ct[0] * vp;
-      s = s + ct[1] * vc;
-      s = s + ct[2] * vm;
-      if (o.edge) {  // edge=True Grad (fdc.py:260-288)
-        if (i == 0)
-          s = -edge_first<T>(phi, idx, st, 1) / o.dx[a];
-        else if (i == n - 1)
-          s = edge_first<T>(phi, idx, st, -1) / o.dx[a];
-      }
-      if (o.param_field != nullptr)
-        s = s * o.param_field[idx];
-      else if (o.has_param)
-        s = s * o.param;
-      out[(long long)comp * g.cells + idx] = s;
-      ++comp;
-    }
+    grad_cell<T>(g, o, phi, out, c);
+  }
+}
+
+// The outer shell only (every cell with an index 0 or n-1 along an active axis, each once): rewrites the
+// face cells after the TMA main pass when edge=True (one-sided formulas, fdc.py:203-366).  blockIdx.y =
+// face id (axis*2 + side); a cell belongs to the first axis (in order) on whose boundary it lies.
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(kBlock) k_apply_shell(GridDev g, EqDev<T> eq, const T* __restrict__ phi,
+                                                        T* __restrict__ out) {
+  const int face = blockIdx.y, ax = face >> 1, up = face & 1;
+  if (!g.act[ax]) return;
+  if (up && g.n[ax] == 1) return;
+  const int bb = (ax == 0) ? 1 : 0, cc = (ax == 2) ? 1 : 2;
+  const long long ncell = (long long)g.n[bb] * g.n[cc];
+  const int plane = up ? g.n[ax] - 1 : 0;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ncell;
+       k += (long long)gridDim.x * blockDim.x) {
+    int ib = (int)(k / g.n[cc]), ic = (int)(k - (long long)ib * g.n[cc]);
+    Cell c;
+    c.i[ax] = plane;
+    c.i[bb] = ib;
+    c.i[cc] = ic;
+    c.idx = ((long long)c.i[0] * g.n[1] + c.i[1]) * g.n[2] + c.i[2];
+    bool dup = false;
+    for (int e = 0; e < ax; ++e)
+      if (g.act[e]) dup |= (c.i[e] == 0) | (c.i[e] == g.n[e] - 1);
+    if (dup) continue;
+    if (GRAD)
+      grad_cell<T>(g, eq.op[0], phi, out, c);
+    else
+      out[c.idx] = apply_cell<T>(g, eq, phi, c);
   }
 }
 

@@ -383,28 +383,34 @@ __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, con
 // guarantees whole tiles).  `val(i)` returns the stencilled quantity at linear index i from global
 // memory, computed exactly like the staged one.  A row/column is wrapped when the first/last index of
 // the axis is inside the solver region (mesh/tools.py:7-20 opens the slicer on periodic sides).
-template <typename T, typename K, typename F>
+// ALL: every side wraps, whatever the region -- the explicit operator application, which is defined on
+// every cell with torch.roll's wrap-around (fdc.py:171-200); partial tiles allowed (the row below the
+// last VALID row is handled by the caller, see pw_consumer).
+template <typename T, typename K, bool ALL = false, typename F>
 __device__ __forceinline__ void wrap_halo(const GridDev& g, const ConsCtx<T, K>& c, int x, T (&up)[VecOf<T>::N],
                                           T (&dn)[VecOf<T>::N], T (&zl)[K::RY], T (&zr)[K::RY], F val) {
   constexpr int VEC = VecOf<T>::N;
   const long long base = (long long)x * g.n[1] * g.n[2];
+  if (ALL && c.zg >= g.n[2]) return;  // a column of a partial tile beyond the array
   if (!K::FLAT) {
-    if (c.yb == 0 && g.lo[1] == 0) {
+    if (c.yb == 0 && (ALL || g.lo[1] == 0)) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) up[e] = val(base + (long long)(g.n[1] - 1) * g.n[2] + c.zg + e);
     }
-    if (c.yb + K::RY == g.n[1] && g.hi[1] == g.n[1]) {
+    if (c.yb + K::RY == g.n[1] && (ALL || g.hi[1] == g.n[1])) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) dn[e] = val(base + c.zg + e);
     }
   }
-  if (c.zg == 0 && g.lo[2] == 0) {
+  if (c.zg == 0 && (ALL || g.lo[2] == 0)) {
 #pragma unroll
-    for (int k = 0; k < K::RY; ++k) zl[k] = val(base + (long long)(c.yb + k) * g.n[2] + g.n[2] - 1);
+    for (int k = 0; k < K::RY; ++k)
+      if (!ALL || c.yb + k < g.n[1]) zl[k] = val(base + (long long)(c.yb + k) * g.n[2] + g.n[2] - 1);
   }
-  if (c.zg + VEC == g.n[2] && g.hi[2] == g.n[2]) {
+  if (c.zg + VEC == g.n[2] && (ALL || g.hi[2] == g.n[2])) {
 #pragma unroll
-    for (int k = 0; k < K::RY; ++k) zr[k] = val(base + (long long)(c.yb + k) * g.n[2]);
+    for (int k = 0; k < K::RY; ++k)
+      if (!ALL || c.yb + k < g.n[1]) zr[k] = val(base + (long long)(c.yb + k) * g.n[2]);
   }
 }
 

@@ -16,6 +16,10 @@ enum PwMode {
   PW_EULER = 2,    // out = in + dt*(rhs - A(in))       on the region, in elsewhere
   PW_APPLY_V = 3,  // out = A(in) on the region, 0 elsewhere; sum r0*out
   PW_APPLY_T = 4,  // out = A(in) ...; sums out*in, out*out, r0*out; skipped when finished_flag
+  // the explicit operators (ops._Aop, FDC().laplacian/.div/.grad): defined on EVERY cell with
+  // torch.roll's wrap-around on every axis (fdc.py:171-200), no region, no sums.  R in, W out(s).
+  PW_APPLY = 5,    // out = sum_k sign*param*Op_k(in)                        2 words per cell
+  PW_GRAD = 6,     // out[a] = param * d(in)/dx_a, one array per mesh axis   1 + d words per cell
 };
 
 template <typename T, typename K>
@@ -173,6 +177,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
                                             int y0, int z0, int x0, int x1, double (&acc_out)[3]) {
   typedef PwCfg<T, K> C;
   constexpr int VEC = C::VEC;
+  constexpr bool ALL = (MODE == PW_APPLY || MODE == PW_GRAD);  // every cell, wrap-around on every axis
   ConsCtx<T, K> c;
   cons_setup<T, K>(g, c, y0, z0);
   const bool actx = g.act[0] != 0;
@@ -209,7 +214,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
       load_own(sn, vp);
     }
     const T* h = halo(sc) + c.hoff;
-    const bool xreg = x >= g.lo[0] && x < g.hi[0];
+    const bool xreg = ALL || (x >= g.lo[0] && x < g.hi[0]);
     const bool xown = x >= g.olo0 && x < g.ohi0;
     const int gx = x + g.goff0;
     const bool xshell = actx && (gx == 0 || gx == g.gn0 - 1);
@@ -233,9 +238,65 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
       }
       if (!LEAN && p.wrap) {
         const T* ing = static_cast<const T*>(p.src0);
-        wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return ing[i]; });
+        wrap_halo<T, K, ALL>(g, c, x, up, dn, zl, zr, [&](long long i) { return ing[i]; });
+        if (ALL && !K::FLAT && c.zg < g.n[2]) {
+          // partial tile along axis 1: the row below the last valid row is row 0 (it sits in one of
+          // the thread's own -- invalid, never stored -- rows)
+#pragma unroll
+          for (int k = 0; k + 1 < K::RY; ++k)
+            if (c.yb + k + 1 == g.n[1]) {
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) vc[k + 1][e] = ing[(long long)x * n12 + c.zg + e];
+            }
+        }
       }
       const int clx = coef_class(g, 0, x);
+      if (MODE == PW_GRAD) {
+        // central gradient, one output array per mesh axis (fdc.py:80-87); op order of k_grad
+        const OpDev<T>& o = eq.op[0];
+#pragma unroll
+        for (int k = 0; k < K::RY; ++k) {
+          const int cy = LEAN ? 0 : c.cly[k];
+          T g0[VEC], g1[VEC], g2[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int cz = LEAN ? 0 : c.clz[e];
+            const T v0 = vc[k][e];
+            const T yp = (k == K::RY - 1) ? dn[e] : vc[k + 1 < K::RY ? k + 1 : k][e];
+            const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
+            const T zp = (e == VEC - 1) ? zr[k] : vc[k][e + 1 < VEC ? e + 1 : e];
+            const T zm = (e == 0) ? zl[k] : vc[k][e > 0 ? e - 1 : 0];
+            T s = o.coef[0][clx][0] * vp[k][e];
+            s = s + o.coef[0][clx][1] * v0;
+            s = s + o.coef[0][clx][2] * vm[k][e];
+            if (o.has_param) s = s * o.param;
+            g0[e] = s;
+            if (!K::FLAT) {
+              s = o.coef[1][cy][0] * yp;
+              s = s + o.coef[1][cy][1] * v0;
+              s = s + o.coef[1][cy][2] * ym;
+              if (o.has_param) s = s * o.param;
+              g1[e] = s;
+            }
+            s = o.coef[2][cz][0] * zp;
+            s = s + o.coef[2][cz][1] * v0;
+            s = s + o.coef[2][cz][2] * zm;
+            if (o.has_param) s = s * o.param;
+            g2[e] = s;
+          }
+          T* row = op_ + (long long)k * g.n[2];
+          stg_row<T, K, LEAN>(row, c, k, g0);
+          if (!K::FLAT) {
+            stg_row<T, K, LEAN>(row + g.cells, c, k, g1);
+            stg_row<T, K, LEAN>(row + 2 * g.cells, c, k, g2);
+          } else {
+            stg_row<T, K, LEAN>(row + g.cells, c, k, g2);
+          }
+        }
+        op_ += n12;
+        release(sc);
+        return;
+      }
       star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, vm, vc, vp, up, dn, zl, zr,
                                       [&](int k, int e, T v) { ax[k][e] = v; });
       if (MODE == PW_JACOBI && LEAN) {
@@ -286,6 +347,8 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
             xn = xc + dt * res;
           }
           o[e] = xn;
+        } else if (MODE == PW_APPLY) {
+          o[e] = ax[k][e];  // every valid cell (stg_row masks the others)
         } else {  // PW_APPLY_V / PW_APPLY_T
           const T a = in ? ax[k][e] : (T)0;
           o[e] = a;
@@ -400,7 +463,7 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       pw_consumer<T, K, MODE, false, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                             x1, acc);
   }
-  if (MODE == PW_EULER) return;  // no reductions
+  if (MODE == PW_EULER || MODE == PW_APPLY || MODE == PW_GRAD) return;  // no reductions
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   P2PDev pp = p.p2p;  // slabs: the host sets p.p2p when this launch sums over the ranks itself
@@ -735,6 +798,53 @@ bool launch_bi_st_tma(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, cons
                       const T* v, const T* r0, T* t_out, T* s_out, SolverState* st, double* partials, int stage) {
   return tma_flat(g) ? launch_bi_st_k<T, KFlat>(s, g, eq, tile, r, v, r0, t_out, s_out, st, partials, stage)
                      : launch_bi_st_k<T, KStd>(s, g, eq, tile, r, v, r0, t_out, s_out, st, partials, stage);
+}
+
+// ---- explicit operators on every cell (PW_APPLY / PW_GRAD) ------------------------------------------
+// Constant-coefficient star operators on 2-D / 3-D grids whose contiguous axis is a whole number of
+// 16-byte vectors; everything else (field advection, Tensor coefficient, rz tables, 1-D, odd n2) stays
+// on k_apply / k_grad.  edge=True is NOT a reason to leave: the one-sided face values are written by the
+// shell kernels (kernels_generic.cuh k_apply_shell / k_grad_shell) after the main pass.
+template <typename T>
+inline bool apply_eligible(const GridDev& g, const pa_equation& eq) {
+  constexpr int VEC = VecOf<T>::N;
+  if (eq.nops < 1 || eq.nops > PA_MAX_OPS) return false;
+  for (int k = 0; k < eq.nops; ++k) {
+    const pa_op& o = eq.ops[k];
+    if (o.kind != PA_OP_STAR || o.param_field != nullptr || o.coef_tab[0] || o.coef_tab[1] || o.coef_tab[2])
+      return false;
+  }
+  if (!g.act[2] || (!g.act[1] && !g.act[0])) return false;
+  if (g.n[2] % VEC != 0 || g.n[2] < 2 * VEC) return false;
+  if (g.act[1] && g.n[1] < 4) return false;
+  if (g.act[0] && g.n[0] < 3) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+template <typename T>
+inline void apply_tile_plan(const GridDev& g, TilePlan& p) {
+  pw_tile_plan<T>(g, p);
+  p.wrap = 1;  // edge tiles always fetch the wrapped halo row / column (wrap_halo<ALL>)
+}
+
+template <typename T, typename K>
+static bool launch_star_grad_k(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile_in,
+                               const T* in, T* out) {
+  typedef PwCfg<T, K> C;
+  TilePlan tile = tile_in;
+  tile.src0 = in;
+  CUtensorMap tm_in;
+  if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
+  launch_star_tma_n<T, K, PW_GRAD, 1>(s, tm_in, tm_in, g, eq, tile, false, out, nullptr, (T)0, nullptr, nullptr, 0);
+  return true;
+}
+
+// out[(axis), cell] = param * d(in)/dx_axis for every active mesh axis (eq.op[0] is the Grad star)
+template <typename T>
+bool launch_star_grad(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, const T* in,
+                      T* out) {
+  return tma_flat(g) ? launch_star_grad_k<T, KFlat>(s, g, eq, tile, in, out)
+                     : launch_star_grad_k<T, KStd>(s, g, eq, tile, in, out);
 }
 
 template <typename T, int MODE>

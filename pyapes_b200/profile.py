@@ -49,3 +49,86 @@ def cg_kernel_times(n, iters: int = 20, variant: int = 0, dtype: str = "double",
     return {"phaseA_ms": a, "phaseB_ms": b, "small_ms": c, "iter_ms": tot, "launches_per_iter": launches,
             "tiled": bool(tiled), "path": {2.0: "tma", 1.0: "register-tiled", 0.0: "generic"}[tiled],
             "kernels": names, "share": {"phaseA": a / tot, "phaseB": b / tot, "bc+shell": c / tot}}
+
+
+def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", reps: int = 20, variant: str = "tma",
+                         kinds=None, vals=None, device: str = "cuda") -> dict:
+    """Device time of ONE explicit operator application (`pa_stencil_apply` / `pa_grad_apply` through the C
+    ABI, exactly what `Solver.Aop` / `FDC().laplacian/.grad/.div` call), CUDA events on the launching stream
+    around `reps` back-to-back calls after 3 warm-up calls.  Calls rotate over enough distinct input/output
+    buffer pairs to exceed 2x the 126 MB L2, so every call reads its input from HBM.
+    op: "laplacian" | "grad" | "div_upwind" | "div_central" | "advdiff" (div + laplacian, 2 operators).
+    Algorithmic words per cell: 2 (R phi, W out), Grad 1 + ndim."""
+    import math
+    import os
+
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdc import FDC
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import L_lower_equation
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    shape = list(shape)
+    nd = len(shape)
+    kinds = kinds or ["dirichlet"] * (2 * nd)
+    vals = vals or [0.0] * (2 * nd)
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, device, dtype)
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    x = var()
+    esz = x.element_size()
+    cells = x.numel()
+    ncomp = nd if op == "grad" else 1
+    pair_bytes = cells * esz * (1 + ncomp)
+    nbuf = max(1, min(64, math.ceil(2.2 * 126e6 / pair_bytes)))
+    g = torch.Generator(device=device).manual_seed(7)
+    ins = [torch.rand(x.shape, generator=g, dtype=x.dtype, device=device) - 0.5 for _ in range(nbuf)]
+    outs = [torch.empty((1, ncomp, *shape) if op == "grad" else x.shape, dtype=x.dtype, device=device)
+            for _ in range(nbuf)]
+    code, lib = N.dtype_code(x.dtype), N.lib()
+    grid = L.lower_grid(mesh.nx, var.bcs)
+    stream = N.current_stream(x.device)
+    if op == "grad":
+        coeffs = FDC({"grad": {"edge": False}}).grad.build_A_coeffs(var)
+        popr, keep = L.lower_op(coeffs, nd, x.dtype, dx=mesh._dx, field_device=x.device)
+
+        def call(i):
+            N.check(lib.pa_grad_apply(grid, popr, code, ins[i].data_ptr(), outs[i].data_ptr(), stream))
+    else:
+        fdm = FDM({"div": {"limiter": "none" if op == "div_central" else "upwind", "edge": False}})
+        term = {"laplacian": lambda: fdm.laplacian(1.0, var), "div_upwind": lambda: fdm.div(1.0, var),
+                "div_central": lambda: fdm.div(1.0, var),
+                "advdiff": lambda: fdm.div(1.0, var) - fdm.laplacian(0.1, var)}[op]()
+        eq, keep = L_lower_equation(term.ops, var)
+        term.ops = {}
+
+        def call(i):
+            N.check(lib.pa_stencil_apply(grid, eq, code, ins[i].data_ptr(), outs[i].data_ptr(), stream))
+
+    prev = os.environ.get("PA_APPLY_VARIANT")
+    if variant == "generic":
+        os.environ["PA_APPLY_VARIANT"] = "generic"
+    else:
+        os.environ.pop("PA_APPLY_VARIANT", None)
+    try:
+        for i in range(3):
+            call(i % nbuf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            call(i % nbuf)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        if prev is None:
+            os.environ.pop("PA_APPLY_VARIANT", None)
+        else:
+            os.environ["PA_APPLY_VARIANT"] = prev
+    ms = e0.elapsed_time(e1) / reps
+    words = 1 + ncomp
+    return {"op": op, "shape": shape, "dtype": dtype, "variant": variant, "ms": ms, "reps": reps, "buffers": nbuf,
+            "GLUP/s": cells / (ms * 1e-3) / 1e9, "words_per_cell": words,
+            "GB/s": cells * words * esz / (ms * 1e-3) / 1e9,
+            "l2_policy": f"{nbuf} rotating buffer pairs, {nbuf * pair_bytes / 2**20:.0f} MiB > 2 x L2"}

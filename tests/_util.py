@@ -88,3 +88,53 @@ def product_equation(case, fdm, var, dev):
         else:
             eq = eq - op if sign < 0 else eq + op
     return eq
+
+
+# ---- the explicit operators of the tile fixtures (tests/golden/make_golden_tiles.py) ---------
+def oracle_tile_outputs(case, phi=None):
+    """Every output key of an ops_tiles.pt case, computed by the oracle."""
+    xs, dx = oracle_axes(case)
+    bcs = oracle_bcs(case)
+    phi = case["phi"].clone() if phi is None else phi
+    u = case["u_const"]
+    has_ns = any(k in ("neumann", "symmetry") for _, k, _ in case["bcs"])
+    out = {}
+    out["lap"] = O.Equation([O.Term("laplacian", 1.0, None)], dx, xs, bcs).build(phi).aop(phi)
+    grad = O.apply_grad(O.grad_coeffs(phi, dx, bcs), phi)
+    out["grad"] = grad
+    out["div_upwind_const"] = O.apply_scalar_op(O.div_coeffs(u, phi, dx, bcs, "upwind"), phi)
+    if not has_ns:
+        out["div_central_const"] = O.apply_scalar_op(O.div_coeffs(u, phi, dx, bcs, "none"), phi)
+    e = O.Equation([O.Term("div", 1.0, u, "upwind"), O.Term("laplacian", -1.0, 0.1)], dx, xs, bcs).build(phi)
+    out["advdiff"] = e.aop(phi)
+    out["lap_edge"] = O.edge_laplacian(O.apply_scalar_op(O.laplacian_coeffs(phi, dx, bcs), phi), phi, dx)
+    out["grad_edge"] = O.edge_grad(grad.clone(), phi, dx)
+    return out
+
+
+def product_tile_outputs(case, var):
+    """The same keys through the public API of the product package (-> C ABI -> CUDA)."""
+    import torch as _t
+
+    from pyapes_b200.solver.fdc import FDC
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+
+    u = case["u_const"]
+    has_ns = any(k in ("neumann", "symmetry") for _, k, _ in case["bcs"])
+    out = {}
+    s = Solver(None)
+    s.set_eq(FDM().laplacian(var) == _t.zeros_like(var()))
+    out["lap"] = s.Aop(var)
+    out["grad"] = FDC({"grad": {"edge": False}}).grad(var)
+    out["div_upwind_const"] = FDC({"div": {"limiter": "upwind", "edge": False}}).div(u, var)
+    if not has_ns:
+        out["div_central_const"] = FDC({"div": {"limiter": "none", "edge": False}}).div(u, var)
+    fdm = FDM({"div": {"limiter": "upwind", "edge": False}})
+    s = Solver(None)
+    s.set_eq(fdm.div(u, var) - fdm.laplacian(0.1, var) == _t.zeros_like(var()))
+    out["advdiff"] = s.Aop(var)
+    out["lap_edge"] = FDC({"laplacian": {"edge": True}}).laplacian(var)
+    out["grad_edge"] = FDC({"grad": {"edge": True}}).grad(var)
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+    return out

@@ -13,6 +13,7 @@ OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
 EDGES = U.load("edges.pt")
 RZ = U.load("rz_ops.pt")
+TILES = U.load("ops_tiles.pt")
 
 
 @pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
@@ -95,6 +96,16 @@ def test_edge_fixtures(case):
         assert torch.equal(j, out["jac_" + names[a]])
     for (a, b), h in O.hessian(phi, dx).items():
         assert torch.equal(h, out["hess_" + names[a] + names[b]])
+
+
+@pytest.mark.parametrize("case", TILES, ids=[c["name"] for c in TILES])
+def test_tile_fixtures(case):
+    """Multi-tile shapes of the TMA-tiled explicit operators (tests/golden/make_golden_tiles.py)."""
+    torch.set_default_dtype(U.TDTYPE[case["spec"]["dtype"]])
+    got = U.oracle_tile_outputs(case)
+    assert sorted(got) == sorted(case["out"])
+    for key, ref in case["out"].items():
+        assert torch.equal(got[key], ref), key
 
 
 @pytest.mark.parametrize("case", RZ, ids=[c["name"] for c in RZ])
