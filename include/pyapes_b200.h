@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 #define PA_MAX_OPS 4
 #define PA_MAX_FACES 6
 
@@ -161,6 +161,8 @@ typedef struct {
   double tol;
   int32_t result_in_alt; /* 1: the final iterate is in x_alt and the previous one in x */
   int32_t launches;      /* kernels launched by this call */
+  int32_t swaps;         /* x updates performed (ping-pong swaps); 0: x_alt was never written */
+  int32_t reserved;
 } pa_report;
 
 typedef struct {

@@ -15,6 +15,6 @@ def install_as_pyapes() -> None:
     names = ["", ".backend", ".geometry", ".geometry.basis", ".geometry.box", ".geometry.cylinder",
              ".mesh", ".mesh._mesh", ".mesh.tools", ".variables", ".variables.bcs", ".variables.fields", ".variables.container",
              ".solver", ".solver.tools", ".solver.types", ".solver.fdc", ".solver.fdm", ".solver.linalg",
-             ".solver.ops", ".testing", ".testing.poisson"]
+             ".solver.ops", ".testing", ".testing.poisson", ".testing.burgers", ".runner"]
     for n in names:
         sys.modules["pyapes" + n] = importlib.import_module("pyapes_b200" + n)

@@ -75,11 +75,31 @@ def _face_points(bc, grid) -> tuple[Tensor, Tensor]:
     return g[idx_f], g[idx_1]
 
 
-def face_value(bc, grid, var: Tensor, var_dim: int) -> tuple[float | None, Tensor | None]:
-    """(scalar, per-cell array) form of bc.bc_val (bcs.py:203-213, 240-249)."""
+def _frozen_callable_check(bc, grid, var: Tensor, out) -> None:
+    """The solvers evaluate a callable `bc_val` ONCE per solve and keep the face values fixed; the reference
+    calls it at every BC application with the CURRENT iterate (bcs.py:203-206, 240-241; linalg.py:295-297).
+    The two agree unless the callable reads `var`.  Probe: evaluate it again on a shifted copy of the field;
+    a different answer means it depends on the iterate, which the device-side iteration cannot honour
+    (SURVEY.md 8b fallback rule: raise, never run a silently different computation)."""
+    probe = bc.bc_val(grid, bc.bc_mask, var * 0.5 + 1.0, bc.bc_val_opt)
+    same = (torch.equal(torch.as_tensor(out), torch.as_tensor(probe)) if isinstance(out, Tensor) or isinstance(probe, Tensor)
+            else out == probe)
+    if not same:
+        raise NotImplementedError(
+            f"pyapes_b200: the callable bc_val of face {bc.bc_face!r} depends on the field itself; inside a solver "
+            "the reference re-evaluates it on every iterate, which the device-resident iteration does not do. "
+            "Use a callable of (grid, mask) only, or apply such a BC explicitly with BC.apply between solves."
+        )
+
+
+def face_value(bc, grid, var: Tensor, var_dim: int, frozen: bool = False) -> tuple[float | None, Tensor | None]:
+    """(scalar, per-cell array) form of bc.bc_val (bcs.py:203-213, 240-249).  `frozen`: the caller keeps
+    the values for a whole solve (see _frozen_callable_check)."""
     v = bc.bc_val
     if callable(v):
         out = v(grid, bc.bc_mask, var, bc.bc_val_opt)
+        if frozen:
+            _frozen_callable_check(bc, grid, var, out)
         if not isinstance(out, Tensor):
             return float(out), None
         return (float(out), None) if out.numel() == 1 else (None, out)
@@ -92,7 +112,7 @@ def face_value(bc, grid, var: Tensor, var_dim: int) -> tuple[float | None, Tenso
     return None, None
 
 
-def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int) -> tuple[N.FaceBC, Any]:
+def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int, frozen: bool = False) -> tuple[N.FaceBC, Any]:
     """One pa_face_bc.  Returns the struct and the tensor (if any) that must stay alive."""
     f = N.FaceBC()
     f.axis = kernel_axis(bc.bc_face_dim, nd)
@@ -104,7 +124,7 @@ def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int) -> tuple[N.FaceBC, 
     dt, dev = var.dtype, var.device
     if bc.bc_type == "dirichlet":
         assert bc.bc_val is not None, "BC: bc_val is not specified!"
-        s, arr = face_value(bc, grid, var, var_dim)
+        s, arr = face_value(bc, grid, var, var_dim, frozen)
         if arr is None and s is None:
             raise TypeError("Dirichlet: bc_val must be float, int, callable or list!")
         if arr is not None:
@@ -113,7 +133,7 @@ def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int) -> tuple[N.FaceBC, 
             f.value = s
     elif bc.bc_type == "neumann":
         assert bc.bc_val is not None, "BC: bc_val is not specified!"
-        s, arr = face_value(bc, grid, var, var_dim)
+        s, arr = face_value(bc, grid, var, var_dim, frozen)
         if arr is None and s is None:
             raise TypeError("Neumann: bc_val must be float, int, callable or list!")
         xf, x1 = _face_points(bc, grid)
@@ -129,11 +149,12 @@ def lower_face(bc, grid, var: Tensor, var_dim: int, nd: int) -> tuple[N.FaceBC, 
     return f, keep
 
 
-def lower_faces(bcs, grid, var: Tensor, var_dim: int, nd: int):
+def lower_faces(bcs, grid, var: Tensor, var_dim: int, nd: int, frozen: bool = False):
+    """`frozen=True` from the solvers: the face values stay fixed for the whole solve."""
     arr = (N.FaceBC * max(len(bcs), 1))()
     keep = []
     for i, bc in enumerate(bcs):
-        arr[i], k = lower_face(bc, grid, var, var_dim, nd)
+        arr[i], k = lower_face(bc, grid, var, var_dim, nd, frozen)
         keep.append(k)
     return arr, len(bcs), keep
 

@@ -76,6 +76,8 @@ class Report(C.Structure):
         ("tol", C.c_double),
         ("result_in_alt", C.c_int32),
         ("launches", C.c_int32),
+        ("swaps", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -152,7 +154,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        if handle.pa_abi_version() != 1:
+        if handle.pa_abi_version() != 2:
             raise NativeError("pyapes_b200: ABI version mismatch, rebuild the library")
         _lib = handle
     return _lib

@@ -151,8 +151,10 @@ struct Launcher {
 // device scratch of the slab-periodic boundary condition (two planes), grown on demand — never
 // while a stream capture is active (run_solver / euler_impl reserve it before capturing)
 static void* bc_scratch(size_t bytes) {
-  static void* p = nullptr;
-  static size_t cap = 0;
+  static void* p_dev[kMaxDevices] = {};
+  static size_t cap_dev[kMaxDevices] = {};
+  void*& p = p_dev[current_device()];
+  size_t& cap = cap_dev[current_device()];
   if (bytes > cap) {
     if (p) cudaFree(p);
     p = nullptr;
@@ -264,6 +266,7 @@ __global__ void k_state_init(SolverState* st, double tolerance, int max_it, unsi
   st->done = 0;
   st->status = PA_RUNNING;
   st->finished_flag = 0;
+  st->swaps = 0;
 }
 
 // ---- workspace carving -------------------------------------------------------------------
@@ -327,14 +330,23 @@ static void fill_report(pa_report* rep, const SolverState* h, int launches) {
   rep->tol = h->tol;
   rep->result_in_alt = 0;
   rep->launches = launches;
+  rep->swaps = 0;
+  rep->reserved = 0;
+}
+
+static void set_swaps(pa_report* rep, int swaps) {
+  rep->swaps = swaps;
+  rep->result_in_alt = swaps & 1;
 }
 
 // The iteration loop runs on a private non-blocking stream (stream capture is not allowed
 // on the legacy default stream torch hands us); it is ordered after the caller's stream by
 // an event, and the call returns only after that stream has drained (poll_state).
 static int solver_stream(cudaStream_t caller, cudaStream_t* out) {
-  static cudaStream_t s = nullptr;
-  static cudaEvent_t ev = nullptr;
+  static cudaStream_t s_dev[kMaxDevices] = {};
+  static cudaEvent_t ev_dev[kMaxDevices] = {};
+  cudaStream_t& s = s_dev[current_device()];
+  cudaEvent_t& ev = ev_dev[current_device()];
   if (!s) {
     PA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     PA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -351,7 +363,8 @@ struct CommLane {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 static CommLane* comm_lane() {
-  static CommLane lane;
+  static CommLane lane_dev[kMaxDevices];
+  CommLane& lane = lane_dev[current_device()];
   if (!lane.s) {
     int lo = 0, hi = 0;  // highest priority: its few CTAs must not queue behind the compute kernel's
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -867,6 +880,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     rep->tol = 1.0;
     rep->result_in_alt = 0;
     rep->launches = L.count;
+    rep->swaps = 0;
+    rep->reserved = 0;
     return PA_OK;
   }
 
@@ -896,8 +911,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       PA_CUDA(cudaGetLastError());
       if (!hs->done) return fail(PA_ERR_CUDA, "persistent CG kernel returned without latching `done`");
       fill_report(rep, hs, L.count);
-      int swaps = hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0);
-      rep->result_in_alt = swaps & 1;
+      set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
       return PA_OK;
     }
     if (cfg->variant == 3) return fail(PA_ERR_UNSUPPORTED, "cooperative launch is not available on this device");
@@ -982,11 +996,21 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
-  if (dist && nccl_first_error() != ncclSuccess)
+  // a distributed solve that ends on an error leaves the host's epoch behind the mailbox contents (and the
+  // ranks may have left at different reductions): never trust the mailboxes again, ncclAllReduce takes over
+  if (dist && nccl_first_error() != ncclSuccess) {
+    g_p2p.ready = false;
     return fail(PA_ERR_NCCL, std::string("NCCL: ") + nccl_api().GetErrorString(nccl_first_error()));
-  if (rc != PA_OK) return rc;
+  }
+  if (rc != PA_OK) {
+    if (dist) g_p2p.ready = false;
+    return rc;
+  }
   cudaError_t le = cudaGetLastError();
-  if (le != cudaSuccess) return fail(PA_ERR_CUDA, cudaGetErrorString(le));
+  if (le != cudaSuccess) {
+    if (dist) g_p2p.ready = false;
+    return fail(PA_ERR_CUDA, cudaGetErrorString(le));
+  }
   if (h->status == PA_PEER_LOST) {
     g_p2p.ready = false;  // the mailboxes are in an unknown state: never use them again
     return fail(PA_ERR_NCCL, "multi-GPU: a peer rank did not join a fused all-reduce within 60 s (peer-memory watchdog)");
@@ -1000,10 +1024,11 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   }
   if (dist && g_p2p.ready) g_p2p.epoch = h->epoch - 1ull;  // unchanged if no reduction used the mailboxes
   fill_report(rep, h, L.count);
-  // iterations completed with an update == number of ping-pong swaps
-  int swaps = h->itr;
-  if (h->status == PA_BAD_TOL && method != PA_METHOD_BICGSTAB) swaps += 1;  // x was written, itr not bumped
-  rep->result_in_alt = swaps & 1;
+  // ping-pong swaps == x updates performed.  CG / Jacobi bump itr after the update (an invalid tolerance
+  // latches in between: x written, itr not bumped); BiCGSTAB bumps itr at the head of the iteration and can
+  // latch PA_BAD_TOL before the update (linalg.py:233-240), so it counts its updates itself.
+  int swaps = (method == PA_METHOD_BICGSTAB) ? h->swaps : h->itr + (h->status == PA_BAD_TOL ? 1 : 0);
+  set_swaps(rep, swaps);
   return PA_OK;
 }
 
@@ -1068,6 +1093,26 @@ int pa_device_count(void) {
       return fail(PA_ERR_CUDA, "no CUDA device: pyapes_b200 has no CPU path");            \
   } while (0)
 
+// Every entry point runs on the device that OWNS its arrays, whatever the caller's current device is
+// (a Field on cuda:1 in a process whose current device is 0): streams, scratch buffers and function
+// attributes are cached per device ordinal, and the caller's device is restored on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    if (p == nullptr || cudaGetDevice(&prev) != cudaSuccess) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (a.type == cudaMemoryTypeDevice && a.device != prev && cudaSetDevice(a.device) == cudaSuccess) switched = true;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 #define PA_DISPATCH(dtype, CALL)                                                          \
   do {                                                                                    \
     if ((dtype) == PA_F64) {                                                              \
@@ -1083,6 +1128,7 @@ int pa_device_count(void) {
 int pa_stencil_apply(const pa_grid* g, const pa_equation* eq, int dtype, const void* phi,
                      void* out, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq))) return rc;
   if (!phi || !out || phi == out) return fail(PA_ERR_ARG, "phi/out null or aliased");
@@ -1115,6 +1161,7 @@ extern "C" {
 int pa_grad_apply(const pa_grid* g, const pa_op* op, int dtype, const void* phi, void* out,
                   void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g))) return rc;
   if (!op || op->kind != PA_OP_STAR) return fail(PA_ERR_ARG, "grad needs a PA_OP_STAR operator");
@@ -1137,6 +1184,7 @@ extern "C" {
 int pa_bc_apply(const pa_grid* g, int nfaces, const pa_face_bc* faces, int dtype, void* phi,
                 void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!phi) return fail(PA_ERR_ARG, "phi is null");
@@ -1179,6 +1227,7 @@ int pa_cg_solve(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_fa
                 int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg,
                 void* ws, size_t ws_bytes_, pa_report* report, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_CG, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
@@ -1221,6 +1270,7 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
                      size_t ws_bytes_, void* comm, int rank, int nranks, pa_report* report,
                      void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
@@ -1286,6 +1336,7 @@ int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nface
                   int dtype, void* x, void* x_alt, const void* rhs, const pa_solver_cfg* cfg, void* ws,
                   size_t ws_bytes_, void* comm, int rank, int nranks, pa_report* report, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   if (method != PA_METHOD_CG && method != PA_METHOD_BICGSTAB && method != PA_METHOD_JACOBI)
@@ -1301,6 +1352,7 @@ int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_
                   int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
                   size_t ws_bytes_, double* out_ms, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!x || !x_alt || !rhs || !ws || !out_ms || iters < 1) return fail(PA_ERR_ARG, "bad argument");
@@ -1313,6 +1365,7 @@ int pa_bicgstab_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
                       const void* rhs, const pa_solver_cfg* cfg, void* ws, size_t ws_bytes_,
                       pa_report* report, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_BICGSTAB, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
@@ -1325,6 +1378,7 @@ int pa_jacobi_solve(const pa_grid* g, const pa_equation* eq, int nfaces,
                     const pa_solver_cfg* cfg, void* ws, size_t ws_bytes_, pa_report* report,
                     void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   int rc = check_solver_args(g, eq, nfaces, faces, x, x_alt, rhs, cfg, ws, report);
   if (rc) return rc;
   PA_DISPATCH(dtype, run_solver<T>(PA_METHOD_JACOBI, g, eq, nfaces, faces, (T*)x, (T*)x_alt,
@@ -1437,6 +1491,7 @@ int pa_euler_step(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_
                   int dtype, const void* phi, void* phi_new, const void* rhs, double dt,
                   void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!phi || !phi_new || phi == phi_new) return fail(PA_ERR_ARG, "phi/phi_new null or aliased");
@@ -1449,6 +1504,7 @@ int pa_euler_steps(const pa_grid* g, const pa_equation* eq, int nfaces, const pa
                    int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
                    int* result_in_alt, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!phi || !phi_alt || phi == phi_alt || !result_in_alt || nsteps < 0)
@@ -1461,6 +1517,7 @@ int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, con
                         int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
                         int* result_in_alt, void* comm, int rank, int nranks, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
   int rc;
   if ((rc = check_grid(g)) || (rc = check_eq(eq)) || (rc = check_faces(nfaces, faces))) return rc;
   if (!phi || !phi_alt || phi == phi_alt || !result_in_alt || nsteps < 0)
@@ -1474,6 +1531,7 @@ int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, con
 
 int pa_axpy(int dtype, long long n, double a, const void* x, const void* y, void* out, void* stream) {
   PA_REQUIRE_DEVICE();
+  DeviceGuard guard(x);
   if (n < 0 || !x || !y || !out) return fail(PA_ERR_ARG, "bad argument");
   PA_DISPATCH(dtype, axpy_impl<T>(n, a, (const T*)x, (const T*)y, (T*)out, (cudaStream_t)stream));
 }

@@ -16,6 +16,14 @@ constexpr int kBlock = 256;          // threads per CTA of the generic kernels
 constexpr int kMaxPartials = 4096;   // upper bound on CTAs taking part in a reduction
 constexpr int kNumSums = 4;          // reduction slots per launch
 constexpr int kNumSMs = 148;         // B200
+constexpr int kMaxDevices = 16;      // per-device caches (streams, scratch, function attributes)
+
+// ordinal of the calling thread's current device, clamped into the per-device cache arrays
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
 
 // ---- grid ------------------------------------------------------------------------------
 struct GridDev {
@@ -247,7 +255,7 @@ struct SolverState {
   int done;
   int status;
   int finished_flag;  // bicgstab's `finished`
-  int pad;
+  int swaps;          // BiCGSTAB: x updates performed (== ping-pong swaps); itr is bumped BEFORE the update there
   unsigned int ticket[8];
   unsigned long long epoch;  // sequence number of the next peer-memory all-reduce (p2p_allreduce)
   unsigned int halo_count;   // boundary CTAs of phase B that have written their planes (monotonic)

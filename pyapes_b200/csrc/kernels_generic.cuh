@@ -130,6 +130,7 @@ __device__ void finalize_stage(int stage, SolverState* st) {
       sc[S_RHO] = sc[S_RHO_NEXT];
     } break;
     case ST_BI_FIN: {
+      st->swaps += 1;  // this stage runs right after the x update of the iteration (never once `done` is set)
       if (st->finished_flag) {  // early exit path: `finished = True; continue`
         st->done = 1;
         st->status = PA_CONVERGED;

@@ -676,7 +676,8 @@ template <typename T, int RY>
 inline void launch_cg_phaseA_ry(cudaStream_t s, const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
                                 const T* r, const T* d_old, T* d_new, SolverState* st, double* partials) {
   typedef TileCfg<T, RY> C;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_cg_phaseA<T, RY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr = true;
@@ -690,7 +691,8 @@ inline void launch_cg_phaseB_ry(cudaStream_t s, const TilePlan& p, const GridDev
                                 const T* x_old, T* x_new, const T* d, T* r, SolverState* st,
                                 double* partials) {
   typedef TileCfg<T, RY> C;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_cg_phaseB<T, RY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr = true;

@@ -893,7 +893,20 @@ static __global__ void k_wait_halo(SolverState* st, unsigned int nboundary) {
   if (st->done) return;
   const unsigned int target = st->halo_target + nboundary;
   st->halo_target = target;
+  // watchdog like p2p_allreduce's: the count only advances if phase B really runs next to this kernel (CUDA
+  // does not promise that for independent graph branches) -- never spin for ever
+  unsigned int spins = 0;
+  unsigned long long t0 = 0ull;
   while (*(volatile unsigned int*)&st->halo_count < target) {
+    if ((++spins & 0xfffu) == 0u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > kP2PTimeoutNs) {
+        st->done = 1;
+        st->status = PA_PEER_LOST;
+        return;
+      }
+    }
   }
   __threadfence();
 }
@@ -914,7 +927,8 @@ template <typename T, typename K, bool WRAP, bool UNI>
 static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* d_new, SolverState* st, double* partials) {
   typedef TmaCfg<T, K> C;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_cg_phaseA_tma<T, K, WRAP, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
     attr = true;
@@ -949,7 +963,8 @@ template <typename T, typename K, bool WRAP, bool UNI>
 static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* x_new, T* r, SolverState* st, double* partials, int sub) {
   typedef TmaCfg<T, K> C;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;

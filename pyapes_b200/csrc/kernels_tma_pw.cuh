@@ -22,11 +22,18 @@ enum PwMode {
   PW_GRAD = 6,     // out[a] = param * d(in)/dx_a, one array per mesh axis   1 + d words per cell
 };
 
-template <typename T, typename K>
+// MODE decides the pipeline: the explicit operators (PW_APPLY / PW_GRAD) stream ONE input and nothing
+// else, so a stage is only the halo tile (9.8 KB) and 2 planes in flight per CTA (S = 4) are not enough
+// bytes in flight to cover the DRAM latency (ncu, 512^3 Laplacian: 53 % of the stall samples were
+// consumers waiting on `full`); they take S = 8.
+template <typename T, typename K, int MODE = 0>
 struct PwCfg : TmaCfg<T, K> {
   typedef TmaCfg<T, K> B;
-  static constexpr int STAGE = B::HALO_SLOT + B::OWN_SLOT;  // in halo, aux own
-  static constexpr size_t SMEM = (size_t)B::S * STAGE + B::BAR_BYTES + 128;
+  static constexpr bool NO_AUX = (MODE == PW_APPLY || MODE == PW_GRAD);
+  static constexpr int S = NO_AUX ? 8 : B::S;
+  static constexpr int STAGE = B::HALO_SLOT + (NO_AUX ? 0 : B::OWN_SLOT);  // in halo, aux own
+  static constexpr int BAR_BYTES = 2 * S * 8;
+  static constexpr size_t SMEM = (size_t)S * STAGE + BAR_BYTES + 128;
 };
 
 struct PwPlan {
@@ -175,7 +182,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
                                             T* __restrict__ out, T* __restrict__ out2, T dt, bool has_aux,
                                             unsigned char* stages, uint64_t* full, uint64_t* empty,
                                             int y0, int z0, int x0, int x1, double (&acc_out)[3]) {
-  typedef PwCfg<T, K> C;
+  typedef PwCfg<T, K, MODE> C;
   constexpr int VEC = C::VEC;
   constexpr bool ALL = (MODE == PW_APPLY || MODE == PW_GRAD);  // every cell, wrap-around on every axis
   ConsCtx<T, K> c;
@@ -308,7 +315,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
 #pragma unroll
     for (int k = 0; k < K::RY; ++k) {
       T av[VEC], o[VEC];
-      if (has_aux) {
+      if (!C::NO_AUX && has_aux) {
         lds_vec<T>(aux(sc) + c.ooff + k * C::OBOXZ, av);
       } else {
 #pragma unroll
@@ -407,11 +414,11 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
 }
 
 template <typename T, typename K, int MODE, int NOPS>
-__global__ void __launch_bounds__(PwCfg<T, K>::THREADS, 2)
+__global__ void __launch_bounds__(PwCfg<T, K, MODE>::THREADS, 2)
 k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_aux,
            TilePlan p, GridDev g, EqDev<T> eq, T* __restrict__ out, T* __restrict__ out2, T dt,
            int has_aux, SolverState* st, double* partials, int stage) {
-  typedef PwCfg<T, K> C;
+  typedef PwCfg<T, K, MODE> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st != nullptr && st->done) return;
   if (MODE == PW_APPLY_T && st->finished_flag) return;
@@ -442,7 +449,7 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
         const int pl = x0 - 1 + i;
         const int s = i & (C::S - 1);
         if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
-        const bool inner = has_aux && (pl >= x0 && pl < x1);
+        const bool inner = !C::NO_AUX && has_aux && (pl >= x0 && pl < x1);
         mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? C::OWN_BYTES : 0)));
         unsigned char* sb = stages + (size_t)s * C::STAGE;
         const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
@@ -725,8 +732,9 @@ template <typename T, typename K, int MODE, int NOPS>
 static void launch_star_tma_n(cudaStream_t s, const CUtensorMap& tm_in, const CUtensorMap& tm_aux,
                               const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, bool has_aux, T* out,
                               T* out2, T dt, SolverState* st, double* partials, int stage) {
-  typedef PwCfg<T, K> C;
-  static bool attr = false;
+  typedef PwCfg<T, K, MODE> C;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_star_tma<T, K, MODE, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr = true;
@@ -761,7 +769,8 @@ static void launch_bi_st_n(cudaStream_t s, const CUtensorMap& tm_r, const CUtens
                            const GridDev& g, const EqDev<T>& eq, const TilePlan& tile, T* t_out, T* s_out,
                            SolverState* st, double* partials, int stage) {
   typedef Pw2Cfg<T, K> C;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(k_bi_st_tma<T, K, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr = true;

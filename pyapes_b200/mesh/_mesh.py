@@ -70,9 +70,16 @@ class Mesh:
         domain: Geometry,
         obstacle: Optional[list[Geometry]],
         spacing: list[int] | list[float] = [],
-        device: str = "cpu",
+        device: str | None = None,
         dtype: str | int = "double",
     ):
+        # The reference's default is "cpu" (mesh/_mesh.py:29).  This package computes on CUDA only, so a
+        # script written for the reference's default can be pointed at the GPU without editing it:
+        # PYAPES_B200_DEFAULT_DEVICE=cuda replaces the DEFAULT (an explicit device= always wins).
+        if device is None:
+            import os
+
+            device = os.environ.get("PYAPES_B200_DEFAULT_DEVICE", "cpu")
         # "cuda:N" is accepted as well (one process per GPU in the slab-decomposed runs)
         assert device.split(":")[0] in TORCH_DEVICE, "Mesh: device only accept cpu or cuda"
         self.device = TorchDevice(device).device

@@ -132,3 +132,107 @@ def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", re
             "GLUP/s": cells / (ms * 1e-3) / 1e9, "words_per_cell": words,
             "GB/s": cells * words * esz / (ms * 1e-3) / 1e9,
             "l2_policy": f"{nbuf} rotating buffer pairs, {nbuf * pair_bytes / 2**20:.0f} MiB > 2 x L2"}
+
+
+# ---------------------------------------------------------------------------------------------
+# The other BASELINE.json configs as timed runs (bench.py `secondary`, tools/bench_configs.py)
+# ---------------------------------------------------------------------------------------------
+MIXED_BCS = (["periodic", "periodic", "neumann", "symmetry", "dirichlet", "dirichlet"], [None, None, 0.5, None, 0.0, 0.0])
+
+
+def _event_time(fn, reps: int = 1) -> float:
+    """Device ms of `reps` calls of fn after one warm-up call (CUDA events, current stream)."""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dtype: str = "double", variant: int = 0,
+                      device: str = "cuda", reps: int = 1) -> dict:
+    """Fixed-count solve (tol 1e-300) of the Poisson problem through the public API; GLUP/s = cells x
+    iterations / device time of solver.solve().  words per LUP: SURVEY.md §8d (CG 8, BiCGSTAB 17 canonical,
+    Jacobi 3)."""
+    import warnings
+
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    shape = list(shape)
+    nd = len(shape)
+    kinds = kinds or ["dirichlet"] * (2 * nd)
+    vals = vals or [0.0] * (2 * nd)
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, device, dtype)
+    tdt = torch.float64 if dtype == "double" else torch.float32
+    g = torch.Generator().manual_seed(1234)
+    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64).to(tdt).to(device)
+    work = rhs.clone()
+    max_it = iters - 1 if method in ("cg", "jacobi") else iters
+    launches = [0]
+
+    def run():
+        work.copy_(rhs)  # set_eq adds the Neumann adjustment in place
+        var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+        s = Solver({"fdm": {"method": method, "tol": 1e-300, "max_it": max_it, "report": False, "variant": variant,
+                            "check_every": iters + (iters & 1)}})
+        s.set_eq(FDM().laplacian(1.0, var) == work)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rep = s.solve()
+        assert rep["itr"] == iters, rep
+        launches[0] = getattr(var, "_last_launches", 0)
+
+    ms = _event_time(run, reps)
+    torch.set_default_dtype(torch.float64)
+    cells = 1
+    for v in shape:
+        cells *= v
+    words = {"cg": 8, "bicgstab": 17, "jacobi": 3}[method]
+    esz = 8 if dtype == "double" else 4
+    glups = cells * iters / (ms * 1e-3) / 1e9
+    return {"shape": shape, "method": method, "dtype": dtype, "iters": iters, "ms": ms, "GLUP/s": glups,
+            "words_per_lup": words, "GB/s": glups * words * esz, "launches": launches[0]}
+
+
+def euler_throughput(shape, limiter: str, steps: int, dtype: str = "double", device: str = "cuda") -> dict:
+    """Config 3: explicit Euler steps of the advection-diffusion equation ddt + div(u phi) - nu lap(phi) = 0,
+    u = 1, nu = 0.1, Dirichlet 0, phi0 = rand(seed 1234); 2 words per LUP (R phi, W phi_new)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import homogeneous_bcs
+
+    shape = list(shape)
+    nd = len(shape)
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, device, dtype)
+    var = Field("c", 1, mesh, {"domain": homogeneous_bcs(nd, 0.0, "dirichlet"), "obstacle": None})
+    g = torch.Generator().manual_seed(1234)
+    var.set_var_tensor(torch.rand(1, *shape, generator=g, dtype=torch.float64).to(var().dtype).to(device))
+    nu, u = 0.1, 1.0
+    # SURVEY §8d's dt = 0.2 dx^2/nu is beyond the explicit diffusion limit dx^2/(2 nd nu) in 3-D; half
+    # the limit keeps a long run finite
+    var.set_time(0.5 * min(mesh._dx) ** 2 / (2 * nd * nu), 0.0)
+    fdm = FDM({"div": {"limiter": limiter, "edge": False}})
+    s = Solver({"fdm": {"method": "euler", "tol": 0.0, "max_it": 0, "report": False, "n_steps": steps}})
+    s.set_eq(fdm.ddt(var) + fdm.div(u, var) - fdm.laplacian(nu, var) == 0.0)
+    ms = _event_time(lambda: s.solve(), 1)
+    torch.set_default_dtype(torch.float64)
+    cells = 1
+    for v in shape:
+        cells *= v
+    esz = 8 if dtype == "double" else 4
+    glups = cells * steps / (ms * 1e-3) / 1e9
+    assert bool(torch.isfinite(var()).all())
+    return {"shape": shape, "method": f"euler/{limiter}", "dtype": dtype, "iters": steps, "ms": ms, "GLUP/s": glups,
+            "words_per_lup": 2, "GB/s": glups * 2 * esz}

@@ -69,7 +69,7 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     code = N.dtype_code(x.dtype)
     slab = getattr(mesh, "slab", None)
     grid = L.lower_grid(mesh.nx, var.bcs, slab)
-    faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd)
+    faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd, frozen=True)
     eq, keep_e = L_lower_equation(eqs, var, implicit_ddt)
     lib = N.lib()
     ws_bytes = lib.pa_solver_workspace_bytes(grid, code, N.METHOD[method])
@@ -94,7 +94,7 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
                                                N.current_stream(x.device)))
     del keep_f, keep_e, ws
     var._last_launches = rep.launches
-    if rep.itr > 0 or rep.status == N.BAD_TOL:
+    if rep.swaps > 0:  # (0: the iterate was never updated, x_alt is unwritten scratch)
         if rep.result_in_alt:
             var.VAR, var.VARo = x_alt, x
         else:
@@ -143,7 +143,7 @@ def euler_explicit(var: Field, rhs: Tensor | None, eqs, config: FDMSolverConfig,
     code = N.dtype_code(x.dtype)
     slab = getattr(mesh, "slab", None)
     grid = L.lower_grid(mesh.nx, var.bcs, slab)
-    faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd)
+    faces, nfaces, keep_f = L.lower_faces(var.bcs, mesh.grid, x, 0, nd, frozen=True)
     eq, keep_e = L_lower_equation(eqs, var)
     dt = float(eqs[0]["param"][0])
     n_steps = int(config.get("n_steps", 1))

@@ -1,0 +1,19 @@
+"""Callable boundary values shared by the fixture generator (run against the real reference) and
+the GPU tests (run against pyapes_b200): signature `(grid, mask, var, opt)` (bcs.py:32,203-205)."""
+import torch
+
+
+def neumann_cos(grid, mask, *_):
+    return 0.3 * torch.cos(2.0 * grid[1][mask])
+
+
+def dirichlet_sin(grid, mask, *_):
+    return torch.sin(3.0 * grid[1][mask]) + grid[0][mask]
+
+
+def dirichlet_of_var(grid, mask, var, *_):
+    """Depends on the field itself: the reference re-evaluates it at every BC application."""
+    return 0.5 * var[0][mask] + 1.0
+
+
+CALLABLES = {"neumann_cos": neumann_cos, "dirichlet_sin": dirichlet_sin, "dirichlet_of_var": dirichlet_of_var}

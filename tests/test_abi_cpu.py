@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/pyapes_b200.h but not exported"
         assert name in N.SYMBOLS, f"{name} has no ctypes prototype in pyapes_b200/_native.py"
-    assert lib.pa_abi_version() == 1
+    assert lib.pa_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
@@ -39,7 +39,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(N.Grid) == 60
     assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8 + 4 + 4 + 8 + 24
     assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
-    assert C.sizeof(N.Report) == 24 and C.sizeof(N.SolverCfg) == 24
+    assert C.sizeof(N.Report) == 32 and C.sizeof(N.SolverCfg) == 24
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

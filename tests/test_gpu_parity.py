@@ -230,8 +230,18 @@ def test_solver_fixtures(case, variant):
     ref = case["report"]
     sol = var().cpu()
     if f32:
+        # fp32: the dot products are accumulated in fp64 here and in fp32 (torch CPU order) in the reference, so
+        # the count may move a little; the final tolerance and the solution must still be the reference's
         assert abs(rep["itr"] - ref["itr"]) <= max(3, ref["itr"] // 10), (rep, ref)
         assert rep["converge"] == ref["converge"]
+        if ref["converge"]:
+            assert rep["tol"] <= case["tol"], (rep, ref)
+        if rep["itr"] == ref["itr"] and case["method"] == "cg":
+            assert abs(rep["tol"] - ref["tol"]) <= 0.05 * ref["tol"] + 1e-7, (rep, ref)
+        smax = case["solution"].abs().max().item() + 1e-30
+        dsol = (sol - case["solution"]).abs().max().item()
+        print(f"fp32 {case['name']} v{variant}: itr {rep['itr']}/{ref['itr']} tol {rep['tol']:.4e}/{ref['tol']:.4e} dsol/smax {dsol / smax:.2e}")
+        assert dsol <= 1e-4 * smax, (dsol, smax, rep, ref)
         return
     maxit_warn = [x for x in w if issubclass(x.category, RuntimeWarning) and "Maximum iteration" in str(x.message)]
     scale = case["sol_abs_sum"] / sol.numel() + 1e-300
