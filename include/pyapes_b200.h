@@ -262,6 +262,14 @@ int pa_cg_solve_dist(const pa_grid* g, const pa_equation* eq, int nfaces, const 
 int pa_p2p_local_handle(void* out64);
 int pa_p2p_attach(const void* handles, int rank, int nranks);
 int pa_p2p_enabled(void);
+/* --- halo exchange over peer memory (CG on slabs): the IPC allocation behind pa_p2p_local_handle also holds a
+ *     landing zone of 2 slots x 2 sides x cap bytes (cap: PA_HALO_MIB MiB, default 8) into which the neighbours'
+ *     phase-B kernels store their boundary planes of r directly (NVLink stores + one flag word per side), so the
+ *     CG loop contains no NCCL call.  pa_p2p_halo_cap() = this rank's bytes per landing plane (0: none);
+ *     every rank must use the same value: the host layer takes the minimum over the ranks and calls
+ *     pa_p2p_set_halo_cap(min).  A plane larger than the cap keeps the ncclSend/ncclRecv exchange. */
+long long pa_p2p_halo_cap(void);
+int pa_p2p_set_halo_cap(long long bytes);
 int pa_p2p_disable(void); /* every rank must agree: the host layer disables all if one rank failed to attach */
 
 /* --- any of the three solvers on a slab (method = PA_METHOD_*); pa_cg_solve_dist is the CG case.

@@ -112,6 +112,8 @@ SYMBOLS = {
     "pa_p2p_local_handle": (C.c_int, [_P]),
     "pa_p2p_attach": (C.c_int, [_P, C.c_int, C.c_int]),
     "pa_p2p_enabled": (C.c_int, []),
+    "pa_p2p_halo_cap": (C.c_longlong, []),
+    "pa_p2p_set_halo_cap": (C.c_int, [C.c_longlong]),
     "pa_p2p_disable": (C.c_int, []),
     "pa_solve_dist": (C.c_int, [C.c_int, C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                 _P, _P, _P, C.POINTER(SolverCfg), _P, C.c_size_t, _P, C.c_int, C.c_int,

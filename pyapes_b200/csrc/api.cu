@@ -254,6 +254,7 @@ __global__ void k_state_init(SolverState* st, double tolerance, int max_it, unsi
   st->epoch = epoch;
   st->halo_count = 0u;
   st->halo_target = 0u;
+  st->halo_cnt[0] = st->halo_cnt[1] = 0u;
   for (int i = 0; i < 8; ++i) {
     st->sum[i] = 0.0;
     st->scal[i] = 0.0;
@@ -380,14 +381,29 @@ static CommLane* comm_lane() {
 // far; it is identical on every rank because all ranks run the same solves with bitwise identical
 // scalars (and therefore the same iteration counts).
 struct P2PCtx {
-  unsigned long long* local = nullptr;       // this rank's mailbox (device memory, exported by IPC)
+  unsigned long long* local = nullptr;       // this rank's IPC allocation: mailbox | halo flags | landing zone
   unsigned long long** peers_dev = nullptr;  // device array [nranks] of mapped mailboxes
+  char* peer_base[16] = {};                  // the same mappings, host side (halo landing zones of the peers)
   int rank = 0, nranks = 0;
   unsigned long long epoch = 0;
   bool ready = false;
+  size_t halo_cap = 0;                       // bytes per landing plane (0: no landing zone)
 };
 static P2PCtx g_p2p;
 constexpr size_t kMailboxBytes = 2 * 16 * 8 * sizeof(unsigned long long);
+// layout of the IPC allocation (common.cuh HaloDev): [0, 2048) mailbox; [2048, 4096) two flag words
+// (lower ghost ready, upper ghost ready); from 4096: landing planes [slot 2][side 2], halo_cap bytes each
+constexpr size_t kHaloFlagOff = kMailboxBytes;
+constexpr size_t kHaloLandOff = 4096;
+static_assert(kMailboxBytes == 2048, "layout");
+
+// bytes per landing plane: PA_HALO_MIB (default 8 MiB = a 1024^2 fp64 plane); 0 disables the landing zone
+static size_t halo_cap_bytes() {
+  const char* e = getenv("PA_HALO_MIB");
+  long mib = e ? atol(e) : 8;
+  if (mib < 0) mib = 0;
+  return (size_t)mib << 20;
+}
 
 static P2PDev p2p_dev(const Dist* dist) {
   P2PDev d{nullptr, 0, 0, 0, 0};
@@ -397,6 +413,38 @@ static P2PDev p2p_dev(const Dist* dist) {
     d.nranks = g_p2p.nranks;
   }
   return d;
+}
+
+// Peer-memory halo exchange of the TMA CG kernels (common.cuh HaloDev): possible when the mailboxes are up,
+// a plane fits a landing slot and axes 1/2 are not periodic (the wrapped halo reads go to the r array itself).
+template <typename T>
+static HaloDev halo_dev(const Dist* dist, const GridDev& g, const TilePlan& tile) {
+  HaloDev h{{nullptr, nullptr}, 0, {nullptr, nullptr}, nullptr, 0, 0, 0};
+  const size_t plane = (size_t)g.n[1] * g.n[2] * sizeof(T);
+  if (!dist || p2p_dev(dist).peers == nullptr || g_p2p.halo_cap == 0 || plane > g_p2p.halo_cap || tile.wrap) return h;
+  if (getenv("PA_NO_PEER_HALO")) return h;
+  const int P = dist->nranks, me = dist->rank;
+  const int lower = me > 0 ? me - 1 : (dist->ring ? P - 1 : -1);
+  const int upper = me < P - 1 ? me + 1 : (dist->ring ? 0 : -1);
+  const size_t cap = g_p2p.halo_cap;
+  h.slot_bytes = (long long)(2 * cap);
+  if (lower >= 0) {  // my first owned plane is the lower neighbour's UPPER ghost (side 1)
+    h.dst[0] = g_p2p.peer_base[lower] + kHaloLandOff + cap;
+    h.flag_dst[0] = (unsigned long long*)(g_p2p.peer_base[lower] + kHaloFlagOff) + 1;
+  }
+  if (upper >= 0) {  // my last owned plane is the upper neighbour's LOWER ghost (side 0)
+    h.dst[1] = g_p2p.peer_base[upper] + kHaloLandOff;
+    h.flag_dst[1] = (unsigned long long*)(g_p2p.peer_base[upper] + kHaloFlagOff);
+  }
+  h.flag_src = (const unsigned long long*)((char*)g_p2p.local + kHaloFlagOff);
+  h.tiles = tile.tiles_y * tile.tiles_z;
+  h.on = 1;
+  return h;
+}
+
+__global__ void k_halo_flags_init(unsigned long long* flags, unsigned long long v) {
+  flags[0] = v;
+  flags[1] = v;
 }
 
 // ---- CG -----------------------------------------------------------------------------------
@@ -427,8 +475,15 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
       L.count += 2;
     }
     mark(1);
-    CommLane* lane = (dist && tma_interior_chunks(*tma, g) >= 4) ? comm_lane() : nullptr;  // enough interior work to hide it
-    if (lane) {
+    const bool peer_halo = tma->tile.halo.on != 0;
+    CommLane* lane = (dist && !peer_halo && tma_interior_chunks(*tma, g) >= 4) ? comm_lane() : nullptr;  // enough interior work to hide it
+    if (peer_halo) {
+      // r's boundary planes travel INSIDE phase B (stores into the neighbours' landing zones); boundary
+      // chunks first so that they arrive early.  No NCCL call, no second stream, no waiting kernel.
+      launch_cg_phaseB_tma<T>(L.s, *tma, g, eq, parity, nxt, r, w.st, w.partials, tma_interior_chunks(*tma, g) >= 1 ? 4 : 0);
+      ++L.count;
+      overlapped = true;
+    } else if (lane) {
       // overlap: ONE phase B launch whose boundary chunks are scheduled first and count themselves
       // in; on the (high-priority) communication stream k_wait_halo waits for that count, then their r
       // planes go out while the interior chunks are still running.  (A split into two launches cost
@@ -499,8 +554,9 @@ static void cg_iteration(Launcher& L, const GridDev& g, const EqDev<T>& eq, int 
       k_finalize<T><<<1, 1, 0, L.s>>>(ST_CG_FIN, w.st);
       L.count += 2;
     }
-    if (overlapped) cudaStreamWaitEvent(L.s, comm_lane()->join, 0);  // r ghosts before the next phase A
-    ++L.count;
+    const bool peer_halo = tma != nullptr && tma->tile.halo.on != 0;
+    if (overlapped && !peer_halo) cudaStreamWaitEvent(L.s, comm_lane()->join, 0);  // r ghosts before the next phase A
+    if (!peer_halo) ++L.count;
   }
   mark(3);
 }
@@ -796,7 +852,17 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     plan.fuse_fin = tmap.tile.fuse_fin = 0;
     if (use_tma && cfg->variant != 4) {  // (variant 4 on slabs: keep the NCCL all-reduces, for A/B runs)
       tmap.tile.p2p = p2p_dev(dist);
-      if (tmap.tile.p2p.peers != nullptr) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+      if (tmap.tile.p2p.peers != nullptr) {
+        tmap.tile.fuse_fin = static_shell(nfaces, faces);
+        tmap.tile.halo = halo_dev<T>(dist, g, tmap.tile);
+        if (tmap.tile.halo.on) {
+          const bool flat = tma_flat(g);
+          const int boxz = flat ? TmaCfg<T, KFlat>::BOXZ : TmaCfg<T, KStd>::BOXZ;
+          const int boxy = flat ? TmaCfg<T, KFlat>::BOXY : TmaCfg<T, KStd>::BOXY;
+          if (!make_map<T>(&tmap.r_land, (const T*)((char*)g_p2p.local + kHaloLandOff), g, boxz, boxy, 4, g_p2p.halo_cap))
+            tmap.tile.halo.on = 0;
+        }
+      }
     }
   }
 
@@ -835,6 +901,18 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       dist_allreduce(*dist, &w.st->sum[R_A], 1, stream);
       k_finalize<T><<<1, 1, 0, stream>>>(ST_CG_INIT, w.st);
       L.count += 4;
+      if (use_tma && tmap.tile.halo.on) {
+        // the first phase A (parity 0) reads landing slot 1: seed it with the ghost planes NCCL has just
+        // delivered, and raise both flags to the sequence number that phase A will ask for (epoch - 1)
+        char* land = (char*)g_p2p.local + kHaloLandOff + 2 * g_p2p.halo_cap;
+        const size_t pb = (size_t)plane * sizeof(T);
+        if (g.olo0 > 0)
+          PA_CUDA(cudaMemcpyAsync(land, r + (long long)(g.olo0 - 1) * plane, pb, cudaMemcpyDeviceToDevice, stream));
+        if (g.ohi0 < g.n[0])
+          PA_CUDA(cudaMemcpyAsync(land + g_p2p.halo_cap, r + (long long)g.ohi0 * plane, pb, cudaMemcpyDeviceToDevice, stream));
+        k_halo_flags_init<<<1, 1, 0, stream>>>((unsigned long long*)((char*)g_p2p.local + kHaloFlagOff), g_p2p.epoch);
+        L.count += 1;
+      }
     }
   } else if (method == PA_METHOD_BICGSTAB) {
     T* r0 = (T*)w.vec[0];
@@ -1285,8 +1363,17 @@ int pa_p2p_local_handle(void* out64) {
   PA_REQUIRE_DEVICE();
   if (!out64) return fail(PA_ERR_ARG, "null argument");
   if (!g_p2p.local) {
-    PA_CUDA(cudaMalloc((void**)&g_p2p.local, kMailboxBytes));
-    PA_CUDA(cudaMemset(g_p2p.local, 0, kMailboxBytes));
+    // mailbox + halo flags + landing zone in ONE allocation: one IPC handle per rank maps all of it
+    size_t cap = halo_cap_bytes();
+    size_t bytes = kHaloLandOff + 4 * cap;
+    if (cudaMalloc((void**)&g_p2p.local, bytes) != cudaSuccess) {  // no room for the landing zone: mailboxes only
+      cudaGetLastError();
+      cap = 0;
+      bytes = kHaloLandOff;
+      PA_CUDA(cudaMalloc((void**)&g_p2p.local, bytes));
+    }
+    g_p2p.halo_cap = cap;
+    PA_CUDA(cudaMemset(g_p2p.local, 0, kHaloLandOff));
     PA_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -1316,6 +1403,7 @@ int pa_p2p_attach(const void* handles, int rank, int nranks) {
     }
     ptrs[p] = (unsigned long long*)mapped;
   }
+  for (int p = 0; p < nranks; ++p) g_p2p.peer_base[p] = (char*)ptrs[p];
   if (!g_p2p.peers_dev) PA_CUDA(cudaMalloc((void**)&g_p2p.peers_dev, 16 * sizeof(unsigned long long*)));
   PA_CUDA(cudaMemcpy(g_p2p.peers_dev, ptrs.data(), (size_t)nranks * sizeof(unsigned long long*),
                      cudaMemcpyHostToDevice));
@@ -1327,6 +1415,12 @@ int pa_p2p_attach(const void* handles, int rank, int nranks) {
 }
 
 int pa_p2p_enabled(void) { return g_p2p.ready ? 1 : 0; }
+long long pa_p2p_halo_cap(void) { return (long long)g_p2p.halo_cap; }
+int pa_p2p_set_halo_cap(long long bytes) {
+  if (bytes < 0 || (size_t)bytes > g_p2p.halo_cap) return fail(PA_ERR_ARG, "halo cap can only be lowered");
+  g_p2p.halo_cap = (size_t)bytes;
+  return PA_OK;
+}
 int pa_p2p_disable(void) {
   g_p2p.ready = false;
   return PA_OK;

@@ -260,6 +260,8 @@ struct SolverState {
   unsigned long long epoch;  // sequence number of the next peer-memory all-reduce (p2p_allreduce)
   unsigned int halo_count;   // boundary CTAs of phase B that have written their planes (monotonic)
   unsigned int halo_target;  // value halo_count reaches when the current iteration's are all done
+  unsigned int halo_cnt[2];  // peer-memory halo exchange: phase-B CTAs that have stored their share of the
+                             // first / last owned plane into the neighbour's landing zone (reset by the last one)
 };
 
 // ---- all-reduce over NVLink peer memory -----------------------------------------------------
@@ -275,6 +277,25 @@ struct P2PDev {
   unsigned long long* const* peers;  // device array [nranks]: mailbox of every rank (peers[me] is local)
   int me, nranks;
   int slot0, count;                  // which SolverState::sum entries are reduced
+};
+
+// ---- halo exchange over NVLink peer memory (CG on slabs) ------------------------------------------
+// Every rank owns a landing zone next to its mailbox (same IPC allocation): [slot 2][side 2] planes, side 0 =
+// the ghost plane below the owned range, side 1 the one above, plus one flag word per side.  Phase B of
+// iteration k stores the new r of its first / last owned plane straight into the neighbour's landing zone
+// (slot = iteration parity) while it writes its own copy, and the last CTA to finish a plane publishes the
+// sequence number of the iteration in the neighbour's flag.  The producer lane of the neighbour's next phase A
+// waits for that flag and TMA-loads the ghost plane from the landing zone.  No NCCL call, no second stream and
+// no waiting kernel inside the loop: the only dependency is between kernels on DIFFERENT GPUs.
+struct HaloDev {
+  void* dst[2];                        // [0]: first owned plane -> lower neighbour; [1]: last -> upper (null: none);
+                                       // addresses of landing slot 0, slot s lies s * slot_bytes further
+  long long slot_bytes;
+  unsigned long long* flag_dst[2];     // the neighbours' flag words
+  const unsigned long long* flag_src;  // this rank's two flag words (volatile reads)
+  int tiles;                           // CTAs that share one plane (tiles_y * tiles_z)
+  int slot;                            // landing slot phase B writes / phase A reads
+  int on;
 };
 
 // Watchdog of the flag wait: a peer that never arrives (crashed rank, a rank that left the solve on an

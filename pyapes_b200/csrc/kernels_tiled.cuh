@@ -58,9 +58,15 @@ struct TilePlan {
   // multi-GPU, TMA CG kernels: all-reduce over peer memory inside the kernel (common.cuh P2PDev);
   // peers == nullptr -> raw sums are left for the NCCL all-reduce + k_finalize pair
   P2PDev p2p;
+  // slabs, TMA CG kernels: halo exchange through the neighbours' landing zones (common.cuh HaloDev).
+  // ghost_last (phase A): the two chunks that read a ghost plane are scheduled LAST, which gives the
+  // neighbour's phase B the longest time to deliver it.
+  HaloDev halo = {{nullptr, nullptr}, 0, {nullptr, nullptr}, nullptr, 0, 0, 0};
+  int ghost_last = 0;
 };
 
 __device__ __forceinline__ int tile_chunk(const TilePlan& p, int z) {
+  if (p.ghost_last) return z < p.chunks - 2 ? z + 1 : (z == p.chunks - 2 ? 0 : z);
   if (z < p.b_lo) return z;
   if (z < p.b_lo + p.b_hi) return p.chunks - p.b_hi + (z - p.b_lo);
   return p.chunk0 + (z - p.b_lo - p.b_hi);
@@ -151,6 +157,8 @@ inline bool plan_tiles_ry(const GridDev& g, const pa_equation& eq, TilePlan& p, 
   p.dist = 0;
   p.chunk0 = 0;
   p.b_lo = p.b_hi = p.signal_halo = 0;
+  p.halo = HaloDev{{nullptr, nullptr}, 0, {nullptr, nullptr}, nullptr, 0, 0, 0};
+  p.ghost_last = 0;
   p.wrap = 0;
   p.src0 = p.src1 = nullptr;
   p.p2p = P2PDev{nullptr, 0, 0, 0, 0};

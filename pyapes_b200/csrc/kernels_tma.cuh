@@ -140,12 +140,15 @@ static inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// planes / plane_stride_bytes: a stack of (n1 x n2) planes that is not the field itself (the halo landing zone)
 template <typename T>
-static inline bool make_map(CUtensorMap* m, const T* base, const GridDev& g, int boxz, int boxy) {
+static inline bool make_map(CUtensorMap* m, const T* base, const GridDev& g, int boxz, int boxy, int planes = 0,
+                            size_t plane_stride_bytes = 0) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)g.n[2], (cuuint64_t)g.n[1], (cuuint64_t)g.n[0]};
-  cuuint64_t strides[2] = {(cuuint64_t)g.n[2] * sizeof(T), (cuuint64_t)g.n[1] * g.n[2] * sizeof(T)};
+  cuuint64_t dims[3] = {(cuuint64_t)g.n[2], (cuuint64_t)g.n[1], (cuuint64_t)(planes > 0 ? planes : g.n[0])};
+  cuuint64_t strides[2] = {(cuuint64_t)g.n[2] * sizeof(T),
+                           plane_stride_bytes ? (cuuint64_t)plane_stride_bytes : (cuuint64_t)g.n[1] * g.n[2] * sizeof(T)};
   cuuint32_t box[3] = {(cuuint32_t)boxz, (cuuint32_t)boxy, 1u};
   cuuint32_t es[3] = {1u, 1u, 1u};
   CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -160,6 +163,7 @@ struct TmaPlan {
   CUtensorMap x_own[2];     // x, x_alt  (phase B reads the current iterate)
   CUtensorMap r_own, r_halo;
   CUtensorMap d_halo[2];    // the two d buffers
+  CUtensorMap r_land;       // this rank's landing zone: [slot 2][side 2] ghost planes of r (HaloDev)
   const void* r_ptr;        // raw arrays behind r_halo / d_halo (wrap-around reads, TilePlan::src*)
   const void* d_ptr[2];
   int coef_uniform = 0;     // coefficient classes of axes 1 and 2 are bitwise equal (star_cells UNI)
@@ -194,6 +198,8 @@ inline void tma_chunks(const GridDev& g, int tiles, TilePlan& p) {
   p.dist = 0;
   p.chunk0 = 0;
   p.b_lo = p.b_hi = p.signal_halo = 0;
+  p.halo = HaloDev{{nullptr, nullptr}, 0, {nullptr, nullptr}, nullptr, 0, 0, 0};
+  p.ghost_last = 0;
   p.wrap = 0;
   p.src0 = p.src1 = nullptr;
   p.p2p = P2PDev{nullptr, 0, 0, 0, 0};
@@ -582,6 +588,15 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
         }
         stg_row<T, K, LEAN>(xo + (long long)k * g.n[2], c, k, xn);
         stg_row<T, K, LEAN>(ro + (long long)k * g.n[2], c, k, rn);
+        if (p.halo.on) {  // first / last owned plane: the same row also goes to the neighbour's landing zone
+          const long long so = p.halo.slot * p.halo.slot_bytes;
+          if (x == g.olo0 && p.halo.dst[0] != nullptr)
+            stg_row<T, K, LEAN>(reinterpret_cast<T*>(static_cast<char*>(p.halo.dst[0]) + so) + c.goff +
+                                    (long long)k * g.n[2], c, k, rn);
+          if (x == g.ohi0 - 1 && p.halo.dst[1] != nullptr)
+            stg_row<T, K, LEAN>(reinterpret_cast<T*>(static_cast<char*>(p.halo.dst[1]) + so) + c.goff +
+                                    (long long)k * g.n[2], c, k, rn);
+        }
       }
     } else {
 #pragma unroll
@@ -622,6 +637,9 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
+  // sequence number this launch publishes with its boundary planes: the all-reduce epoch at launch (it only
+  // moves in the last CTA's reduction, after every CTA has taken its ticket)
+  const unsigned long long halo_seq = p.halo.on ? *(volatile unsigned long long*)&st->epoch : 0ull;
   // 128-byte aligned start, derived by pointer arithmetic so the compiler keeps the shared
   // address space (LDS instead of generic LD)
   unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -675,6 +693,29 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
     else
       tmaB_consumer<T, K, false, WRAP, UNI>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
   }
+  if (p.halo.on) {
+    // this CTA's rows of the first / last owned plane are in the neighbour's landing zone: count it in; the
+    // last CTA of a plane publishes the sequence number in the neighbour's flag word (release at system scope:
+    // every thread fences its remote stores before the CTA's count, the publisher fences again before the flag)
+    const bool has_lo = p.halo.dst[0] != nullptr && x0 <= g.olo0 && g.olo0 < x1;
+    const bool has_hi = p.halo.dst[1] != nullptr && x0 <= g.ohi0 - 1 && g.ohi0 - 1 < x1;
+    if (has_lo || has_hi) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          if (!(side == 0 ? has_lo : has_hi)) continue;
+          const unsigned int t = atomicAdd(&st->halo_cnt[side], 1u);
+          if (t == (unsigned int)p.halo.tiles - 1u) {
+            atomicExch(&st->halo_cnt[side], 0u);
+            __threadfence_system();
+            *(volatile unsigned long long*)p.halo.flag_dst[side] = halo_seq;
+          }
+        }
+      }
+    }
+  }
   if (p.signal_halo && zc < p.b_lo + p.b_hi) {
     // a boundary chunk: its r planes may leave for the neighbour rank as soon as every such CTA is
     // done (k_wait_halo on the communication stream) while the interior chunks still run
@@ -695,6 +736,30 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   } else {
     grid_reduce<2>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 2>{st, R_A, ST_NONE, p.accum});
   }
+}
+
+// Producer-lane wait for a neighbour's boundary plane: the flag word in this rank's landing zone reaches
+// `need`.  Acquire at system scope, then a proxy fence: the plane was written through the generic proxy (by
+// another GPU) and is about to be read through the async proxy (TMA).  Same 60 s watchdog as p2p_allreduce.
+__device__ __forceinline__ bool halo_wait(const unsigned long long* flag, unsigned long long need) {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0ull;
+  bool ok = true;
+  while (true) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= need) break;
+    if ((++spins & 0x3ffu) == 0u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > kP2PTimeoutNs) {
+        ok = false;
+        break;
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return ok;
 }
 
 // =========================================================================================
@@ -823,8 +888,8 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
 template <typename T, typename K, bool WRAP, bool UNI>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_d,
-                TilePlan p, GridDev g, OpDev<T> o, T* __restrict__ d_new, SolverState* st,
-                double* partials) {
+                const __grid_constant__ CUtensorMap tm_land, TilePlan p, GridDev g, OpDev<T> o,
+                T* __restrict__ d_new, SolverState* st, double* partials) {
   typedef TmaCfg<T, K> C;
   extern __shared__ unsigned char smem_dyn[];
   if (st->done) return;
@@ -852,6 +917,12 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   if (warp == C::CWARPS) {
     if (lane == 0) {
       const int n = x1 - x0 + 2;
+      // peer-memory halo exchange: the ghost planes of r live in this rank's landing zone (tm_land), written
+      // by the neighbours' previous phase B; wait for their flag (sequence number = epoch at launch - 1)
+      const bool halo_on = p.halo.on != 0;
+      const int gl = (halo_on && g.olo0 > 0) ? g.olo0 - 1 : -2;
+      const int gu = (halo_on && g.ohi0 < g.n[0]) ? g.ohi0 : -2;
+      const unsigned long long need = halo_on ? *(volatile unsigned long long*)&st->epoch - 1ull : 0ull;
       for (int i = 0; i < n; ++i) {
         if (!actx && i != 1) continue;
         const int pl = x0 - 1 + i;
@@ -860,9 +931,21 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
         mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
         unsigned char* sb = stages + (size_t)s * C::STAGE_A;
         const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+        const bool ghost = (pl == gl) || (pl == gu);
+        if (ghost) {
+          const int side = (pl == gl) ? 0 : 1;
+          if (!halo_wait(p.halo.flag_src + side, need)) {
+            st->done = 1;  // the neighbour never delivered (watchdog): end the solve, the host reports it
+            st->status = PA_PEER_LOST;
+          }
+        }
         for (int b = 0; b < C::NB; ++b) {
           const int zb = z0 + b * C::OBOXZ;
-          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
+          if (ghost)
+            tma_load_3d(sb + b * C::HBOX_SLOT, &tm_land, zb - C::HZ, C::FLAT ? 0 : y0 - 1,
+                        p.halo.slot * 2 + ((pl == gl) ? 0 : 1), &full[s]);
+          else
+            tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
           tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, &tm_d, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
         }
       }
@@ -937,8 +1020,12 @@ static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
   TilePlan tile = tp.tile;
   tile.src0 = tp.r_ptr;
   tile.src1 = tp.d_ptr[parity];
-  k_cg_phaseA_tma<T, K, WRAP, UNI><<<grid, C::THREADS, C::SMEM_A, s>>>(tp.r_halo, tp.d_halo[parity], tile, g, eq.op[0],
-                                                           d_new, st, partials);
+  if (tile.halo.on) {
+    tile.halo.slot = 1 - parity;  // what the previous iteration's phase B (parity 1 - p) delivered
+    tile.ghost_last = tile.chunks >= 3 ? 1 : 0;
+  }
+  k_cg_phaseA_tma<T, K, WRAP, UNI><<<grid, C::THREADS, C::SMEM_A, s>>>(
+      tp.r_halo, tp.d_halo[parity], tile.halo.on ? tp.r_land : tp.r_halo, tile, g, eq.op[0], d_new, st, partials);
 }
 
 template <typename T>
@@ -986,12 +1073,13 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     tile.chunk0 = c_lo + 1;
     tile.accum = 1;
     nz = c_hi - c_lo - 1;
-  } else if (sub == 3) {  // ONE launch, boundary chunks first, each of their CTAs signals completion
+  } else if (sub == 3 || sub == 4) {  // ONE launch, boundary chunks first
     tile.b_lo = c_lo + 1;
     tile.b_hi = tile.chunks - c_hi;
     tile.chunk0 = tile.b_lo;
-    tile.signal_halo = 1;
+    tile.signal_halo = sub == 3 ? 1 : 0;  // 3: each boundary CTA counts itself in for k_wait_halo (NCCL exchange)
   }
+  if (tile.halo.on) tile.halo.slot = parity;
   dim3 grid(tile.tiles_z, tile.tiles_y, nz);
   k_cg_phaseB_tma<T, K, WRAP, UNI><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
                                                            g, eq.op[0], x_new, r, st, partials);

@@ -136,12 +136,17 @@ def _attach_peer_mailboxes(lib, rank: int, world: int, device, on_gpu: bool) -> 
     if good:
         blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(r[:64] for r in rows))
         good = lib.pa_p2p_attach(blob, rank, world) == 0
-    flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=device if on_gpu else "cpu")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank attached, or nobody uses the mailboxes
-    if int(flag.item()) != 1:
+    # [attached?, bytes per landing plane]: every rank attached or nobody uses the mailboxes; the halo landing
+    # zones (csrc/common.cuh HaloDev) are used with the smallest capacity any rank could allocate
+    flag = torch.tensor([1 if good else 0, int(lib.pa_p2p_halo_cap())], dtype=torch.int64,
+                        device=device if on_gpu else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag[0].item()) != 1:
         lib.pa_p2p_disable()
         warnings.warn("pyapes_b200: peer mailboxes unavailable, CG scalars go through ncclAllReduce")
-    _COMM["p2p"] = int(flag.item()) == 1
+    else:
+        lib.pa_p2p_set_halo_cap(int(flag[1].item()))
+    _COMM["p2p"] = int(flag[0].item()) == 1
 
 
 def destroy_comm() -> None:

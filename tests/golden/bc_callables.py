@@ -3,12 +3,16 @@ the GPU tests (run against pyapes_b200): signature `(grid, mask, var, opt)` (bcs
 import torch
 
 
+# Polynomials only: +, -, * are correctly rounded on the CPU (where the fixtures are made) and on the GPU
+# (where the tests evaluate the callables), transcendental functions are not bit-identical between the two.
 def neumann_cos(grid, mask, *_):
-    return 0.3 * torch.cos(2.0 * grid[1][mask])
+    y = grid[1][mask]
+    return 0.3 * (1.0 - 2.0 * y * y)
 
 
 def dirichlet_sin(grid, mask, *_):
-    return torch.sin(3.0 * grid[1][mask]) + grid[0][mask]
+    y = grid[1][mask]
+    return 3.0 * y * (1.5 - y) + grid[0][mask]
 
 
 def dirichlet_of_var(grid, mask, var, *_):

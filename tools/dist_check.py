@@ -82,6 +82,24 @@ for variant in (0, 1, 2):
             report(f"cg v{variant}", name, res, rep["itr"] == rep1["itr"]
                    and abs(rep["tol"] - rep1["tol"]) <= 1e-10 * max(1.0, rep1["tol"]) and err <= 1e-9)
 
+# ---- CG as the solver runs it by default: iteration pairs replayed as a CUDA graph (fused TMA kernels with the
+#      peer-memory halo exchange and in-kernel all-reduces when the mailboxes are up)
+from pyapes_b200 import _native as _N
+if rank == 0:
+    print(f"[info] p2p mailboxes: {bool(_N.lib().pa_p2p_enabled())}, landing plane cap: {_N.lib().pa_p2p_halo_cap()} B "
+          f"(0 = ncclSend/ncclRecv halo exchange)", flush=True)
+for (name, n, kinds, vals), (tol, max_it) in zip(cases, [(1e-8, 3000), (1e-30, 60), (1e-30, 40), (1e-30, 30), (1e-30, 30), (1e-30, 30)]):
+    res = both(krylov("cg", tol, max_it, 0, graph=True), n, kinds, vals)
+    if res:
+        rep, rep1, err = res
+        report("cg v0 graph", name, res, rep["itr"] == rep1["itr"]
+               and abs(rep["tol"] - rep1["tol"]) <= 1e-10 * max(1.0, rep1["tol"]) and err <= 1e-9)
+res = both(krylov("cg", 1e-9, 4000, 0, graph=True), [96, 80, 192], D6, [0.0, 1.0, 0.5, 0.0, -0.25, 0.0])
+if res:
+    rep, rep1, err = res
+    report("cg v0 graph", "dirichlet 96x80x192 (15 tiles per plane)", res, rep["itr"] == rep1["itr"] and rep["converge"]
+           and abs(rep["tol"] - rep1["tol"]) <= 1e-10 * max(1.0, rep1["tol"]) and err <= 1e-9)
+
 # ---- Jacobi: TMA star engine (variant 0) and generic kernels (variant 1)
 for variant in (0, 1):
     for name, n, kinds, vals in cases:
