@@ -173,7 +173,9 @@ typedef struct {
   int32_t variant;     /* 0 = auto (small grids: persistent kernel; TMA-staged fused kernels, else
                           register-tiled, else generic), 1 = generic kernels, 2 = register-tiled kernels
                           (no TMA), 3 = CG as one persistent cooperative kernel (small grids, every
-                          face Dirichlet), 4 = like 0 but never the persistent kernel */
+                          face Dirichlet), 4 = like 0 but never a whole-solve kernel, 5 = CG as ONE
+                          cooperative launch of the two TMA phases (L2-resident grids, every face Dirichlet;
+                          auto takes it between 80 k and 1.5 M cells) */
 } pa_solver_cfg;
 
 const char* pa_last_error(void);

@@ -27,6 +27,8 @@ namespace pa {
                                                int, T*, SolverState*, double*);                                \
   extern template void launch_cg_phaseB_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&,  \
                                                int, T*, T*, SolverState*, double*, int);                       \
+  extern template bool launch_cg_coop_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&, T*, \
+                                             T*, T*, T*, T*, SolverState*, double*);                           \
   extern template bool launch_star_tma<T, PW_RESID>(cudaStream_t, const GridDev&, const EqDev<T>&,             \
                                                     const TilePlan&, const T*, const T*, T*, T*, T,            \
                                                     SolverState*, double*, int);                               \
@@ -124,6 +126,10 @@ static int check_faces(int nfaces, const pa_face_bc* faces) {
 // measured (tools/bench_small.py): 9.7-10.9 us per iteration against 16.2 us for the fused kernels up to
 // 256^2 / 32^3, break-even near 110 k cells
 constexpr long long kSmallCgCells = 80000;
+// auto-selection window of the cooperative whole-solve TMA kernel (tools/bench_small.py, B200): 17-18 us per
+// iteration against 19-20 for separate launches at 32^3 .. 64^3 and 36 against 38 at 1024^2, equal from 128^3 on
+// (the iteration is bound by the latency of the plane-by-plane march inside a phase, not by the launches)
+constexpr long long kCoopCgCells = 1500000;
 
 static inline int grid_blocks(long long cells) {
   long long b = (cells + kBlock - 1) / kBlock;
@@ -837,7 +843,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   bool tiled = false;
   TmaPlan tmap;
   bool use_tma = false;
-  const bool auto_fused = cfg->variant == 0 || cfg->variant == 4;  // 4: fused kernels, never the persistent one
+  // 4: fused kernels, never a whole-solve kernel; 5: the cooperative whole-solve TMA kernel (L2-resident grids)
+  const bool auto_fused = cfg->variant == 0 || cfg->variant == 4 || cfg->variant == 5;
   if (method == PA_METHOD_CG && auto_fused) {
     use_tma = plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], tmap);
     if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
@@ -1003,6 +1010,27 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     eq_cg.nops = 1;
     eq_cg.op[0].has_shift = 1;
     eq_cg.op[0].shift = (T)c;
+  }
+
+  // L2-resident grids: the whole solve as ONE cooperative launch of the two TMA phases (kernels_tma.cuh
+  // k_cg_coop_tma).  variant 5 forces it; auto (0) takes it between the tiny-grid kernel above and kCoopCgCells.
+  if (method == PA_METHOD_CG && use_tma && !dist && !nonlinear && static_shell(nfaces, faces) && !tmap.tile.wrap &&
+      (cfg->variant == 5 ||
+       (cfg->variant == 0 && g.cells > kSmallCgCells && g.cells <= kCoopCgCells && getenv("PA_NO_COOP_CG") == nullptr))) {
+    if (launch_cg_coop_tma<T>(stream, tmap, g, eq_cg, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], w.st,
+                              w.partials)) {
+      L.count += 1;
+      SolverState* hs = nullptr;
+      int rcp = poll_state(stream, w.st, &hs);
+      if (rcp != PA_OK) return rcp;
+      PA_CUDA(cudaGetLastError());
+      if (!hs->done) return fail(PA_ERR_CUDA, "cooperative CG kernel returned without latching `done`");
+      fill_report(rep, hs, L.count);
+      set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
+      return PA_OK;
+    }
+    cudaGetLastError();
+    if (cfg->variant == 5) return fail(PA_ERR_UNSUPPORTED, "cooperative launch is not available on this device");
   }
   auto iteration = [&](T* cur, T* nxt) {
     const EqDev<T>& e = use_tma ? eq_cg : ((cur == x) ? eq : eq_alt);

@@ -63,6 +63,13 @@ struct TilePlan {
   // neighbour's phase B the longest time to deliver it.
   HaloDev halo = {{nullptr, nullptr}, 0, {nullptr, nullptr}, nullptr, 0, 0, 0};
   int ghost_last = 0;
+  // TMA kernels are PERSISTENT: a launch has at most 2 CTAs per SM and every CTA walks the work items
+  // (tile, chunk) id = blockIdx.x, blockIdx.x + gridDim.x, ... with ONE mbarrier pipeline that keeps running
+  // across item boundaries (the producer lane prefetches the next item while the consumers finish this one).
+  // nz = chunk slots of this launch (== chunks unless a sub-launch takes a subset).
+  int nz = 0;
+  int work_slot = 0;  // entry of the launch in the work-counter pool (kernels_tma.cuh)
+  int first_static = 0;  // 1: a CTA's first item is its block index, the counter serves the rest
 };
 
 __device__ __forceinline__ int tile_chunk(const TilePlan& p, int z) {

@@ -285,6 +285,109 @@ inline bool plan_tma(const GridDev& g, const pa_equation& eq, int nfaces, const 
   return ok;
 }
 
+// ---- work items of the persistent kernels --------------------------------------------------------
+// item id -> (chunk slot, tile row, tile column), chunk slot slowest: CTAs that run side by side work on
+// neighbouring tiles of the same chunk (their halos meet in L2), and on slabs the boundary chunks come first.
+struct WorkItem {
+  int y0, z0, x0, x1;
+  bool lean;  // the tile touches neither the array edge nor a boundary-adjacent coefficient class
+};
+
+template <typename C>
+__device__ __forceinline__ WorkItem work_item(const TilePlan& p, const GridDev& g, int id) {
+  WorkItem w;
+  const int tz = id % p.tiles_z;
+  const int t = id / p.tiles_z;
+  const int ty = t % p.tiles_y;
+  const int zc = t / p.tiles_y;
+  w.z0 = tz * C::TZ;
+  w.y0 = ty * C::TY;
+  w.x0 = tile_chunk(p, zc) * p.cx;
+  w.x1 = min(w.x0 + p.cx, g.n[0]);
+  const bool full_tile = (C::FLAT || w.y0 + C::TY <= g.n[1]) && (w.z0 + C::TZ <= g.n[2]);
+  const bool edge = (!C::FLAT && ((w.y0 < 2) || (w.y0 + C::TY > g.n[1] - 2))) || (w.z0 < 2) || (w.z0 + C::TZ > g.n[2] - 2);
+  w.lean = full_tile && !edge;
+  return w;
+}
+
+__device__ __forceinline__ int work_items(const TilePlan& p) { return p.tiles_z * p.tiles_y * p.nz; }
+
+// Dynamic claims: the CTAs take the next item id from a global counter (like the hardware CTA scheduler
+// did when every item was a CTA) -- a static round-robin gave some CTAs nothing but edge tiles, which run the
+// longer general path, and cost 10 % at 512^3.  The producer lane claims, and hands the id to the consumer
+// warps through a small shared-memory ring that is published by the `full` barrier of the item's first plane
+// (mbarrier arrive = release, wait = acquire); id -1 ends the walk.  Counters come from a per-module pool, one
+// entry per launch (round-robin on the host); the last CTA to leave a launch resets its entry.
+struct WorkCounter {
+  unsigned int next, done;
+};
+constexpr int kWorkPool = 64;
+constexpr int kItemRing = 8;  // > items in flight: the producer is at most S <= 8 planes (>= 3 per item) ahead
+static __device__ WorkCounter g_work_pool[kWorkPool];
+
+static inline int next_work_slot() {
+  static unsigned int rr = 0;
+  return (int)(__atomic_fetch_add(&rr, 1u, __ATOMIC_RELAXED) % kWorkPool);
+}
+
+// producer lane: claim the next item; before publishing it, the stage of its first plane must be free
+template <typename C>
+__device__ __forceinline__ int claim_item(const TilePlan& p, int* item_ring, unsigned seq, uint64_t* full, uint64_t* empty,
+                                          unsigned gi) {
+  // the first item of every CTA is its block index (no atomic in front of the launch's first TMA load); the
+  // counter hands out the ids from gridDim.x on
+  const int id = (seq == 0 && p.first_static) ? (int)blockIdx.x
+                                              : (int)(gridDim.x * (unsigned)p.first_static + atomicAdd(&g_work_pool[p.work_slot].next, 1u));
+  const int s = gi & (C::S - 1);
+  if (gi >= (unsigned)C::S) mbar_wait(&empty[s], ((gi / C::S) - 1) & 1);
+  const bool over = id >= work_items(p);
+  item_ring[seq & (kItemRing - 1)] = over ? -1 : id;
+  if (over) mbar_arrive(&full[s]);  // completes the phase without data: the consumers read the sentinel
+  return over ? -1 : id;
+}
+
+// consumer warps: the item the producer published for sequence number seq (-1: none left)
+template <typename C>
+__device__ __forceinline__ int take_item(const int* item_ring, unsigned seq, uint64_t* full, unsigned gi) {
+  mbar_wait(&full[gi & (C::S - 1)], (gi / C::S) & 1);
+  return *(volatile const int*)&item_ring[seq & (kItemRing - 1)];
+}
+
+// a kernel that goes on after the sentinel (several phases per launch): the sentinel used one stage of the ring
+// like a plane would have, so the consumer warps hand it back like a plane
+template <typename C>
+__device__ __forceinline__ void consumer_release_sentinel(uint64_t* empty, unsigned gi) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[gi & (C::S - 1)]);
+}
+
+// every CTA, once, when it has no work left: the last one re-arms the launch's counter
+__device__ __forceinline__ void work_leave(const TilePlan& p) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    WorkCounter* w = &g_work_pool[p.work_slot];
+    __threadfence();
+    if (atomicAdd(&w->done, 1u) == gridDim.x - 1u) {
+      w->next = 0u;
+      w->done = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// grid of a persistent launch: 2 CTAs per SM (occupancy of every TMA kernel), never more than the items
+inline int persistent_grid(const TilePlan& p, int nz) {
+  const long long items = (long long)p.tiles_z * p.tiles_y * nz;
+  const long long slots = (long long)kNumSMs * 2;
+  return (int)(items < slots ? (items > 0 ? items : 1) : slots);
+}
+
+// consumer warps only (the producer warp runs ahead in its own loop): named barrier 1
+template <int CWARPS>
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(CWARPS * 32) : "memory");
+}
+
 // ---- consumer-side geometry -----------------------------------------------------------------------
 template <typename T, typename K>
 struct ConsCtx {
@@ -483,24 +586,29 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
 // KERNEL, so that the edge tiles of non-periodic problems (30 % of the tiles at 512^2 planes) do not carry
 // the wrapped-halo loads, their branches and the registers they pin: as a run-time branch they cost the
 // general path 22 % more instructions and 9 spill reloads per plane, and phase B 7 % at 512^3.
-template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false>
+// gi0: pipeline counter of the item's first plane (x0-1) -- the CTA's mbarrier ring keeps running across items;
+// STRIDE: bytes between stages (a kernel that alternates phases uses the larger of the two layouts)
+// HALO: the launch stores its first / last owned plane of r into the neighbours' landing zones as well (slabs with
+// the peer-memory halo exchange); a template parameter so that single-GPU launches do not carry those stores
+template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false, int STRIDE = TmaCfg<T, K>::STAGE_B,
+          bool HALO = false>
 __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ x_new, T* __restrict__ r, T alpha,
                                               unsigned char* stages, uint64_t* full, uint64_t* empty,
-                                              int y0, int z0, int x0, int x1, double (&acc_out)[2]) {
+                                              int y0, int z0, int x0, int x1, double (&acc_out)[2], unsigned gi0) {
   typedef TmaCfg<T, K> C;
   constexpr int VEC = C::VEC;
   ConsCtx<T, K> c;
   cons_setup<T, K>(g, c, y0, z0);
-  const bool actx = g.act[0] != 0;
+  constexpr bool actx = true;  // kernel axis 0 is active on every TMA path (plan_tma)
   const long long n12 = (long long)g.n[1] * g.n[2];
   T* xo = x_new + (long long)x0 * n12 + c.goff;
   T* ro = r + (long long)x0 * n12 + c.goff;
 
-  auto halo = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B); };
-  auto ownx = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B + C::HALO_SLOT); };
+  auto halo = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * STRIDE); };
+  auto ownx = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * STRIDE + C::HALO_SLOT); };
   auto ownr = [&](int s) {
-    return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_B + C::HALO_SLOT + C::OWN_SLOT);
+    return reinterpret_cast<const T*>(stages + (size_t)s * STRIDE + C::HALO_SLOT + C::OWN_SLOT);
   };
   auto load_own = [&](int s, T (&v)[K::RY][VEC]) {
     const T* h = halo(s) + c.hoff;
@@ -515,16 +623,17 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
   T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
   double a0 = 0.0, a1 = 0.0;
 
-  // prologue: plane x0-1 (counter 0) -> A ; plane x0 (counter 1) -> B
-  if (actx) {
-    mbar_wait(&full[0], 0);
-    load_own(0, A);
-    release(0);
+  // prologue: plane x0-1 (counter gi0) -> A ; plane x0 (counter gi0 + 1) -> B
+  {
+    const unsigned s0 = gi0 & (C::S - 1), s1 = (gi0 + 1) & (C::S - 1);
+    mbar_wait(&full[s0], (gi0 / C::S) & 1);
+    load_own(s0, A);
+    release(s0);
+    mbar_wait(&full[s1], ((gi0 + 1) / C::S) & 1);
+    load_own(s1, B);
   }
-  mbar_wait(&full[1 % C::S], 0);
-  load_own(1 % C::S, B);
 
-  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, unsigned i) {
     // i = pipeline counter of plane x+1; plane x sits in stage (i-1)%S
     const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
     if (actx) {
@@ -588,7 +697,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
         }
         stg_row<T, K, LEAN>(xo + (long long)k * g.n[2], c, k, xn);
         stg_row<T, K, LEAN>(ro + (long long)k * g.n[2], c, k, rn);
-        if (p.halo.on) {  // first / last owned plane: the same row also goes to the neighbour's landing zone
+        if (HALO) {  // first / last owned plane: the same row also goes to the neighbour's landing zone
           const long long so = p.halo.slot * p.halo.slot_bytes;
           if (x == g.olo0 && p.halo.dst[0] != nullptr)
             stg_row<T, K, LEAN>(reinterpret_cast<T*>(static_cast<char*>(p.halo.dst[0]) + so) + c.goff +
@@ -613,7 +722,8 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
     release(sc);
   };
 
-  int x = x0, i = 2;
+  int x = x0;
+  unsigned i = gi0 + 2;
   while (true) {
     step(A, B, Cc, x, i);
     if (++x >= x1) break;
@@ -625,11 +735,108 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
     if (++x >= x1) break;
     ++i;
   }
-  acc_out[0] = a0;
-  acc_out[1] = a1;
+  release(i & (C::S - 1));  // the plane above the chunk: its own cells were read, the ring moves on
+  acc_out[0] += a0;
+  acc_out[1] += a1;
 }
 
-template <typename T, typename K, bool WRAP, bool UNI>
+// ---- phase B over this CTA's work items: producer lane / consumer warps ------------------------------
+template <typename T, typename K, int STRIDE>
+__device__ __forceinline__ unsigned phaseB_produce(const CUtensorMap* tm_d, const CUtensorMap* tm_x,
+                                                   const CUtensorMap* tm_r, const TilePlan& p, const GridDev& g,
+                                                   unsigned char* stages, uint64_t* full, uint64_t* empty,
+                                                   int* item_ring, unsigned gi) {
+  typedef TmaCfg<T, K> C;
+  for (unsigned seq = 0;; ++seq) {
+    const int id = claim_item<C>(p, item_ring, seq, full, empty, gi);
+    if (id < 0) break;
+    const WorkItem w = work_item<C>(p, g, id);
+    const int n = w.x1 - w.x0 + 2;  // planes x0-1 .. x1
+    for (int k = 0; k < n; ++k, ++gi) {
+      const int pl = w.x0 - 1 + k;
+      const int s = gi & (C::S - 1);
+      if (k > 0 && gi >= (unsigned)C::S) mbar_wait(&empty[s], ((gi / C::S) - 1) & 1);  // (k == 0: claim_item waited)
+      const bool inner = (pl >= w.x0 && pl < w.x1);
+      mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? 2 * C::OWN_BYTES : 0)));
+      unsigned char* sb = stages + (size_t)s * STRIDE;
+      const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+      for (int b = 0; b < C::NB; ++b) {
+        const int zb = w.z0 + b * C::OBOXZ;
+        tma_load_3d(sb + b * C::HBOX_SLOT, tm_d, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+        if (inner) {
+          tma_load_3d(sb + C::HALO_SLOT + b * C::OBOX_SLOT, tm_x, zb, w.y0, xw, &full[s]);
+          tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT + b * C::OBOX_SLOT, tm_r, zb, w.y0, xw, &full[s]);
+        }
+      }
+    }
+  }
+  return gi;
+}
+
+template <typename T, typename K, bool WRAP, bool UNI, int STRIDE, bool HALO = false>
+__device__ __forceinline__ unsigned phaseB_consume(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
+                                                   T* __restrict__ x_new, T* __restrict__ r, T alpha, SolverState* st,
+                                                   unsigned long long halo_seq, unsigned char* stages, uint64_t* full,
+                                                   uint64_t* empty, const int* item_ring, double (&acc)[2],
+                                                   unsigned gi) {
+  typedef TmaCfg<T, K> C;
+  for (unsigned seq = 0;; ++seq) {
+    const int id = take_item<C>(item_ring, seq, full, gi);
+    if (id < 0) break;
+    const WorkItem w = work_item<C>(p, g, id);
+    if (w.lean)
+      tmaB_consumer<T, K, true, false, false, STRIDE, HALO>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
+                                                            w.x0, w.x1, acc, gi);
+    else
+      tmaB_consumer<T, K, false, WRAP, UNI, STRIDE, HALO>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
+                                                          w.x0, w.x1, acc, gi);
+    gi += (unsigned)(w.x1 - w.x0 + 2);
+    if (HALO) {
+      // this item's rows of the first / last owned plane are in the neighbour's landing zone: count it in; the
+      // last item of a plane publishes the sequence number in the neighbour's flag word (release at system
+      // scope: every thread fences its remote stores before the count, the publisher fences again before the flag)
+      const bool has_lo = p.halo.dst[0] != nullptr && w.x0 <= g.olo0 && g.olo0 < w.x1;
+      const bool has_hi = p.halo.dst[1] != nullptr && w.x0 <= g.ohi0 - 1 && g.ohi0 - 1 < w.x1;
+      if (has_lo || has_hi) {
+        __threadfence_system();
+        consumer_sync<C::CWARPS>();
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (!(side == 0 ? has_lo : has_hi)) continue;
+            const unsigned int t = atomicAdd(&st->halo_cnt[side], 1u);
+            if (t == (unsigned int)p.halo.tiles - 1u) {
+              atomicExch(&st->halo_cnt[side], 0u);
+              __threadfence_system();
+              *(volatile unsigned long long*)p.halo.flag_dst[side] = halo_seq;
+            }
+          }
+        }
+      }
+    }
+    if (p.signal_halo && id / (p.tiles_z * p.tiles_y) < p.b_lo + p.b_hi) {
+      // NCCL exchange overlapped with the interior chunks: a boundary item is done (k_wait_halo counts them)
+      __threadfence();
+      consumer_sync<C::CWARPS>();
+      if (threadIdx.x == 0) atomicAdd(&st->halo_count, 1u);
+    }
+  }
+  return gi;
+}
+
+template <typename C>
+__device__ __forceinline__ void pipe_init(uint64_t* full, uint64_t* empty) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], C::CWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_r, TilePlan p, GridDev g, OpDev<T> o,
@@ -639,7 +846,7 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   if (st->done) return;
   // sequence number this launch publishes with its boundary planes: the all-reduce epoch at launch (it only
   // moves in the last CTA's reduction, after every CTA has taken its ticket)
-  const unsigned long long halo_seq = p.halo.on ? *(volatile unsigned long long*)&st->epoch : 0ull;
+  const unsigned long long halo_seq = HALO ? *(volatile unsigned long long*)&st->epoch : 0ull;
   // 128-byte aligned start, derived by pointer arithmetic so the compiler keeps the shared
   // address space (LDS instead of generic LD)
   unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -647,84 +854,19 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_B);
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int zc = (int)blockIdx.z;
-  const int x0 = tile_chunk(p, zc) * p.cx;
-  const int x1 = min(x0 + p.cx, g.n[0]);
-  const bool actx = g.act[0] != 0;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], C::CWARPS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
+  __shared__ int item_ring[kItemRing];
+  pipe_init<C>(full, empty);
   double acc[2] = {0.0, 0.0};
   if (warp == C::CWARPS) {
-    if (lane == 0) {
-      // producer: planes x0-1 .. x1 (pipeline counters 0 .. cx+1)
-      const int n = x1 - x0 + 2;
-      for (int i = 0; i < n; ++i) {
-        if (!actx && i != 1) continue;
-        const int pl = x0 - 1 + i;
-        const int s = i & (C::S - 1);
-        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
-        const bool inner = (pl >= x0 && pl < x1);
-        mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? 2 * C::OWN_BYTES : 0)));
-        unsigned char* sb = stages + (size_t)s * C::STAGE_B;
-        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
-        for (int b = 0; b < C::NB; ++b) {
-          const int zb = z0 + b * C::OBOXZ;
-          tma_load_3d(sb + b * C::HBOX_SLOT, &tm_d, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
-          if (inner) {
-            tma_load_3d(sb + C::HALO_SLOT + b * C::OBOX_SLOT, &tm_x, zb, y0, xw, &full[s]);
-            tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT + b * C::OBOX_SLOT, &tm_r, zb, y0, xw, &full[s]);
-          }
-        }
-      }
-    }
+    if (lane == 0) phaseB_produce<T, K, C::STAGE_B>(&tm_d, &tm_x, &tm_r, p, g, stages, full, empty, item_ring, 0u);
   } else {
     const T alpha = (T)st->scal[S_ALPHA];
-    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
-    if (full_tile && !edge)
-      tmaB_consumer<T, K, true>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
-    else
-      tmaB_consumer<T, K, false, WRAP, UNI>(p, g, o, x_new, r, alpha, stages, full, empty, y0, z0, x0, x1, acc);
+    phaseB_consume<T, K, WRAP, UNI, C::STAGE_B, HALO>(p, g, o, x_new, r, alpha, st, halo_seq, stages, full, empty,
+                                                      item_ring, acc, 0u);
   }
-  if (p.halo.on) {
-    // this CTA's rows of the first / last owned plane are in the neighbour's landing zone: count it in; the
-    // last CTA of a plane publishes the sequence number in the neighbour's flag word (release at system scope:
-    // every thread fences its remote stores before the CTA's count, the publisher fences again before the flag)
-    const bool has_lo = p.halo.dst[0] != nullptr && x0 <= g.olo0 && g.olo0 < x1;
-    const bool has_hi = p.halo.dst[1] != nullptr && x0 <= g.ohi0 - 1 && g.ohi0 - 1 < x1;
-    if (has_lo || has_hi) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          if (!(side == 0 ? has_lo : has_hi)) continue;
-          const unsigned int t = atomicAdd(&st->halo_cnt[side], 1u);
-          if (t == (unsigned int)p.halo.tiles - 1u) {
-            atomicExch(&st->halo_cnt[side], 0u);
-            __threadfence_system();
-            *(volatile unsigned long long*)p.halo.flag_dst[side] = halo_seq;
-          }
-        }
-      }
-    }
-  }
-  if (p.signal_halo && zc < p.b_lo + p.b_hi) {
-    // a boundary chunk: its r planes may leave for the neighbour rank as soon as every such CTA is
-    // done (k_wait_halo on the communication stream) while the interior chunks still run
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&st->halo_count, 1u);
-  }
-  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  work_leave(p);
+  const int nblocks = gridDim.x;
+  const int bid = blockIdx.x;
   if (p.fuse_fin) {
     // static shell: this launch also finalizes the iteration; on slabs the two sums first go
     // through the peer-memory all-reduce (p.p2p), single GPU: p.p2p.peers == nullptr
@@ -765,22 +907,22 @@ __device__ __forceinline__ bool halo_wait(const unsigned long long* flag, unsign
 // =========================================================================================
 // phase A
 // =========================================================================================
-template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false>
+template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false, int STRIDE = TmaCfg<T, K>::STAGE_A>
 __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ d_new, T beta, unsigned char* stages,
                                               uint64_t* full, uint64_t* empty, int y0, int z0, int x0,
-                                              int x1, double& acc_out) {
+                                              int x1, double& acc_out, unsigned gi0) {
   typedef TmaCfg<T, K> C;
   constexpr int VEC = C::VEC;
   ConsCtx<T, K> c;
   cons_setup<T, K>(g, c, y0, z0);
-  const bool actx = g.act[0] != 0;
+  constexpr bool actx = true;  // kernel axis 0 is active on every TMA path (plan_tma)
   const long long n12 = (long long)g.n[1] * g.n[2];
   T* dout = d_new + (long long)x0 * n12 + c.goff;
 
-  auto rt = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_A) + c.hoff; };
+  auto rt = [&](int s) { return reinterpret_cast<const T*>(stages + (size_t)s * STRIDE) + c.hoff; };
   auto dt = [&](int s) {
-    return reinterpret_cast<const T*>(stages + (size_t)s * C::STAGE_A + C::HALO_SLOT) + c.hoff;
+    return reinterpret_cast<const T*>(stages + (size_t)s * STRIDE + C::HALO_SLOT) + c.hoff;
   };
   // d_new = r + beta*d on the thread's own cells of the plane in stage s   (linalg.py:141)
   auto own_dn = [&](int s, T (&v)[K::RY][VEC]) {
@@ -808,16 +950,17 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
   T A[K::RY][VEC], B[K::RY][VEC], Cc[K::RY][VEC];
   double acc = 0.0;
 
-  if (actx) {
-    mbar_wait(&full[0], 0);
-    own_dn(0, A);
-    release(0);
+  {
+    const unsigned s0 = gi0 & (C::S - 1), s1 = (gi0 + 1) & (C::S - 1);
+    mbar_wait(&full[s0], (gi0 / C::S) & 1);
+    own_dn(s0, A);
+    release(s0);
+    mbar_wait(&full[s1], ((gi0 + 1) / C::S) & 1);
+    own_dn(s1, B);
+    write_d(B);
   }
-  mbar_wait(&full[1 % C::S], 0);
-  own_dn(1 % C::S, B);
-  write_d(B);
 
-  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, int i) {
+  auto step = [&](T (&vm)[K::RY][VEC], T (&vc)[K::RY][VEC], T (&vp)[K::RY][VEC], int x, unsigned i) {
     const int sn = i & (C::S - 1), sc = (i - 1) & (C::S - 1);
     if (actx) {
       mbar_wait(&full[sn], (i / C::S) & 1);
@@ -870,7 +1013,8 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
     release(sc);
   };
 
-  int x = x0, i = 2;
+  int x = x0;
+  unsigned i = gi0 + 2;
   while (true) {
     step(A, B, Cc, x, i);
     if (++x >= x1) break;
@@ -882,7 +1026,76 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
     if (++x >= x1) break;
     ++i;
   }
-  acc_out = acc;
+  release(i & (C::S - 1));  // the plane above the chunk
+  acc_out += acc;
+}
+
+// ---- phase A over this CTA's work items ------------------------------------------------------------
+template <typename T, typename K, int STRIDE>
+__device__ __forceinline__ unsigned phaseA_produce(const CUtensorMap* tm_r, const CUtensorMap* tm_d,
+                                                   const CUtensorMap* tm_land, const TilePlan& p, const GridDev& g,
+                                                   SolverState* st, unsigned char* stages, uint64_t* full,
+                                                   uint64_t* empty, int* item_ring, unsigned gi) {
+  typedef TmaCfg<T, K> C;
+  // peer-memory halo exchange: the ghost planes of r live in this rank's landing zone (tm_land), written
+  // by the neighbours' previous phase B; wait for their flag (sequence number = epoch at launch - 1)
+  const bool halo_on = p.halo.on != 0;
+  const int gl = (halo_on && g.olo0 > 0) ? g.olo0 - 1 : -2;
+  const int gu = (halo_on && g.ohi0 < g.n[0]) ? g.ohi0 : -2;
+  const unsigned long long need = halo_on ? *(volatile unsigned long long*)&st->epoch - 1ull : 0ull;
+  for (unsigned seq = 0;; ++seq) {
+    const int id = claim_item<C>(p, item_ring, seq, full, empty, gi);
+    if (id < 0) break;
+    const WorkItem w = work_item<C>(p, g, id);
+    const int n = w.x1 - w.x0 + 2;
+    for (int k = 0; k < n; ++k, ++gi) {
+      const int pl = w.x0 - 1 + k;
+      const int s = gi & (C::S - 1);
+      if (k > 0 && gi >= (unsigned)C::S) mbar_wait(&empty[s], ((gi / C::S) - 1) & 1);  // (k == 0: claim_item waited)
+      mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
+      unsigned char* sb = stages + (size_t)s * STRIDE;
+      const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+      const bool ghost = (pl == gl) || (pl == gu);
+      if (ghost) {
+        const int side = (pl == gl) ? 0 : 1;
+        if (!halo_wait(p.halo.flag_src + side, need)) {
+          st->done = 1;  // the neighbour never delivered (watchdog): end the solve, the host reports it
+          st->status = PA_PEER_LOST;
+        }
+      }
+      for (int b = 0; b < C::NB; ++b) {
+        const int zb = w.z0 + b * C::OBOXZ;
+        if (ghost)
+          tma_load_3d(sb + b * C::HBOX_SLOT, tm_land, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1,
+                      p.halo.slot * 2 + ((pl == gl) ? 0 : 1), &full[s]);
+        else
+          tma_load_3d(sb + b * C::HBOX_SLOT, tm_r, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+        tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, tm_d, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+      }
+    }
+  }
+  return gi;
+}
+
+template <typename T, typename K, bool WRAP, bool UNI, int STRIDE>
+__device__ __forceinline__ unsigned phaseA_consume(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
+                                                   T* __restrict__ d_new, T beta, unsigned char* stages,
+                                                   uint64_t* full, uint64_t* empty, const int* item_ring, double& acc,
+                                                   unsigned gi) {
+  typedef TmaCfg<T, K> C;
+  for (unsigned seq = 0;; ++seq) {
+    const int id = take_item<C>(item_ring, seq, full, gi);
+    if (id < 0) break;
+    const WorkItem w = work_item<C>(p, g, id);
+    if (w.lean)
+      tmaA_consumer<T, K, true, false, false, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0, w.x1,
+                                                      acc, gi);
+    else
+      tmaA_consumer<T, K, false, WRAP, UNI, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0, w.x1,
+                                                    acc, gi);
+    gi += (unsigned)(w.x1 - w.x0 + 2);
+  }
+  return gi;
 }
 
 template <typename T, typename K, bool WRAP, bool UNI>
@@ -900,73 +1113,214 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * C::STAGE_A);
   uint64_t* empty = full + C::S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int y0 = blockIdx.y * C::TY, z0 = blockIdx.x * C::TZ;
-  const int zc = (int)blockIdx.z;
-  const int x0 = tile_chunk(p, zc) * p.cx;
-  const int x1 = min(x0 + p.cx, g.n[0]);
-  const bool actx = g.act[0] != 0;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], C::CWARPS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
+  __shared__ int item_ring[kItemRing];
+  pipe_init<C>(full, empty);
   double acc[1] = {0.0};
   if (warp == C::CWARPS) {
-    if (lane == 0) {
-      const int n = x1 - x0 + 2;
-      // peer-memory halo exchange: the ghost planes of r live in this rank's landing zone (tm_land), written
-      // by the neighbours' previous phase B; wait for their flag (sequence number = epoch at launch - 1)
-      const bool halo_on = p.halo.on != 0;
-      const int gl = (halo_on && g.olo0 > 0) ? g.olo0 - 1 : -2;
-      const int gu = (halo_on && g.ohi0 < g.n[0]) ? g.ohi0 : -2;
-      const unsigned long long need = halo_on ? *(volatile unsigned long long*)&st->epoch - 1ull : 0ull;
-      for (int i = 0; i < n; ++i) {
-        if (!actx && i != 1) continue;
-        const int pl = x0 - 1 + i;
-        const int s = i & (C::S - 1);
-        if (i >= C::S) mbar_wait(&empty[s], ((i / C::S) - 1) & 1);
-        mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
-        unsigned char* sb = stages + (size_t)s * C::STAGE_A;
-        const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
-        const bool ghost = (pl == gl) || (pl == gu);
-        if (ghost) {
-          const int side = (pl == gl) ? 0 : 1;
-          if (!halo_wait(p.halo.flag_src + side, need)) {
-            st->done = 1;  // the neighbour never delivered (watchdog): end the solve, the host reports it
-            st->status = PA_PEER_LOST;
-          }
-        }
-        for (int b = 0; b < C::NB; ++b) {
-          const int zb = z0 + b * C::OBOXZ;
-          if (ghost)
-            tma_load_3d(sb + b * C::HBOX_SLOT, &tm_land, zb - C::HZ, C::FLAT ? 0 : y0 - 1,
-                        p.halo.slot * 2 + ((pl == gl) ? 0 : 1), &full[s]);
-          else
-            tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
-          tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, &tm_d, zb - C::HZ, C::FLAT ? 0 : y0 - 1, xw, &full[s]);
-        }
-      }
-    }
+    if (lane == 0)
+      phaseA_produce<T, K, C::STAGE_A>(&tm_r, &tm_d, &tm_land, p, g, st, stages, full, empty, item_ring, 0u);
   } else {
     const T beta = (T)st->scal[S_BETA];
-    const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
-    if (full_tile && !edge)
-      tmaA_consumer<T, K, true>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
-    else
-      tmaA_consumer<T, K, false, WRAP, UNI>(p, g, o, d_new, beta, stages, full, empty, y0, z0, x0, x1, acc[0]);
+    phaseA_consume<T, K, WRAP, UNI, C::STAGE_A>(p, g, o, d_new, beta, stages, full, empty, item_ring, acc[0], 0u);
   }
-  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  work_leave(p);
+  const int nblocks = gridDim.x;
+  const int bid = blockIdx.x;
   {
     P2PDev pp = p.p2p;  // slabs: d.Ad summed over the ranks right here when the peer mailboxes exist
     pp.slot0 = R_A;
     pp.count = 1;
     const int stage = (p.dist && pp.peers == nullptr) ? ST_NONE : ST_CG_DAD;
     grid_reduce<1>(acc, partials, nblocks, bid, &st->ticket[0], StoreSums<T, 1>{st, R_A, stage, 0, pp});
+  }
+}
+
+// =========================================================================================
+// L2-resident grids: the WHOLE CG solve as one cooperative launch of the two phases
+// =========================================================================================
+// Below a few million cells the six CG vectors stay in the 126 MB L2 and an iteration of the two fused kernels
+// is bound by launch + pipeline-fill + reduction latency (1024^2: 16 us per kernel for 3 us of L2 traffic).
+// Here the CTAs stay resident for the whole solve: per iteration phase A and phase B run over dynamically
+// claimed items with the same producer / consumer code as the stand-alone kernels, the mbarrier ring keeps
+// running from phase to phase, and each phase ends in ONE grid-wide step that is reduction, scalar stage and
+// barrier at once (last-arriver ticket, then a generation word everybody else spins on).  Preconditions
+// (host): single GPU, static shell (every face Dirichlet: no BC work inside the loop), no periodic axis 1/2.
+template <int NS, typename Fin>
+__device__ __forceinline__ void grid_reduce_sync(double (&v)[NS], double* partials, SolverState* st, unsigned int& gen,
+                                                 WorkCounter* work, Fin fin) {
+  __shared__ bool last_cta;
+  __shared__ double red_smem2[NS * 32];
+  block_sum<NS>(v, red_smem2);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) partials[s * kMaxPartials + blockIdx.x] = v[s];
+    __threadfence();
+    last_cta = atomicAdd(&st->ticket[0], 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  ++gen;
+  if (last_cta) {
+    __threadfence();
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      acc[s] = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc[s] += __ldcg(&partials[s * kMaxPartials + b]);
+    }
+    block_sum<NS>(acc, red_smem2);
+    if (threadIdx.x == 0) {
+      st->ticket[0] = 0u;
+      work->next = 0u;  // every CTA has left the phase's item walk
+      fin(acc);
+      __threadfence();
+      *(volatile unsigned int*)&st->ticket[5] = gen;  // release the others
+    }
+  } else if (threadIdx.x == 0) {
+    while (*(volatile unsigned int*)&st->ticket[5] != gen) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T, typename K, bool UNI>
+__global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
+k_cg_coop_tma(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+              const __grid_constant__ CUtensorMap tm_r_own, const __grid_constant__ CUtensorMap tm_r_halo,
+              const __grid_constant__ CUtensorMap tm_d0, const __grid_constant__ CUtensorMap tm_d1, TilePlan p,
+              GridDev g, OpDev<T> o, T* __restrict__ xa, T* __restrict__ xb, T* __restrict__ r, T* __restrict__ d0,
+              T* __restrict__ d1, SolverState* st, double* partials) {
+  typedef TmaCfg<T, K> C;
+  constexpr int STRIDE = C::STAGE_A > C::STAGE_B ? C::STAGE_A : C::STAGE_B;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  unsigned char* stages = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)C::S * STRIDE);
+  uint64_t* empty = full + C::S;
+  __shared__ int item_ring[kItemRing];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = warp == C::CWARPS && lane == 0;
+  pipe_init<C>(full, empty);
+  WorkCounter* work = &g_work_pool[p.work_slot];
+  unsigned gi = 0, seq = 0, gen = 0;  // pipeline counter, item sequence number, barrier generation
+  int parity = 0;
+  while (true) {
+    // ---- phase A: d_new = r + beta d_old ; d_new . A(d_new) -> alpha
+    {
+      const CUtensorMap* tm_d = parity ? &tm_d1 : &tm_d0;
+      T* d_new = parity ? d0 : d1;
+      double acc[1] = {0.0};
+      if (warp == C::CWARPS) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");  // r, d of the previous phase -> TMA reads
+          for (;; ++seq) {
+            const int id = claim_item<C>(p, item_ring, seq, full, empty, gi);
+            if (id < 0) {
+              ++seq;
+              ++gi;  // the sentinel took one barrier phase
+              break;
+            }
+            const WorkItem w = work_item<C>(p, g, id);
+            const int n = w.x1 - w.x0 + 2;
+            for (int k = 0; k < n; ++k, ++gi) {
+              const int pl = w.x0 - 1 + k;
+              const int s = gi & (C::S - 1);
+              if (k > 0 && gi >= (unsigned)C::S) mbar_wait(&empty[s], ((gi / C::S) - 1) & 1);
+              mbar_expect_tx(&full[s], (uint32_t)(2 * C::HALO_BYTES));
+              unsigned char* sb = stages + (size_t)s * STRIDE;
+              const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+              for (int b = 0; b < C::NB; ++b) {
+                const int zb = w.z0 + b * C::OBOXZ;
+                tma_load_3d(sb + b * C::HBOX_SLOT, &tm_r_halo, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+                tma_load_3d(sb + C::HALO_SLOT + b * C::HBOX_SLOT, tm_d, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+              }
+            }
+          }
+        }
+      } else {
+        const T beta = (T)*(volatile double*)&st->scal[S_BETA];
+        for (;; ++seq) {
+          const int id = take_item<C>(item_ring, seq, full, gi);
+          if (id < 0) {
+            ++seq;
+            consumer_release_sentinel<C>(empty, gi);
+            ++gi;
+            break;
+          }
+          const WorkItem w = work_item<C>(p, g, id);
+          if (w.lean)
+            tmaA_consumer<T, K, true, false, false, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0,
+                                                            w.x1, acc[0], gi);
+          else
+            tmaA_consumer<T, K, false, false, UNI, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0,
+                                                           w.x1, acc[0], gi);
+          gi += (unsigned)(w.x1 - w.x0 + 2);
+        }
+      }
+      grid_reduce_sync<1>(acc, partials, st, gen, work, StoreSums<T, 1>{st, R_A, ST_CG_DAD, 0});
+    }
+    // ---- phase B: x_new = x + alpha d ; r -= alpha A(d) ; sums -> beta, tol, itr, done
+    {
+      const CUtensorMap* tm_d = parity ? &tm_d0 : &tm_d1;  // the d phase A has just written
+      const CUtensorMap* tm_x = parity ? &tm_x1 : &tm_x0;
+      T* x_new = parity ? xa : xb;
+      double acc[2] = {0.0, 0.0};
+      if (warp == C::CWARPS) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (;; ++seq) {
+            const int id = claim_item<C>(p, item_ring, seq, full, empty, gi);
+            if (id < 0) {
+              ++seq;
+              ++gi;
+              break;
+            }
+            const WorkItem w = work_item<C>(p, g, id);
+            const int n = w.x1 - w.x0 + 2;
+            for (int k = 0; k < n; ++k, ++gi) {
+              const int pl = w.x0 - 1 + k;
+              const int s = gi & (C::S - 1);
+              if (k > 0 && gi >= (unsigned)C::S) mbar_wait(&empty[s], ((gi / C::S) - 1) & 1);
+              const bool inner = (pl >= w.x0 && pl < w.x1);
+              mbar_expect_tx(&full[s], (uint32_t)(C::HALO_BYTES + (inner ? 2 * C::OWN_BYTES : 0)));
+              unsigned char* sb = stages + (size_t)s * STRIDE;
+              const int xw = pl < 0 ? pl + g.n[0] : (pl >= g.n[0] ? pl - g.n[0] : pl);
+              for (int b = 0; b < C::NB; ++b) {
+                const int zb = w.z0 + b * C::OBOXZ;
+                tma_load_3d(sb + b * C::HBOX_SLOT, tm_d, zb - C::HZ, C::FLAT ? 0 : w.y0 - 1, xw, &full[s]);
+                if (inner) {
+                  tma_load_3d(sb + C::HALO_SLOT + b * C::OBOX_SLOT, tm_x, zb, w.y0, xw, &full[s]);
+                  tma_load_3d(sb + C::HALO_SLOT + C::OWN_SLOT + b * C::OBOX_SLOT, &tm_r_own, zb, w.y0, xw, &full[s]);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        const T alpha = (T)*(volatile double*)&st->scal[S_ALPHA];
+        for (;; ++seq) {
+          const int id = take_item<C>(item_ring, seq, full, gi);
+          if (id < 0) {
+            ++seq;
+            consumer_release_sentinel<C>(empty, gi);
+            ++gi;
+            break;
+          }
+          const WorkItem w = work_item<C>(p, g, id);
+          if (w.lean)
+            tmaB_consumer<T, K, true, false, false, STRIDE>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
+                                                            w.x0, w.x1, acc, gi);
+          else
+            tmaB_consumer<T, K, false, false, UNI, STRIDE>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
+                                                           w.x0, w.x1, acc, gi);
+          gi += (unsigned)(w.x1 - w.x0 + 2);
+        }
+      }
+      if (threadIdx.x == 0 && blockIdx.x == 0) st->sum[R_SHELL] = 0.0;  // static shell
+      grid_reduce_sync<2>(acc, partials, st, gen, work, StoreSums<T, 2>{st, R_A, ST_CG_FIN, 0});
+    }
+    if (*(volatile int*)&st->done) break;
+    parity ^= 1;
   }
 }
 
@@ -995,6 +1349,7 @@ static __global__ void k_wait_halo(SolverState* st, unsigned int nboundary) {
 }
 
 // number of boundary CTAs of a sub == 3 launch
+// (work items, now that the kernels are persistent)
 inline unsigned int tma_boundary_ctas(const TmaPlan& tp, const GridDev& g) {
   const int c_lo = g.olo0 / tp.tile.cx, c_hi = (g.ohi0 - 1) / tp.tile.cx;
   return (unsigned int)((c_lo + 1 + tp.tile.chunks - c_hi) * tp.tile.tiles_y * tp.tile.tiles_z);
@@ -1016,8 +1371,11 @@ static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     cudaFuncSetAttribute(k_cg_phaseA_tma<T, K, WRAP, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
     attr = true;
   }
-  dim3 grid(tp.tile.tiles_z, tp.tile.tiles_y, tp.tile.chunks);
   TilePlan tile = tp.tile;
+  tile.nz = tile.chunks;
+  tile.work_slot = next_work_slot();
+  tile.first_static = 1;
+  dim3 grid(persistent_grid(tile, tile.nz));
   tile.src0 = tp.r_ptr;
   tile.src1 = tp.d_ptr[parity];
   if (tile.halo.on) {
@@ -1046,14 +1404,14 @@ void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, c
   }
 }
 
-template <typename T, typename K, bool WRAP, bool UNI>
+template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false>
 static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* x_new, T* r, SolverState* st, double* partials, int sub) {
   typedef TmaCfg<T, K> C;
   static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
   bool& attr = attr_dev[current_device()];
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
+    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP, UNI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;
   }
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
@@ -1080,31 +1438,95 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     tile.signal_halo = sub == 3 ? 1 : 0;  // 3: each boundary CTA counts itself in for k_wait_halo (NCCL exchange)
   }
   if (tile.halo.on) tile.halo.slot = parity;
-  dim3 grid(tile.tiles_z, tile.tiles_y, nz);
-  k_cg_phaseB_tma<T, K, WRAP, UNI><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
+  tile.nz = nz;
+  tile.work_slot = next_work_slot();
+  tile.first_static = 1;
+  dim3 grid(persistent_grid(tile, nz));
+  k_cg_phaseB_tma<T, K, WRAP, UNI, HALO><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
                                                            g, eq.op[0], x_new, r, st, partials);
 }
 
 template <typename T>
 void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                           int parity, T* x_new, T* r, SolverState* st, double* partials, int sub = 0) {
-  // three variants of the general (edge-tile) path: periodic wrap, uniform coefficients (every face of
-  // axes 1/2 Dirichlet or periodic: 10 % fewer instructions on the edge tiles), neither
-  if (tma_flat(g)) {
-    if (tp.tile.wrap)
-      launch_cg_phaseB_tma_k<T, KFlat, true, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-    else if (tp.coef_uniform)
-      launch_cg_phaseB_tma_k<T, KFlat, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-    else
-      launch_cg_phaseB_tma_k<T, KFlat, false, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-  } else {
-    if (tp.tile.wrap)
-      launch_cg_phaseB_tma_k<T, KStd, true, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-    else if (tp.coef_uniform)
-      launch_cg_phaseB_tma_k<T, KStd, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
-    else
-      launch_cg_phaseB_tma_k<T, KStd, false, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);
+  // variants of the general (edge-tile) path: periodic wrap, uniform coefficients (every face of axes 1/2
+  // Dirichlet or periodic: 10 % fewer instructions on the edge tiles), neither; and, on slabs with the
+  // peer-memory halo exchange (never together with wrap, api.cu halo_dev), the HALO stores
+  const bool halo = tp.tile.halo.on != 0;
+#define PA_LAUNCH_B(KK)                                                                                      \
+  do {                                                                                                       \
+    if (tp.tile.wrap)                                                                                        \
+      launch_cg_phaseB_tma_k<T, KK, true, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);         \
+    else if (tp.coef_uniform && halo)                                                                        \
+      launch_cg_phaseB_tma_k<T, KK, false, true, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);   \
+    else if (tp.coef_uniform)                                                                                \
+      launch_cg_phaseB_tma_k<T, KK, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);         \
+    else if (halo)                                                                                           \
+      launch_cg_phaseB_tma_k<T, KK, false, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);  \
+    else                                                                                                     \
+      launch_cg_phaseB_tma_k<T, KK, false, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);        \
+  } while (0)
+  if (tma_flat(g))
+    PA_LAUNCH_B(KFlat);
+  else
+    PA_LAUNCH_B(KStd);
+#undef PA_LAUNCH_B
+}
+
+// co-resident CTAs of the cooperative CG kernel on this device (0: cooperative launch unavailable)
+template <typename T, typename K, bool UNI>
+static int cg_coop_max_blocks() {
+  typedef TmaCfg<T, K> C;
+  constexpr size_t SMEM = (size_t)C::S * (C::STAGE_A > C::STAGE_B ? C::STAGE_A : C::STAGE_B) + C::BAR_BYTES + 128;
+  int dev = 0, coop = 0, per_sm = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!coop) return 0;
+  static bool attr_dev[kMaxDevices] = {};
+  bool& attr = attr_dev[current_device()];
+  if (!attr) {
+    cudaFuncSetAttribute(k_cg_coop_tma<T, K, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    attr = true;
   }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop_tma<T, K, UNI>, C::THREADS, SMEM) != cudaSuccess)
+    return 0;
+  return per_sm * sms;
+}
+
+template <typename T, typename K, bool UNI>
+static bool launch_cg_coop_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq, T* xa, T* xb,
+                                 T* r, T* d0, T* d1, SolverState* st, double* partials) {
+  typedef TmaCfg<T, K> C;
+  constexpr size_t SMEM = (size_t)C::S * (C::STAGE_A > C::STAGE_B ? C::STAGE_A : C::STAGE_B) + C::BAR_BYTES + 128;
+  const int maxb = cg_coop_max_blocks<T, K, UNI>();
+  if (maxb <= 0) return false;
+  TilePlan tile = tp.tile;
+  tile.nz = tile.chunks;
+  tile.work_slot = next_work_slot();
+  tile.first_static = 0;  // (the item sequence number runs on over the phases)
+  tile.fuse_fin = 1;
+  int grid = persistent_grid(tile, tile.nz);
+  if (grid > maxb) grid = maxb;
+  GridDev gg = g;
+  OpDev<T> o = eq.op[0];
+  void* args[] = {(void*)&tp.x_own[0], (void*)&tp.x_own[1], (void*)&tp.r_own, (void*)&tp.r_halo, (void*)&tp.d_halo[0],
+                  (void*)&tp.d_halo[1], (void*)&tile, (void*)&gg, (void*)&o, (void*)&xa, (void*)&xb, (void*)&r,
+                  (void*)&d0, (void*)&d1, (void*)&st, (void*)&partials};
+  return cudaLaunchCooperativeKernel((void*)k_cg_coop_tma<T, K, UNI>, dim3(grid), dim3(C::THREADS), args, SMEM, s) ==
+         cudaSuccess;
+}
+
+// the whole CG solve (after the residual init) as ONE cooperative launch; false: not available, use the loop
+template <typename T>
+bool launch_cg_coop_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq, T* xa, T* xb, T* r,
+                        T* d0, T* d1, SolverState* st, double* partials) {
+  if (tp.tile.wrap) return false;
+  if (tma_flat(g))
+    return tp.coef_uniform ? launch_cg_coop_tma_k<T, KFlat, true>(s, tp, g, eq, xa, xb, r, d0, d1, st, partials)
+                           : launch_cg_coop_tma_k<T, KFlat, false>(s, tp, g, eq, xa, xb, r, d0, d1, st, partials);
+  return tp.coef_uniform ? launch_cg_coop_tma_k<T, KStd, true>(s, tp, g, eq, xa, xb, r, d0, d1, st, partials)
+                         : launch_cg_coop_tma_k<T, KStd, false>(s, tp, g, eq, xa, xb, r, d0, d1, st, partials);
 }
 
 }  // namespace pa

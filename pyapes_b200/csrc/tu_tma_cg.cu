@@ -5,7 +5,9 @@ namespace pa {
   template void launch_cg_phaseA_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&, int, T*, \
                                         SolverState*, double*);                                                \
   template void launch_cg_phaseB_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&, int, T*, \
-                                        T*, SolverState*, double*, int);
+                                        T*, SolverState*, double*, int);                                       \
+  template bool launch_cg_coop_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&, T*, T*, T*, T*, \
+                                      T*, SolverState*, double*);
 PA_INST(double)
 PA_INST(float)
 #undef PA_INST

@@ -1,4 +1,5 @@
-"""CG on small grids: per-iteration latency of the kernel variants (0 auto, 1 generic, 3 persistent)."""
+"""CG on small grids: per-iteration latency of the kernel variants (0 auto, 3 persistent generic kernel,
+4 fused TMA kernels as separate launches, 5 cooperative whole-solve TMA kernel)."""
 import json, os, sys, warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -35,8 +36,10 @@ def case(shape, variant, iters=100, dtype="double"):
     return {"shape": shape, "variant": variant, "us_per_iter": round(best / iters * 1e3, 2),
             "GLUP/s": round(n * iters / best / 1e6, 2), "tol": res["tol"], "sum": res["sum"]}
 
-for shape in ([128, 128], [256, 256], [512, 512], [768, 768], [1024, 1024], [32, 32, 32], [48, 48, 48], [64, 64, 64], [96, 96, 96]):
-    for v in (0, 3):
+for shape in ([64, 64], [128, 128], [256, 256], [512, 512], [1024, 1024], [1448, 1448], [32, 32, 32], [64, 64, 64], [96, 96, 96], [128, 128, 128]):
+    for v in (3, 4, 5):
+        if v == 3 and shape[0] ** len(shape) > 300000:
+            continue
         a, b = case(shape, v, 60), case(shape, v, 180)
         pure = (b["us_per_iter"] * 180 - a["us_per_iter"] * 60) / 120  # setup cancels
         print(json.dumps({"shape": shape, "variant": v, "us_per_iter_180": b["us_per_iter"], "us_per_iter_marginal": round(pure, 2)}), flush=True)
