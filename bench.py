@@ -639,7 +639,7 @@ def run_ours(args):
     # --- outside the timed regions: parity at N > 1, config 5 -----------------------------------
     hbm, peak_src = peaks()
     parity, secondary = {}, {}
-    if world > 1:
+    if world > 1 and not args.no_secondary:
         try:
             pd = parity_dist(rank, world, dev)
             if pd:
@@ -670,7 +670,9 @@ def run_ours(args):
     ach_a = B_PER_CELL_PHASE_A * cells / (kt["phaseA_ms"] * 1e-3) / 1e9
     traffic, traffic_note = ncu_traffic(f"phaseB_{n}")
 
-    if world == 1:
+    if world == 1 and args.no_secondary:
+        cpu_obj = None
+    elif world == 1:
         # cpu_baseline (rank 0 at N = 1 only) doubles as the config-2-size parity oracle
         cpu = cpu_baseline(args.cpu_n, args.cpu_iters, keep=True)
         try:
@@ -727,7 +729,7 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_obj
     else:
         out["cpu_baseline"] = {"value": None, "unit": "GLUP/s", "cores": 0, "kind": "see --impl reference",
-                               "sample": "not run at N > 1 (rank 0 at N = 1 only)"}
+                               "sample": "not run (rank 0 at N = 1 only; skipped by --no-secondary)"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -744,6 +746,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-n", type=int, default=256, help="grid of the bounded CPU sample (reference arm)")
     ap.add_argument("--cpu-iters", type=int, default=20, help="CG iterations of the CPU sample (~10-30 s)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="headline only: skip `secondary`, `parity` and the CPU baseline (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

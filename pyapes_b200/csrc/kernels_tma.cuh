@@ -470,7 +470,10 @@ __device__ __forceinline__ void lds_vec(const T* p, T (&v)[VecOf<T>::N]) {
   for (int e = 0; e < VecOf<T>::N; ++e) v[e] = s[e];
 }
 
-template <typename T, typename K, bool LEAN>
+// STREAM: write-once output that nobody re-reads soon (the explicit operators): st.global.cs, so that the
+// output lines are the first to leave L2 and the input's halo rows survive until the neighbouring tile reads
+// them (ncu, 512^3 Grad with plain stores: 1.48 GB read for 1.07 GB of input)
+template <typename T, typename K, bool LEAN, bool STREAM = false>
 __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, const T (&v)[VecOf<T>::N]) {
   typedef typename VecOf<T>::type V;
   constexpr int N = VecOf<T>::N;
@@ -480,7 +483,10 @@ __device__ __forceinline__ void stg_row(T* p, const ConsCtx<T, K>& c, int k, con
     T* s = reinterpret_cast<T*>(&q);
 #pragma unroll
     for (int e = 0; e < N; ++e) s[e] = v[e];
-    *reinterpret_cast<V*>(p) = q;
+    if (STREAM)
+      __stcs(reinterpret_cast<V*>(p), q);
+    else
+      *reinterpret_cast<V*>(p) = q;
   } else {
 #pragma unroll
     for (int e = 0; e < N; ++e)

@@ -292,12 +292,12 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
             g2[e] = s;
           }
           T* row = op_ + (long long)k * g.n[2];
-          stg_row<T, K, LEAN>(row, c, k, g0);
+          stg_row<T, K, LEAN, true>(row, c, k, g0);
           if (!K::FLAT) {
-            stg_row<T, K, LEAN>(row + g.cells, c, k, g1);
-            stg_row<T, K, LEAN>(row + 2 * g.cells, c, k, g2);
+            stg_row<T, K, LEAN, true>(row + g.cells, c, k, g1);
+            stg_row<T, K, LEAN, true>(row + 2 * g.cells, c, k, g2);
           } else {
-            stg_row<T, K, LEAN>(row + g.cells, c, k, g2);
+            stg_row<T, K, LEAN, true>(row + g.cells, c, k, g2);
           }
         }
         op_ += n12;
@@ -372,7 +372,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           }
         }
       }
-      stg_row<T, K, LEAN>(op_ + (long long)k * g.n[2], c, k, o);
+      stg_row<T, K, LEAN, MODE == PW_APPLY>(op_ + (long long)k * g.n[2], c, k, o);
       if (MODE == PW_RESID && op2_) stg_row<T, K, LEAN>(op2_ + (long long)k * g.n[2], c, k, o);
     }
     s0.flush();

@@ -159,7 +159,11 @@ class Discretizer:
             self.A_coeffs = self.build_A_coeffs(var)
             self.rhs_adj = self.adjust_rhs(var)
             return self.apply(self.A_coeffs, var)
-        assert isinstance(args[0], (Field, Tensor, float)), "FDC: for var_j, Field, Tensor and float are allowed!"
+        from pyapes_b200.variables.container import Hess, Jac
+
+        assert isinstance(args[0], (Field, Tensor, float, Jac, Hess)), (
+            "FDC: for var_j, Field, Tensor, float, Jac and Hess are allowed!"
+        )
         assert isinstance(args[1], Field), "FDC: only `Field` is allowed for var_i!"
         self.A_coeffs = self.build_A_coeffs(args[0], args[1], config=self.config)
         self.rhs_adj = self.adjust_rhs(args[0], args[1], config=self.config)
@@ -219,8 +223,18 @@ def _check_limiter(config: DivConfigType | None) -> str:
     return "none"
 
 
-def _adv_of(var_j, var_i: Field):
-    """fdc.py:775-792 -> float (constant) or a (1,*nx) tensor."""
+def _adv_of(var_j, var_i: Field, limiter: str = "none"):
+    """fdc.py:775-792 -> float (constant) or a (1,*nx) tensor.
+
+    Jac-driven advection (fdc.py:639-664,730-735,760-763): for a scalar `var_i` the reference takes
+    `adv[n2d[i]]` with i running over var.dim == 1 only, i.e. the FIRST component of the Jacobian on every
+    mesh axis -- `div(jac, var)` is bit-identical to `div(jac.x[None], var)` [probed on the reference,
+    tests/golden/make_golden_jacdiv.py].  A Hess does not get through the reference either: limiter "upwind"
+    raises NotImplementedError (fdc.py:650-653) and "none" dies in adjust_rhs with AttributeError; both are
+    reproduced."""
+    from pyapes_b200.geometry.basis import n2d_coord
+    from pyapes_b200.variables.container import Hess, Jac
+
     if isinstance(var_j, (float, int)) and not isinstance(var_j, bool):
         return float(var_j)
     if isinstance(var_j, Tensor):
@@ -228,9 +242,21 @@ def _adv_of(var_j, var_i: Field):
         return var_j
     if isinstance(var_j, Field):
         return var_j()
-    raise NotImplementedError(
-        "pyapes_b200 FDC.Div: Jac/Hess-driven advection is out of scope (SURVEY.md §8(f) item 3)"
-    )
+    if isinstance(var_j, Jac):
+        first = n2d_coord(var_i.mesh.coord_sys)[0]
+        return var_j[first].unsqueeze(0)
+    if isinstance(var_j, Hess):
+        if limiter == "upwind":
+            raise NotImplementedError(
+                "FDC: Upwind limiter is not implemented for Hessians and Jacobians advection term."
+            )
+        if any(bc.bc_type in ("neumann", "symmetry") for bc in (var_i.bcs or [])):
+            raise IndexError(
+                "FDC Div: central scheme with Neumann/Symmetry faces is not usable "
+                "(the reference raises IndexError in fdc.py:583-584 as well)"
+            )
+        raise AttributeError("'Hess' object has no attribute 'x'")
+    raise TypeError(f"FDC Div: unsupported advection term {type(var_j).__name__}")
 
 
 class Div(Discretizer):
@@ -244,7 +270,7 @@ class Div(Discretizer):
     def build_A_coeffs(var_j, var_i: Field, config: DiscretizerConfigType):
         assert "div" in config, "FDC Div: config should contain 'div' key."
         limiter = _check_limiter(config["div"])
-        adv = _adv_of(var_j, var_i)
+        adv = _adv_of(var_j, var_i, limiter)
         if isinstance(adv, float):
             return L.div_star_const(adv, var_i.nx, var_i.mesh._dx, var_i.bcs, var_i().dtype, limiter, _rz_x(var_i))
         if var_i.mesh.coord_sys == "rz":
@@ -260,7 +286,7 @@ class Div(Discretizer):
             return torch.zeros_like(var_i())
         assert "div" in config, "FDC Div: config should contain 'div' key."
         limiter = _check_limiter(config["div"])
-        adv = _adv_of(var_j, var_i)
+        adv = _adv_of(var_j, var_i, limiter)
         if isinstance(adv, float):
             adv = torch.ones_like(var_i()) * adv
         if limiter == "none":

@@ -154,6 +154,7 @@ class Div(Operators):
 
     def __call__(self, *inputs: Any) -> "Div":
         if len(inputs) == 2:
+            # (a Jac / Hess is an FDC-level argument only: the reference asserts here as well, fdm.py:255-259)
             assert isinstance(inputs[0], (float, Tensor, Field)), (
                 "FDM Grad: if additional parameter is provided, it must be a float or Tensor or Field!"
             )
@@ -174,9 +175,9 @@ class Div(Operators):
     @staticmethod
     def Aop(var_j, config: DiscretizerConfigType, var_i: Field, A_coeffs) -> Tensor:
         fdc = FDC(config)
-        if isinstance(var_j, (Tensor, float)):
-            return fdc.div.apply(A_coeffs, var_i)
-        return fdc.div.apply(fdc.div.build_A_coeffs(var_j, var_i, config), var_i)
+        if isinstance(var_j, Field):  # live field: the coefficients follow it (fdm.py:306-312)
+            return fdc.div.apply(fdc.div.build_A_coeffs(var_j, var_i, config), var_i)
+        return fdc.div.apply(A_coeffs, var_i)
 
 
 def _no_adjust(var: Field) -> Tensor:

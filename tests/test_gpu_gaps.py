@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CALL = U.load("callables.pt")
+JACDIV = U.load("jacdiv.pt")
 SOL = {c["name"]: c for c in U.load("solvers.pt")}
 
 
@@ -247,3 +248,35 @@ def test_reference_own_solver_tests_pass_unmodified():
     assert out.returncode == 0, tail
     assert " passed" in out.stdout and "failed" not in out.stdout, tail
     assert "pyapes_alias: pyapes.solver.ops -> pyapes_b200.solver.ops" in out.stdout, tail
+
+
+@pytest.mark.parametrize("case", JACDIV, ids=[c["name"] for c in JACDIV])
+def test_jac_driven_div_fixtures(case):
+    """`FDC().div(jac, var)` (fdc.py:639-664,730-735) against the real reference, and the
+    reference's own failures for a Hess / for FDM().div(jac, ...)."""
+    from pyapes_b200.solver.fdc import FDC, hessian, jacobian
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.variables import Field
+
+    mesh, var = U.product_field(case, DEV)
+    var.set_var_tensor(case["phi"].to(DEV).clone())
+    other = Field("q", 1, mesh, None)
+    other.set_var_tensor(case["q"].to(DEV).clone())
+    jac, hess = jacobian(other), hessian(other)
+    out = case["out"]
+    for lim in ("upwind", "none"):
+        if f"div_jac_{lim}" not in out:
+            continue
+        fdc = FDC({"div": {"limiter": lim, "edge": False}})
+        got = fdc.div(jac, var)
+        assert torch.equal(got.cpu(), out[f"div_jac_{lim}"]), lim
+        assert torch.equal(fdc.div.rhs_adj.cpu(), out[f"div_jac_{lim}_rhs_adj"]), lim
+    errors = {"AttributeError": AttributeError, "NotImplementedError": NotImplementedError, "IndexError": IndexError}
+    for lim, err in out["hess_errors"].items():
+        with pytest.raises(errors[err]):
+            FDC({"div": {"limiter": lim, "edge": False}}).div(hess, var)
+    assert out["fdm_div_accepts_jac"] is False
+    with pytest.raises(AssertionError):
+        FDM({"div": {"limiter": "upwind", "edge": False}}).div(jac, var)
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+    torch.set_default_dtype(torch.float64)

@@ -14,6 +14,7 @@ SOL = U.load("solvers.pt")
 EDGES = U.load("edges.pt")
 RZ = U.load("rz_ops.pt")
 TILES = U.load("ops_tiles.pt")
+JACDIV = U.load("jacdiv.pt")
 
 
 @pytest.mark.parametrize("case", OPS, ids=[c["name"] for c in OPS])
@@ -106,6 +107,23 @@ def test_tile_fixtures(case):
     assert sorted(got) == sorted(case["out"])
     for key, ref in case["out"].items():
         assert torch.equal(got[key], ref), key
+
+
+@pytest.mark.parametrize("case", JACDIV, ids=[c["name"] for c in JACDIV])
+def test_jac_driven_div_fixtures(case):
+    """fdc.py:730-735,760-763 for a scalar field: the advection speed of `div(jac, var)` is the Jacobian's FIRST
+    component on every axis."""
+    torch.set_default_dtype(U.TDTYPE[case["spec"]["dtype"]])
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    phi, q, out = case["phi"].clone(), case["q"].clone(), case["out"]
+    adv = O.jacobian(q, dx)[0].unsqueeze(0)
+    for lim in ("upwind", "none"):
+        if f"div_jac_{lim}" not in out:
+            continue
+        got = O.apply_scalar_op(O.div_coeffs(adv, phi, dx, bcs, lim), phi)
+        assert torch.equal(got, out[f"div_jac_{lim}"]), lim
+        assert torch.equal(O.div_rhs_adjust(adv, phi, dx, bcs, lim), out[f"div_jac_{lim}_rhs_adj"]), lim
 
 
 @pytest.mark.parametrize("case", RZ, ids=[c["name"] for c in RZ])
