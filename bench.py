@@ -414,6 +414,9 @@ def secondary_single(hbm, sampler):
         ("cfg4_jacobi_512_mixed", lambda: P.solver_throughput([512] * 3, "jacobi", 100, *MIX)),
         ("cg_1024sq", lambda: P.solver_throughput([1024, 1024], "cg", 1000, *D4)),
         ("cg_512_fp32", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, dtype="single")),
+        # opt-in FMA contraction (PA_FLAG_CONTRACT): the headline solve with ~40 % fewer fp64 instructions
+        ("cg_512_contract", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, reps=3, contract=True)),
+        ("cg_512_exact_same_run", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, reps=3)),
         ("op_laplacian_512", lambda: P.operator_apply_times([512] * 3, "laplacian", reps=40)),
         ("op_grad_512", lambda: P.operator_apply_times([512] * 3, "grad", reps=20)),
         ("op_div_upwind_512", lambda: P.operator_apply_times([512] * 3, "div_upwind", reps=40)),

@@ -176,7 +176,16 @@ typedef struct {
                           face Dirichlet), 4 = like 0 but never a whole-solve kernel, 5 = CG as ONE
                           cooperative launch of the two TMA phases (L2-resident grids, every face Dirichlet;
                           auto takes it between 80 k and 1.5 M cells) */
+  int32_t flags;       /* PA_FLAG_* */
+  int32_t reserved;
 } pa_solver_cfg;
+
+/* pa_solver_cfg.flags.  PA_FLAG_CONTRACT (opt-in): the fused TMA CG kernels evaluate a*b + c as ONE fused
+ * multiply-add instead of the reference's two roundings.  Every stencil value then differs from the reference's in
+ * the last bits (relative ~1e-16 per operation; north_star asks 1e-12 per operator), the iteration count of a
+ * converged solve may move by one; in exchange the kernels issue ~40 % fewer fp64 instructions, which is what a
+ * power-capped step is short of.  Default (0): bit-exact operation order. */
+#define PA_FLAG_CONTRACT 1
 
 const char* pa_last_error(void);
 int pa_abi_version(void);
@@ -275,6 +284,8 @@ int pa_p2p_set_halo_cap(long long bytes);
 int pa_p2p_disable(void); /* every rank must agree: the host layer disables all if one rank failed to attach */
 
 /* --- any of the three solvers on a slab (method = PA_METHOD_*); pa_cg_solve_dist is the CG case.
+ *     Nonlinear advection (pa_op.adv_is_iterate) works on slabs too: the new iterate's ghost planes are exchanged
+ *     after every update.
  *     BiCGSTAB: p and s get their ghost planes by one send/recv pair each before the operator
  *     application that reads them, and {r0.v}, {|s|^2}, {t.s, t.t, r0.t}, {|r|^2} are all-reduced
  *     (4 per iteration).  Jacobi: one exchange of the new iterate + one all-reduce {|dx|^2}. */
@@ -288,10 +299,16 @@ int pa_euler_steps_dist(const pa_grid* g, const pa_equation* eq, int nfaces, con
                         int dtype, void* phi, void* phi_alt, const void* rhs, double dt, int nsteps,
                         int* result_in_alt, void* comm, int rank, int nranks, void* stream);
 
+/* --- ghost planes of a slab-decomposed field: first / last OWNED plane -> the neighbours' ghost planes
+ *     (ncclSend / ncclRecv, a ring when `ring` != 0); returns when the exchange is complete.  Used by the explicit
+ *     FDC operators on a SlabMesh (the reference's operators read one cell up and down every axis). */
+int pa_halo_exchange(const pa_grid* g, int dtype, void* phi, int ring, void* comm, int rank, int nranks, void* stream);
+
 /* --- instrumented CG pass (measurement only): `iters` iterations with every section bracketed
  *     by CUDA events on the launching stream.  out_ms[6] = average per iteration of
  *     {phase A (d update + d.Ad), phase B (x,r update), BC faces + shell norm, whole iteration,
  *      kernel launches} and [5] = 1 if the tiled kernels ran. */
+/*     (`variant`: pa_solver_cfg.variant, + 0x100 for PA_FLAG_CONTRACT) */
 int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
                   int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
                   size_t ws_bytes, double* out_ms, void* stream);

@@ -18,6 +18,7 @@ BC_KIND = {"dirichlet": 1, "neumann": 2, "symmetry": 3, "periodic": 4}
 OP_STAR, OP_DIV_CENTRAL_FIELD, OP_DIV_UPWIND_FIELD, OP_DIV_UPWINDFD_FIELD = 0, 1, 2, 3
 METHOD = {"cg": 0, "bicgstab": 1, "jacobi": 2}
 RUNNING, CONVERGED, MAXIT, BAD_TOL = 0, 1, 2, 3
+FLAG_CONTRACT = 1
 
 
 class FaceBC(C.Structure):
@@ -88,6 +89,8 @@ class SolverCfg(C.Structure):
         ("check_every", C.c_int32),
         ("use_graph", C.c_int32),
         ("variant", C.c_int32),
+        ("flags", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -120,6 +123,7 @@ SYMBOLS = {
                                 C.POINTER(Report), _P]),
     "pa_euler_steps_dist": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                       _P, _P, _P, C.c_double, C.c_int, C.POINTER(C.c_int), _P, C.c_int, C.c_int, _P]),
+    "pa_halo_exchange": (C.c_int, [C.POINTER(Grid), C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "pa_cg_profile": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,
                                 _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(C.c_double), _P]),
     "pa_bicgstab_solve": (C.c_int, [C.POINTER(Grid), C.POINTER(Equation), C.c_int, C.POINTER(FaceBC), C.c_int,

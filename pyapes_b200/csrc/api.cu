@@ -586,9 +586,12 @@ static int profile_cg(const pa_grid* pg, const pa_equation* peq, int nfaces, con
   Launcher L{stream};
   TilePlan plan;
   TmaPlan tmap;
+  const bool contract = (variant & 0x100) != 0;
+  variant &= 0xff;
   bool use_tma = variant == 0 && plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1],
                                              (T*)w.vec[2], tmap);
   if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+  if (use_tma) tmap.contract = (contract && !tmap.tile.wrap) ? 1 : 0;
   bool tiled = !use_tma && (variant == 0 || variant == 2) && plan_tiles<T>(g, *peq, plan);
   if (tiled) plan.fuse_fin = static_shell(nfaces, faces);
   k_state_init<<<1, 1, 0, stream>>>(w.st, 1e-300, iters + 10);
@@ -830,8 +833,8 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       eq_alt.op[k].adv = x_alt;
       nonlinear = true;
     }
-  if (nonlinear && dist)
-    return fail(PA_ERR_UNSUPPORTED, "multi-GPU: nonlinear advection div(var, var) on slabs is not built");
+  // (on slabs the iterate's ghost planes are refreshed after every update, see `iteration` below: the central
+  //  scheme reads the advection speed one cell up and down the slab axis)
   int nvec = method_nvec(method);
   if (ws_size < ws_bytes(g.cells, sizeof(T), nvec))
     return fail(PA_ERR_ARG, "workspace too small (see pa_solver_workspace_bytes)");
@@ -848,6 +851,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   if (method == PA_METHOD_CG && auto_fused) {
     use_tma = plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], tmap);
     if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
+    if (use_tma) tmap.contract = ((cfg->flags & PA_FLAG_CONTRACT) && !tmap.tile.wrap) ? 1 : 0;
   }
   if (method == PA_METHOD_CG && !use_tma && (auto_fused || cfg->variant == 2))
     tiled = plan_tiles<T>(g, *peq, plan);
@@ -1015,6 +1019,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   // L2-resident grids: the whole solve as ONE cooperative launch of the two TMA phases (kernels_tma.cuh
   // k_cg_coop_tma).  variant 5 forces it; auto (0) takes it between the tiny-grid kernel above and kCoopCgCells.
   if (method == PA_METHOD_CG && use_tma && !dist && !nonlinear && static_shell(nfaces, faces) && !tmap.tile.wrap &&
+      !tmap.contract &&
       (cfg->variant == 5 ||
        (cfg->variant == 0 && g.cells > kSmallCgCells && g.cells <= kCoopCgCells && getenv("PA_NO_COOP_CG") == nullptr))) {
     if (launch_cg_coop_tma<T>(stream, tmap, g, eq_cg, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], w.st,
@@ -1041,6 +1046,10 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       bicgstab_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, pw, dist);
     else
       jacobi_iteration<T>(L, g, e, nfaces, faces, w, cur, nxt, rhs, pw, dist);
+    if (dist && nonlinear && method != PA_METHOD_JACOBI) {  // (Jacobi exchanges its new iterate anyway)
+      dist_halo_exchange<T>(*dist, nxt, (long long)g.n[1] * g.n[2], g.olo0, g.ohi0, L.s);
+      ++L.count;
+    }
   };
 
   const long long max_iters = (method == PA_METHOD_BICGSTAB)
@@ -1470,6 +1479,32 @@ int pa_solve_dist(int method, const pa_grid* g, const pa_equation* eq, int nface
                                    ws_bytes_, report, (cudaStream_t)stream, nranks > 1 ? &d : nullptr));
 }
 
+}  // extern "C"
+template <typename T>
+static int halo_impl(const pa_grid* pg, T* phi, const Dist& d, cudaStream_t s) {
+  if (!nccl_api().ok) return fail(PA_ERR_NCCL, nccl_api().error);
+  nccl_first_error() = ncclSuccess;
+  dist_halo_exchange<T>(d, phi, (long long)pg->n[1] * pg->n[2], pg->olo0, pg->ohi0, s);
+  PA_CUDA(cudaStreamSynchronize(s));
+  if (nccl_first_error() != ncclSuccess)
+    return fail(PA_ERR_NCCL, std::string("NCCL: ") + nccl_api().GetErrorString(nccl_first_error()));
+  return PA_OK;
+}
+extern "C" {
+
+int pa_halo_exchange(const pa_grid* g, int dtype, void* phi, int ring, void* comm, int rank, int nranks, void* stream) {
+  PA_REQUIRE_DEVICE();
+  DeviceGuard guard(phi);
+  int rc;
+  if ((rc = check_grid(g))) return rc;
+  if (!phi) return fail(PA_ERR_ARG, "phi is null");
+  if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(PA_ERR_ARG, "bad communicator");
+  if (nranks == 1) return PA_OK;
+  Dist d{(ncclComm_t)comm, rank, nranks};
+  d.ring = ring ? 1 : 0;
+  PA_DISPATCH(dtype, halo_impl<T>(g, (T*)phi, d, (cudaStream_t)stream));
+}
+
 int pa_cg_profile(const pa_grid* g, const pa_equation* eq, int nfaces, const pa_face_bc* faces,
                   int dtype, void* x, void* x_alt, const void* rhs, int iters, int variant, void* ws,
                   size_t ws_bytes_, double* out_ms, void* stream) {
@@ -1542,7 +1577,6 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
   EqDev<T> eq_b = eq_a;  // nonlinear advection: the speed is the field being advanced (see run_solver)
   for (int k = 0; k < peq->nops; ++k)
     if (peq->ops[k].kind != PA_OP_STAR && peq->ops[k].adv_is_iterate) {
-      if (dist) return fail(PA_ERR_UNSUPPORTED, "multi-GPU: nonlinear advection div(var, var) on slabs is not built");
       eq_a.op[k].adv = a;
       eq_b.op[k].adv = b;
     }

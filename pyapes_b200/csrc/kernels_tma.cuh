@@ -167,6 +167,7 @@ struct TmaPlan {
   const void* r_ptr;        // raw arrays behind r_halo / d_halo (wrap-around reads, TilePlan::src*)
   const void* d_ptr[2];
   int coef_uniform = 0;     // coefficient classes of axes 1 and 2 are bitwise equal (star_cells UNI)
+  int contract = 0;         // opt-in FMA contraction (PA_FLAG_CONTRACT; never with periodic axes 1/2)
 };
 
 // wave-aware chunking along axis 0 (shared by the CG and the star-engine plans)
@@ -450,6 +451,7 @@ struct StepSum<double> {
   double& acc;
   __device__ __forceinline__ explicit StepSum(double& a) : acc(a) {}
   __device__ __forceinline__ void add(double q) { acc += q; }
+  __device__ __forceinline__ void fma_add(double a, double b) { acc = fma(a, b, acc); }
   __device__ __forceinline__ void flush() {}
 };
 template <>
@@ -458,6 +460,7 @@ struct StepSum<float> {
   float part = 0.f;
   __device__ __forceinline__ explicit StepSum(double& a) : acc(a) {}
   __device__ __forceinline__ void add(float q) { part += q; }
+  __device__ __forceinline__ void fma_add(float a, float b) { part = fmaf(a, b, part); }
   __device__ __forceinline__ void flush() { acc += (double)part; }
 };
 
@@ -529,6 +532,17 @@ __device__ __forceinline__ void wrap_halo(const GridDev& g, const ConsCtx<T, K>&
   }
 }
 
+// a*b + c: two roundings (the reference's operation sequence; the library is built with -fmad=false) or, in the
+// OPT-IN contraction mode (pa_solver_cfg.flags & PA_FLAG_CONTRACT), one fused multiply-add.  Contraction changes the
+// last bits of every stencil value (relative 1e-16 per operation, far inside north_star's 1e-12 per operator) and
+// nearly halves the fp64 instructions of the fused CG kernels -- what a power-capped step is short of.
+template <bool CONTRACT, typename T>
+__device__ __forceinline__ T mad(T a, T b, T c) {
+  if (CONTRACT) return fma(a, b, c);
+  const T m = a * b;
+  return m + c;
+}
+
 // the star operator on the thread's cells: same bits as eval_equation, with two exact shortcuts --
 // the accumulator starts from the first axis' sum instead of 0 + sum (they differ only in the sign
 // of an all-zero sum, erased by the `0 + acc` below), and (acc * param) * sign is one
@@ -536,7 +550,7 @@ __device__ __forceinline__ void wrap_halo(const GridDev& g, const ConsCtx<T, K>&
 // Kernel axis 0 is always active on this path (plan_tma).
 // UNI: the three coefficient classes of axes 1 and 2 hold the same numbers (no Neumann / Symmetry face on
 // those axes), so the general path takes class 0 like the LEAN one -- same bits, no per-cell selects.
-template <typename T, typename K, bool LEAN, typename F, bool UNI = false>
+template <typename T, typename K, bool LEAN, typename F, bool UNI = false, bool CONTRACT = false>
 __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K>& c, const T (&cx)[3],
                                            bool actx, const T (&vm)[K::RY][VecOf<T>::N],
                                            const T (&vc)[K::RY][VecOf<T>::N], const T (&vp)[K::RY][VecOf<T>::N],
@@ -561,25 +575,25 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
       T acc;
       {
         T s = cx[0] * vp[k][e];
-        s = s + cx[1] * v0;
-        s = s + cx[2] * vm[k][e];
+        s = mad<CONTRACT>(cx[1], v0, s);
+        s = mad<CONTRACT>(cx[2], vm[k][e], s);
         acc = s;
       }
       if (!K::FLAT) {
         T s = yap * yp;
-        s = s + yac * v0;
-        s = s + yam * ym;
+        s = mad<CONTRACT>(yac, v0, s);
+        s = mad<CONTRACT>(yam, ym, s);
         acc = acc + s;
       }
       {
         T s = zap * zp;
-        s = s + zac * v0;
-        s = s + zam * zm;
+        s = mad<CONTRACT>(zac, v0, s);
+        s = mad<CONTRACT>(zam, zm, s);
         acc = acc + s;
       }
       if (use_scale) acc = acc * scale;
-      T res = (T)0 + acc;
-      if (o.has_shift) res = res + o.shift * v0;  // + the diagonal operator, last (ops.py:151-152)
+      T res = CONTRACT ? acc : (T)0 + acc;
+      if (o.has_shift) res = mad<CONTRACT>(o.shift, v0, res);  // + the diagonal operator, last (ops.py:151-152)
       emit(k, e, res);
     }
   }
@@ -597,7 +611,7 @@ __device__ __forceinline__ void star_cells(const OpDev<T>& o, const ConsCtx<T, K
 // HALO: the launch stores its first / last owned plane of r into the neighbours' landing zones as well (slabs with
 // the peer-memory halo exchange); a template parameter so that single-GPU launches do not carry those stores
 template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false, int STRIDE = TmaCfg<T, K>::STAGE_B,
-          bool HALO = false>
+          bool HALO = false, bool CONTRACT = false>
 __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ x_new, T* __restrict__ r, T alpha,
                                               unsigned char* stages, uint64_t* full, uint64_t* empty,
@@ -675,7 +689,7 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
         const int clx = actx ? coef_class(g, 0, x) : 0;
         const T cx[3] = {o.coef[0][clx][0], o.coef[0][clx][1], o.coef[0][clx][2]};
         auto keep = [&](int k, int e, T v) { ad[k][e] = v; };
-        star_cells<T, K, LEAN, decltype(keep), UNI>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, keep);
+        star_cells<T, K, LEAN, decltype(keep), UNI, CONTRACT>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, keep);
       }
       // x and r of this plane are only needed now: keep their live range short
 #pragma unroll
@@ -686,18 +700,24 @@ __device__ __forceinline__ void tmaB_consumer(const TilePlan& p, const GridDev& 
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const bool in = LEAN || ((c.inreg >> (k * VEC + e)) & 1u);
-          xn[e] = xv[e] + alpha * vc[k][e];       // linalg.py:122 (d == 0 outside the region)
-          const T t = rv[e] - alpha * ad[k][e];   // linalg.py:131
+          xn[e] = mad<CONTRACT>(alpha, vc[k][e], xv[e]);  // linalg.py:122 (d == 0 outside the region)
+          const T t = CONTRACT ? fma(-alpha, ad[k][e], rv[e]) : rv[e] - alpha * ad[k][e];  // linalg.py:131
           rn[e] = in ? t : rv[e];
           if (xown) {
             if (in) {
-              const T q = t * t;
-              s0.add(q);
+              if (CONTRACT) s0.fma_add(t, t);
+              else {
+                const T q = t * t;
+                s0.add(q);
+              }
             }
             if (!xshell && (LEAN || ((c.nonshell >> (k * VEC + e)) & 1u))) {
               const T df = xn[e] - xv[e];
-              const T q2 = df * df;
-              s1.add(q2);
+              if (CONTRACT) s1.fma_add(df, df);
+              else {
+                const T q2 = df * df;
+                s1.add(q2);
+              }
             }
           }
         }
@@ -779,7 +799,7 @@ __device__ __forceinline__ unsigned phaseB_produce(const CUtensorMap* tm_d, cons
   return gi;
 }
 
-template <typename T, typename K, bool WRAP, bool UNI, int STRIDE, bool HALO = false>
+template <typename T, typename K, bool WRAP, bool UNI, int STRIDE, bool HALO = false, bool CONTRACT = false>
 __device__ __forceinline__ unsigned phaseB_consume(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                                    T* __restrict__ x_new, T* __restrict__ r, T alpha, SolverState* st,
                                                    unsigned long long halo_seq, unsigned char* stages, uint64_t* full,
@@ -791,11 +811,11 @@ __device__ __forceinline__ unsigned phaseB_consume(const TilePlan& p, const Grid
     if (id < 0) break;
     const WorkItem w = work_item<C>(p, g, id);
     if (w.lean)
-      tmaB_consumer<T, K, true, false, false, STRIDE, HALO>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
-                                                            w.x0, w.x1, acc, gi);
+      tmaB_consumer<T, K, true, false, false, STRIDE, HALO, CONTRACT>(p, g, o, x_new, r, alpha, stages, full, empty,
+                                                                      w.y0, w.z0, w.x0, w.x1, acc, gi);
     else
-      tmaB_consumer<T, K, false, WRAP, UNI, STRIDE, HALO>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0, w.z0,
-                                                          w.x0, w.x1, acc, gi);
+      tmaB_consumer<T, K, false, WRAP, UNI, STRIDE, HALO, CONTRACT>(p, g, o, x_new, r, alpha, stages, full, empty, w.y0,
+                                                                    w.z0, w.x0, w.x1, acc, gi);
     gi += (unsigned)(w.x1 - w.x0 + 2);
     if (HALO) {
       // this item's rows of the first / last owned plane are in the neighbour's landing zone: count it in; the
@@ -842,7 +862,7 @@ __device__ __forceinline__ void pipe_init(uint64_t* full, uint64_t* empty) {
   __syncthreads();
 }
 
-template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false>
+template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false, bool CONTRACT = false>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_r, TilePlan p, GridDev g, OpDev<T> o,
@@ -867,8 +887,8 @@ k_cg_phaseB_tma(const __grid_constant__ CUtensorMap tm_d, const __grid_constant_
     if (lane == 0) phaseB_produce<T, K, C::STAGE_B>(&tm_d, &tm_x, &tm_r, p, g, stages, full, empty, item_ring, 0u);
   } else {
     const T alpha = (T)st->scal[S_ALPHA];
-    phaseB_consume<T, K, WRAP, UNI, C::STAGE_B, HALO>(p, g, o, x_new, r, alpha, st, halo_seq, stages, full, empty,
-                                                      item_ring, acc, 0u);
+    phaseB_consume<T, K, WRAP, UNI, C::STAGE_B, HALO, CONTRACT>(p, g, o, x_new, r, alpha, st, halo_seq, stages, full,
+                                                                empty, item_ring, acc, 0u);
   }
   work_leave(p);
   const int nblocks = gridDim.x;
@@ -913,7 +933,8 @@ __device__ __forceinline__ bool halo_wait(const unsigned long long* flag, unsign
 // =========================================================================================
 // phase A
 // =========================================================================================
-template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false, int STRIDE = TmaCfg<T, K>::STAGE_A>
+template <typename T, typename K, bool LEAN, bool WRAP = false, bool UNI = false, int STRIDE = TmaCfg<T, K>::STAGE_A,
+          bool CONTRACT = false>
 __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                               T* __restrict__ d_new, T beta, unsigned char* stages,
                                               uint64_t* full, uint64_t* empty, int y0, int z0, int x0,
@@ -940,7 +961,7 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       lds_vec<T>(rp + k * C::BOXZ, a);
       lds_vec<T>(dp + k * C::BOXZ, b);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) v[k][e] = a[e] + beta * b[e];
+      for (int e = 0; e < VEC; ++e) v[k][e] = mad<CONTRACT>(beta, b[e], a[e]);
     }
   };
   auto write_d = [&](const T (&v)[K::RY][VEC]) {
@@ -985,19 +1006,19 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
         lds_vec<T>(rp - C::BOXZ, a);
         lds_vec<T>(dp - C::BOXZ, b);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) up[e] = a[e] + beta * b[e];
+        for (int e = 0; e < VEC; ++e) up[e] = mad<CONTRACT>(beta, b[e], a[e]);
         lds_vec<T>(rp + K::RY * C::BOXZ, a);
         lds_vec<T>(dp + K::RY * C::BOXZ, b);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) dn[e] = a[e] + beta * b[e];
+        for (int e = 0; e < VEC; ++e) dn[e] = mad<CONTRACT>(beta, b[e], a[e]);
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) up[e] = dn[e] = (T)0;
       }
 #pragma unroll
       for (int k = 0; k < K::RY; ++k) {
-        zl[k] = rp[k * C::BOXZ - 1] + beta * dp[k * C::BOXZ - 1];
-        zr[k] = rp[k * C::BOXZ + VEC] + beta * dp[k * C::BOXZ + VEC];
+        zl[k] = mad<CONTRACT>(beta, dp[k * C::BOXZ - 1], rp[k * C::BOXZ - 1]);
+        zr[k] = mad<CONTRACT>(beta, dp[k * C::BOXZ + VEC], rp[k * C::BOXZ + VEC]);
       }
       if (WRAP) {
         const T* rg = static_cast<const T*>(p.src0);
@@ -1009,11 +1030,14 @@ __device__ __forceinline__ void tmaA_consumer(const TilePlan& p, const GridDev& 
       // d == 0 outside the solver region: d*Ad needs no region mask, only array bounds
       auto dot = [&](int k, int e, T ad) {
         if (LEAN || ((c.valid >> (k * VEC + e)) & 1u)) {
-          const T q = vc[k][e] * ad;
-          sd.add(q);
+          if (CONTRACT) sd.fma_add(vc[k][e], ad);
+          else {
+            const T q = vc[k][e] * ad;
+            sd.add(q);
+          }
         }
       };
-      star_cells<T, K, LEAN, decltype(dot), UNI>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, dot);
+      star_cells<T, K, LEAN, decltype(dot), UNI, CONTRACT>(o, c, cx, actx, vm, vc, vp, up, dn, zl, zr, dot);
     }
     sd.flush();
     release(sc);
@@ -1083,7 +1107,7 @@ __device__ __forceinline__ unsigned phaseA_produce(const CUtensorMap* tm_r, cons
   return gi;
 }
 
-template <typename T, typename K, bool WRAP, bool UNI, int STRIDE>
+template <typename T, typename K, bool WRAP, bool UNI, int STRIDE, bool CONTRACT = false>
 __device__ __forceinline__ unsigned phaseA_consume(const TilePlan& p, const GridDev& g, const OpDev<T>& o,
                                                    T* __restrict__ d_new, T beta, unsigned char* stages,
                                                    uint64_t* full, uint64_t* empty, const int* item_ring, double& acc,
@@ -1094,17 +1118,17 @@ __device__ __forceinline__ unsigned phaseA_consume(const TilePlan& p, const Grid
     if (id < 0) break;
     const WorkItem w = work_item<C>(p, g, id);
     if (w.lean)
-      tmaA_consumer<T, K, true, false, false, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0, w.x1,
-                                                      acc, gi);
+      tmaA_consumer<T, K, true, false, false, STRIDE, CONTRACT>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0,
+                                                                w.x0, w.x1, acc, gi);
     else
-      tmaA_consumer<T, K, false, WRAP, UNI, STRIDE>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0, w.x0, w.x1,
-                                                    acc, gi);
+      tmaA_consumer<T, K, false, WRAP, UNI, STRIDE, CONTRACT>(p, g, o, d_new, beta, stages, full, empty, w.y0, w.z0,
+                                                              w.x0, w.x1, acc, gi);
     gi += (unsigned)(w.x1 - w.x0 + 2);
   }
   return gi;
 }
 
-template <typename T, typename K, bool WRAP, bool UNI>
+template <typename T, typename K, bool WRAP, bool UNI, bool CONTRACT = false>
 __global__ void __launch_bounds__(TmaCfg<T, K>::THREADS, 2)
 k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_d,
                 const __grid_constant__ CUtensorMap tm_land, TilePlan p, GridDev g, OpDev<T> o,
@@ -1127,7 +1151,8 @@ k_cg_phaseA_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant_
       phaseA_produce<T, K, C::STAGE_A>(&tm_r, &tm_d, &tm_land, p, g, st, stages, full, empty, item_ring, 0u);
   } else {
     const T beta = (T)st->scal[S_BETA];
-    phaseA_consume<T, K, WRAP, UNI, C::STAGE_A>(p, g, o, d_new, beta, stages, full, empty, item_ring, acc[0], 0u);
+    phaseA_consume<T, K, WRAP, UNI, C::STAGE_A, CONTRACT>(p, g, o, d_new, beta, stages, full, empty, item_ring, acc[0],
+                                                          0u);
   }
   work_leave(p);
   const int nblocks = gridDim.x;
@@ -1367,14 +1392,14 @@ inline int tma_interior_chunks(const TmaPlan& tp, const GridDev& g) {
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-template <typename T, typename K, bool WRAP, bool UNI>
+template <typename T, typename K, bool WRAP, bool UNI, bool CONTRACT = false>
 static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* d_new, SolverState* st, double* partials) {
   typedef TmaCfg<T, K> C;
   static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
   bool& attr = attr_dev[current_device()];
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseA_tma<T, K, WRAP, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
+    cudaFuncSetAttribute(k_cg_phaseA_tma<T, K, WRAP, UNI, CONTRACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
     attr = true;
   }
   TilePlan tile = tp.tile;
@@ -1388,7 +1413,7 @@ static void launch_cg_phaseA_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
     tile.halo.slot = 1 - parity;  // what the previous iteration's phase B (parity 1 - p) delivered
     tile.ghost_last = tile.chunks >= 3 ? 1 : 0;
   }
-  k_cg_phaseA_tma<T, K, WRAP, UNI><<<grid, C::THREADS, C::SMEM_A, s>>>(
+  k_cg_phaseA_tma<T, K, WRAP, UNI, CONTRACT><<<grid, C::THREADS, C::SMEM_A, s>>>(
       tp.r_halo, tp.d_halo[parity], tile.halo.on ? tp.r_land : tp.r_halo, tile, g, eq.op[0], d_new, st, partials);
 }
 
@@ -1400,24 +1425,28 @@ void launch_cg_phaseA_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, c
   if (tma_flat(g)) {
     if (tp.tile.wrap)
       launch_cg_phaseA_tma_k<T, KFlat, true, false>(s, tp, g, eq, parity, d_new, st, partials);
+    else if (tp.contract)
+      launch_cg_phaseA_tma_k<T, KFlat, false, false, true>(s, tp, g, eq, parity, d_new, st, partials);
     else
       launch_cg_phaseA_tma_k<T, KFlat, false, false>(s, tp, g, eq, parity, d_new, st, partials);
   } else {
     if (tp.tile.wrap)
       launch_cg_phaseA_tma_k<T, KStd, true, false>(s, tp, g, eq, parity, d_new, st, partials);
+    else if (tp.contract)
+      launch_cg_phaseA_tma_k<T, KStd, false, false, true>(s, tp, g, eq, parity, d_new, st, partials);
     else
       launch_cg_phaseA_tma_k<T, KStd, false, false>(s, tp, g, eq, parity, d_new, st, partials);
   }
 }
 
-template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false>
+template <typename T, typename K, bool WRAP, bool UNI, bool HALO = false, bool CONTRACT = false>
 static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const GridDev& g, const EqDev<T>& eq,
                                    int parity, T* x_new, T* r, SolverState* st, double* partials, int sub) {
   typedef TmaCfg<T, K> C;
   static bool attr_dev[kMaxDevices] = {};  // the attribute is per device
   bool& attr = attr_dev[current_device()];
   if (!attr) {
-    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP, UNI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
+    cudaFuncSetAttribute(k_cg_phaseB_tma<T, K, WRAP, UNI, HALO, CONTRACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
     attr = true;
   }
   // iteration parity p: x_old = x buffer p, d (already updated by phase A) = d buffer 1-p
@@ -1448,7 +1477,7 @@ static void launch_cg_phaseB_tma_k(cudaStream_t s, const TmaPlan& tp, const Grid
   tile.work_slot = next_work_slot();
   tile.first_static = 1;
   dim3 grid(persistent_grid(tile, nz));
-  k_cg_phaseB_tma<T, K, WRAP, UNI, HALO><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
+  k_cg_phaseB_tma<T, K, WRAP, UNI, HALO, CONTRACT><<<grid, C::THREADS, C::SMEM_B, s>>>(tp.d_halo[1 - parity], tp.x_own[parity], tp.r_own, tile,
                                                            g, eq.op[0], x_new, r, st, partials);
 }
 
@@ -1459,18 +1488,26 @@ void launch_cg_phaseB_tma(cudaStream_t s, const TmaPlan& tp, const GridDev& g, c
   // Dirichlet or periodic: 10 % fewer instructions on the edge tiles), neither; and, on slabs with the
   // peer-memory halo exchange (never together with wrap, api.cu halo_dev), the HALO stores
   const bool halo = tp.tile.halo.on != 0;
-#define PA_LAUNCH_B(KK)                                                                                      \
-  do {                                                                                                       \
-    if (tp.tile.wrap)                                                                                        \
-      launch_cg_phaseB_tma_k<T, KK, true, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);         \
-    else if (tp.coef_uniform && halo)                                                                        \
-      launch_cg_phaseB_tma_k<T, KK, false, true, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);   \
-    else if (tp.coef_uniform)                                                                                \
-      launch_cg_phaseB_tma_k<T, KK, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);         \
-    else if (halo)                                                                                           \
-      launch_cg_phaseB_tma_k<T, KK, false, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);  \
-    else                                                                                                     \
-      launch_cg_phaseB_tma_k<T, KK, false, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);        \
+#define PA_LAUNCH_B(KK)                                                                                            \
+  do {                                                                                                             \
+    if (tp.tile.wrap)                                                                                              \
+      launch_cg_phaseB_tma_k<T, KK, true, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);               \
+    else if (tp.contract && tp.coef_uniform && halo)                                                               \
+      launch_cg_phaseB_tma_k<T, KK, false, true, true, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);   \
+    else if (tp.contract && tp.coef_uniform)                                                                       \
+      launch_cg_phaseB_tma_k<T, KK, false, true, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);  \
+    else if (tp.contract && halo)                                                                                  \
+      launch_cg_phaseB_tma_k<T, KK, false, false, true, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);  \
+    else if (tp.contract)                                                                                          \
+      launch_cg_phaseB_tma_k<T, KK, false, false, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub); \
+    else if (tp.coef_uniform && halo)                                                                              \
+      launch_cg_phaseB_tma_k<T, KK, false, true, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);         \
+    else if (tp.coef_uniform)                                                                                      \
+      launch_cg_phaseB_tma_k<T, KK, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);               \
+    else if (halo)                                                                                                 \
+      launch_cg_phaseB_tma_k<T, KK, false, false, true>(s, tp, g, eq, parity, x_new, r, st, partials, sub);        \
+    else                                                                                                           \
+      launch_cg_phaseB_tma_k<T, KK, false, false>(s, tp, g, eq, parity, x_new, r, st, partials, sub);              \
   } while (0)
   if (tma_flat(g))
     PA_LAUNCH_B(KFlat);

@@ -1,4 +1,4 @@
-// Translation unit: TMA-staged CG kernels
+// Translation unit: TMA-staged CG kernels, double
 #include "kernels_tma.cuh"
 namespace pa {
 #define PA_INST(T)                                                                                             \
@@ -9,6 +9,5 @@ namespace pa {
   template bool launch_cg_coop_tma<T>(cudaStream_t, const TmaPlan&, const GridDev&, const EqDev<T>&, T*, T*, T*, T*, \
                                       T*, SolverState*, double*);
 PA_INST(double)
-PA_INST(float)
 #undef PA_INST
 }  // namespace pa

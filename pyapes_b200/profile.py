@@ -154,7 +154,7 @@ def _event_time(fn, reps: int = 1) -> float:
 
 
 def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dtype: str = "double", variant: int = 0,
-                      device: str = "cuda", reps: int = 1) -> dict:
+                      device: str = "cuda", reps: int = 1, contract: bool = False) -> dict:
     """Fixed-count solve (tol 1e-300) of the Poisson problem through the public API; GLUP/s = cells x
     iterations / device time of solver.solve().  words per LUP: SURVEY.md §8d (CG 8, BiCGSTAB 17 canonical,
     Jacobi 3)."""
@@ -183,7 +183,7 @@ def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dty
         work.copy_(rhs)  # set_eq adds the Neumann adjustment in place
         var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
         s = Solver({"fdm": {"method": method, "tol": 1e-300, "max_it": max_it, "report": False, "variant": variant,
-                            "check_every": iters + (iters & 1)}})
+                            "check_every": iters + (iters & 1), "contract": contract}})
         s.set_eq(FDM().laplacian(1.0, var) == work)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

@@ -125,9 +125,20 @@ class Discretizer:
         phi = var()
         N.require_cuda(phi, "field")
         nd = var.mesh.dim
-        if getattr(var.mesh, "slab", None) is not None:
-            raise NotImplementedError("pyapes_b200: explicit FDC operators on a slab-decomposed mesh are not built yet")
-        grid = L.lower_grid(var.nx, var.bcs)
+        slab = getattr(var.mesh, "slab", None)
+        if slab is not None and slab["world"] > 1:
+            # Slab-decomposed mesh: refresh the ghost planes, then apply on the local block.  Every OWNED cell
+            # gets the single-GPU value, with one exception: edge=False on a NON-periodic slab axis leaves the two
+            # global x-boundary planes with a local instead of the global wrap-around neighbour -- values that are
+            # torch.roll artefacts in the reference as well (it never uses them); edge=True replaces them by the
+            # one-sided formulas and is identical everywhere.  Ghost planes of the result are not meaningful.
+            from pyapes_b200 import parallel
+
+            gl = L.lower_grid(var.nx, var.bcs, slab)
+            N.check(N.lib().pa_halo_exchange(gl, N.dtype_code(phi.dtype), phi.data_ptr(), 1 if slab["periodic"] else 0,
+                                             parallel.get_comm(phi.device), slab["rank"], slab["world"],
+                                             N.current_stream(phi.device)))
+        grid = L.lower_grid(var.nx, var.bcs, slab)  # (slab: coefficient classes follow the GLOBAL plane index)
         if edge and var.mesh.coord_sys == "rz":
             raise NotImplementedError("pyapes_b200: edge=True on rz meshes is not built")
         op, keep = L.lower_op(A_coeffs, nd, phi.dtype, edge=edge_code, dx=var.mesh._dx, adv_const=adv_const,

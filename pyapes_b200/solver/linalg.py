@@ -81,6 +81,7 @@ def _run(method: str, var: Field, rhs: Tensor, eqs, config: FDMSolverConfig, mes
     cfg.check_every = int(config.get("check_every", 0))
     cfg.use_graph = 1 if config.get("use_graph", True) else 0
     cfg.variant = int(config.get("variant", 0))
+    cfg.flags = N.FLAG_CONTRACT if config.get("contract", False) else 0
     rep = N.Report()
     if slab is not None and slab["world"] > 1:
         from pyapes_b200 import parallel

@@ -49,6 +49,8 @@ class FDMSolverConfig(TypedDict, total=False):
     use_graph: bool   # replay the iteration as a CUDA graph
     variant: int      # 0 auto, 1 generic kernels, 2 register-tiled, 3 persistent small-grid CG, 4 fused (TMA) only
     n_steps: int      # explicit Euler: time steps per solve()
+    contract: bool    # opt-in FMA contraction in the fused TMA CG kernels (PA_FLAG_CONTRACT): ~1e-16 relative per
+    #                   operation instead of bit-exact, fewer fp64 instructions; default False
 
 
 class SolverConfig(TypedDict):

@@ -39,7 +39,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(N.Grid) == 60
     assert C.sizeof(N.Op) == 4 + 4 + 8 + 8 + 27 * 8 + 8 + 24 + 24 + 12 + 12 + 8 + 4 + 4 + 8 + 24
     assert C.sizeof(N.Equation) == 8 + 4 * C.sizeof(N.Op)
-    assert C.sizeof(N.Report) == 32 and C.sizeof(N.SolverCfg) == 24
+    assert C.sizeof(N.Report) == 32 and C.sizeof(N.SolverCfg) == 32
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -280,3 +280,43 @@ def test_jac_driven_div_fixtures(case):
         FDM({"div": {"limiter": "upwind", "edge": False}}).div(jac, var)
     FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
     torch.set_default_dtype(torch.float64)
+
+
+@pytest.mark.parametrize("shape", [[48, 40, 64], [40, 1024]])
+def test_contraction_mode_is_opt_in_and_within_tolerance(shape):
+    """PA_FLAG_CONTRACT (config key "contract"): the fused TMA CG kernels use one FMA where the reference rounds
+    twice.  north_star's bar is 1e-12 relative per operator; after ONE iteration (x = alpha d: one operator
+    application and two dot products) the iterate must agree with the bit-exact mode to that bar, 20 lockstep
+    iterations to 1e-10, and a converged solve must need the same number of iterations +- 1."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import homogeneous_bcs
+
+    nd = len(shape)
+    g = torch.Generator().manual_seed(1234)
+    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64).to(DEV)
+
+    def run(tol, max_it, contract):
+        mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, DEV, "double")
+        var = Field("p", 1, mesh, {"domain": homogeneous_bcs(nd, 0.0, "dirichlet"), "obstacle": None})
+        s = Solver({"fdm": {"method": "cg", "tol": tol, "max_it": max_it, "report": False, "variant": 4,
+                            "contract": contract}})
+        s.set_eq(FDM().laplacian(1.0, var) == rhs.clone())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rep = s.solve()
+        return rep, var().clone()
+
+    for max_it, bar in ((0, 1e-12), (19, 1e-10)):
+        (re, xe), (rc, xc) = run(1e-30, max_it, False), run(1e-30, max_it, True)
+        assert re["itr"] == rc["itr"] == max_it + 1
+        scale = xe.abs().max().item()
+        assert (xe - xc).abs().max().item() <= bar * scale, (max_it, (xe - xc).abs().max().item() / scale)
+        assert abs(re["tol"] - rc["tol"]) <= bar * re["tol"]
+        assert not torch.equal(xe, xc) or max_it == 0  # the mode really changes bits (not a no-op flag)
+    (re, xe), (rc, xc) = run(1e-8, 5000, False), run(1e-8, 5000, True)
+    assert re["converge"] and rc["converge"] and abs(re["itr"] - rc["itr"]) <= 1, (re, rc)
+    assert (xe - xc).abs().max().item() <= 1e-8 * xe.abs().max().item()

@@ -56,7 +56,7 @@ def test_headline_kernels_keep_local_memory_out_of_the_plane_loops():
     res = _resources()
     checked = 0
     for name, (mangled, _, _) in res.items():
-        if not re.search(r"k_cg_phase[AB]_tma<double, pa::KStd, false, (true|false)(, false)?>", name):
+        if not re.search(r"k_cg_phase[AB]_tma<double, pa::KStd, false, (true|false)(, false)*>", name):
             continue
         sass = subprocess.run([CUOBJDUMP, "-sass", "-fun", mangled, LIB], capture_output=True, text=True).stdout
         n = len(re.findall(r"\s(LDL|STL)[. ]", sass))
@@ -67,7 +67,7 @@ def test_headline_kernels_keep_local_memory_out_of_the_plane_loops():
 
 def test_headline_cg_kernels_use_tma_and_mbarriers():
     res = _resources()
-    for pat in (r"k_cg_phaseA_tma<double, pa::KStd, false, false>", r"k_cg_phaseB_tma<double, pa::KStd, false, true, false>"):
+    for pat in (r"k_cg_phaseA_tma<double, pa::KStd, false, false, false>", r"k_cg_phaseB_tma<double, pa::KStd, false, true, false, false>"):
         hits = [v[0] for k, v in res.items() if re.search(pat, k)]
         assert len(hits) == 1, pat
         sass = subprocess.run([CUOBJDUMP, "-sass", "-fun", hits[0], LIB], capture_output=True, text=True).stdout

@@ -157,6 +157,69 @@ for limiter in ("upwind", "upwind_fd"):
             rep, rep1, err = res
             report(f"euler {limiter}", name, res, err == 0.0)
 
+
+# ---- nonlinear advection div(var, var) on slabs (fdm.py:306-312): the iterate's ghost planes follow every update
+def burgers(method, limiter, max_it):
+    def build(var, rhs, x0):
+        var.set_var_tensor(0.2 * x0.clone())
+        fdm = FDM({"div": {"limiter": limiter, "edge": False}})
+        cfg = {"method": method, "tol": 1e-30, "max_it": max_it, "report": False}
+        if method == "euler":
+            var.set_time(0.05 * min(var.mesh._dx) ** 2 / 0.1, 0.0)
+            s = Solver({"fdm": {"method": "euler", "n_steps": max_it, "report": False}})
+            s.set_eq(fdm.ddt(var) + fdm.div(var, var) - fdm.laplacian(0.1, var) == 0.0)
+        else:
+            s = Solver({"fdm": cfg})
+            s.set_eq(fdm.div(var, var) - fdm.laplacian(0.1, var) == rhs)
+        return s.solve()
+    return build
+
+
+for method, limiter, its, tol in (("bicgstab", "none", 8, 1e-8), ("bicgstab", "upwind", 8, 1e-8), ("jacobi", "upwind", 20, 1e-12),
+                                  ("cg", "none", 6, 1e-8), ("euler", "none", 15, 0.0), ("euler", "upwind", 15, 0.0)):
+    name, n, kinds, vals = cases[0]
+    res = both(burgers(method, limiter, its), n, kinds, vals)
+    if res:
+        rep, rep1, err = res
+        report(f"nonlinear {method}/{limiter}", name, res, rep["itr"] == rep1["itr"] and err <= tol)
+
+
+# ---- explicit FDC operators on slabs: every owned cell equals the single-GPU value (edge=True: everywhere;
+#      edge=False: except the two global x-boundary planes, whose values are wrap-around artefacts)
+def fdc_check(kinds, vals, n, periodic):
+    global ok
+    from pyapes_b200.solver.fdc import FDC
+    g = torch.Generator().manual_seed(77)
+    phi_global = torch.rand(1, *n, generator=g, dtype=torch.float64) - 0.5
+    mesh = SlabMesh(Box[0:1, 0:1, 0:1], None, n, rank, world, dev, "double", periodic=periodic)
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    var.set_var_tensor(mesh.local_slice(phi_global).to(dev))
+    m1 = Mesh(Box[0:1, 0:1, 0:1], None, n, dev, "double")
+    v1 = Field("p", 1, m1, {"domain": mixed_bcs(vals, kinds), "obstacle": None})
+    v1.set_var_tensor(phi_global.to(dev))
+    for opname, edge in (("laplacian", False), ("laplacian", True), ("grad", False), ("grad", True), ("div", False)):
+        cfg = {opname: {"edge": edge}} if opname != "div" else {"div": {"limiter": "upwind", "edge": False}}
+        call = (lambda f, v: f.div(0.7, v)) if opname == "div" else (lambda f, v: getattr(f, opname)(v))
+        loc = call(FDC(cfg), var)
+        ref = call(FDC(cfg), v1) if rank == 0 else None
+        own = loc[:, :, mesh.slab["olo0"]:mesh.slab["ohi0"]] if opname == "grad" else mesh.owned(loc)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(own.contiguous().cpu(), parts, dst=0)
+        if rank == 0:
+            full = torch.cat(parts, dim=2 if opname == "grad" else 1)
+            r = ref.cpu()
+            sl = slice(None) if (edge or periodic) else slice(1, -1)
+            a = full[:, :, sl] if opname == "grad" else full[:, sl]
+            b = r[:, :, sl] if opname == "grad" else r[:, sl]
+            good = torch.equal(a, b)
+            ok &= bool(good)
+            print(f"[fdc {opname} edge={edge}] {'periodic-x' if periodic else 'dirichlet'} P={world} bit-equal on owned cells: {'OK' if good else 'FAIL'}", flush=True)
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+
+
+fdc_check(D6, [0.0, 1.0, 0.5, 0.0, -0.25, 0.0], [40, 36, 64], False)
+fdc_check(["periodic", "periodic", "neumann", "symmetry", "dirichlet", "dirichlet"], [None, None, 0.5, None, 0.0, 0.0], [44, 36, 32], True)
+
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
