@@ -376,10 +376,16 @@ __device__ __forceinline__ void work_leave(const TilePlan& p) {
   }
 }
 
-// grid of a persistent launch: 2 CTAs per SM (occupancy of every TMA kernel), never more than the items
+// Grid of a launch.  Up to three waves of items the launch is PERSISTENT: 2 CTAs per SM (the occupancy of every TMA
+// kernel) walk the items with a running pipeline -- measured +4 % on CG at 256^3, where the fill / drain of one CTA
+// per item is a visible share of a short kernel.  Beyond that one CTA per item, handed out by the hardware scheduler
+// as before (the CTA takes item blockIdx.x, the counter then answers "none left"): at 512^3 (6.9 waves) 296
+// resident CTAs that start together march through the planes in lockstep and phase B measured 0.967 ms in that
+// state against 0.857 ms with the scheduler's staggered starts -- the same 13 % a static round-robin lost.
 inline int persistent_grid(const TilePlan& p, int nz) {
   const long long items = (long long)p.tiles_z * p.tiles_y * nz;
   const long long slots = (long long)kNumSMs * 2;
+  if (items > 3 * slots) return (int)items;
   return (int)(items < slots ? (items > 0 ? items : 1) : slots);
 }
 
