@@ -232,7 +232,8 @@ __device__ __forceinline__ T apply_cell(const GridDev& g, const EqDev<T>& eq, co
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       if (!g.act[a]) continue;
-      const int i = c.i[a], n = g.n[a];
+      // (axis 0 of a slab: the GLOBAL plane index decides -- local plane 0 may be a ghost plane)
+      const int i = (a == 0) ? c.i[0] + g.goff0 : c.i[a], n = (a == 0) ? g.gn0 : g.n[a];
       if (i != 0 && i != n - 1) continue;
       const long long st = stride_of(g, a) * (i == 0 ? 1 : -1);
       T t = (T)2 * phi[idx];
@@ -284,10 +285,11 @@ __device__ __forceinline__ void grad_cell(const GridDev& g, const OpDev<T>& o, c
     T s = ct[0] * vp;
     s = s + ct[1] * vc;
     s = s + ct[2] * vm;
-    if (o.edge) {  // edge=True Grad (fdc.py:260-288)
-      if (i == 0)
+    if (o.edge) {  // edge=True Grad (fdc.py:260-288); axis 0 of a slab: the GLOBAL plane index decides
+      const int gi = (a == 0) ? i + g.goff0 : i, gn = (a == 0) ? g.gn0 : n;
+      if (gi == 0)
         s = -edge_first<T>(phi, idx, st, 1) / o.dx[a];
-      else if (i == n - 1)
+      else if (gi == gn - 1)
         s = edge_first<T>(phi, idx, st, -1) / o.dx[a];
     }
     if (o.param_field != nullptr)
@@ -320,7 +322,9 @@ __global__ void __launch_bounds__(kBlock) k_apply_shell(GridDev g, EqDev<T> eq, 
   if (up && g.n[ax] == 1) return;
   const int bb = (ax == 0) ? 1 : 0, cc = (ax == 2) ? 1 : 2;
   const long long ncell = (long long)g.n[bb] * g.n[cc];
-  const int plane = up ? g.n[ax] - 1 : 0;
+  // axis 0 of a slab: the local plane that holds the global face, if this rank has it
+  const int plane = (ax == 0) ? (up ? g.gn0 - 1 : 0) - g.goff0 : (up ? g.n[ax] - 1 : 0);
+  if (plane < 0 || plane >= g.n[ax]) return;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ncell;
        k += (long long)gridDim.x * blockDim.x) {
     int ib = (int)(k / g.n[cc]), ic = (int)(k - (long long)ib * g.n[cc]);
@@ -330,8 +334,11 @@ __global__ void __launch_bounds__(kBlock) k_apply_shell(GridDev g, EqDev<T> eq, 
     c.i[cc] = ic;
     c.idx = ((long long)c.i[0] * g.n[1] + c.i[1]) * g.n[2] + c.i[2];
     bool dup = false;
-    for (int e = 0; e < ax; ++e)
-      if (g.act[e]) dup |= (c.i[e] == 0) | (c.i[e] == g.n[e] - 1);
+    for (int e = 0; e < ax; ++e) {
+      if (!g.act[e]) continue;
+      const int gi = (e == 0) ? c.i[0] + g.goff0 : c.i[e], gn = (e == 0) ? g.gn0 : g.n[e];
+      dup |= (gi == 0) | (gi == gn - 1);
+    }
     if (dup) continue;
     if (GRAD)
       grad_cell<T>(g, eq.op[0], phi, out, c);
