@@ -175,7 +175,9 @@ typedef struct {
                           (no TMA), 3 = CG as one persistent cooperative kernel (small grids, every
                           face Dirichlet), 4 = like 0 but never a whole-solve kernel, 5 = CG as ONE
                           cooperative launch of the two TMA phases (L2-resident grids, every face Dirichlet;
-                          auto takes it between 80 k and 1.5 M cells) */
+                          auto takes it between 80 k and 1.5 M cells on 3-D meshes), 6 = CG as ONE cooperative
+                          launch with x, r, d resident in the SMs' shared memory (2-D meshes up to ~1.2 M fp64
+                          cells, every face Dirichlet; auto takes it above 80 k cells whenever it fits) */
   int32_t flags;       /* PA_FLAG_* */
   int32_t reserved;
 } pa_solver_cfg;

@@ -12,6 +12,7 @@
 #include "kernels_tma.cuh"
 #include "kernels_tma_pw.cuh"
 #include "kernels_small.cuh"
+#include "kernels_resident.cuh"
 #include "dist.cuh"
 
 namespace pa {
@@ -55,6 +56,14 @@ PA_EXTERN(float)
 PA_EXTERN_APPLY(double)
 PA_EXTERN_APPLY(float)
 #undef PA_EXTERN_APPLY
+#define PA_EXTERN_RES(T)                                                                                           \
+  extern template bool launch_euler_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, \
+                                                T*, T*, const T*, T, int);                                         \
+  extern template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*,      \
+                                             const T*, SolverState*, int);
+PA_EXTERN_RES(double)
+PA_EXTERN_RES(float)
+#undef PA_EXTERN_RES
 extern template bool launch_bi_st_tma<double>(cudaStream_t, const GridDev&, const EqDev<double>&, const TilePlan&,
                                               const double*, const double*, const double*, double*, double*,
                                               SolverState*, double*, int);
@@ -847,7 +856,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   TmaPlan tmap;
   bool use_tma = false;
   // 4: fused kernels, never a whole-solve kernel; 5: the cooperative whole-solve TMA kernel (L2-resident grids)
-  const bool auto_fused = cfg->variant == 0 || cfg->variant == 4 || cfg->variant == 5;
+  const bool auto_fused = cfg->variant == 0 || cfg->variant == 4 || cfg->variant == 5 || cfg->variant == 6;
   if (method == PA_METHOD_CG && auto_fused) {
     use_tma = plan_tma<T>(g, *peq, nfaces, faces, x, x_alt, (T*)w.vec[0], (T*)w.vec[1], (T*)w.vec[2], tmap);
     if (use_tma) tmap.tile.fuse_fin = static_shell(nfaces, faces);
@@ -1014,6 +1023,27 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
     eq_cg.nops = 1;
     eq_cg.op[0].has_shift = 1;
     eq_cg.op[0].shift = (T)c;
+  }
+
+  // 2-D grids that fit the SMs' shared memory: the whole solve as ONE cooperative launch with x, r, d resident
+  // (kernels_resident.cuh).  variant 6 forces it; auto (0) takes it whenever it fits.
+  if (method == PA_METHOD_CG && use_tma && tma_flat(g) && !dist && !nonlinear && static_shell(nfaces, faces) &&
+      !tmap.tile.wrap && !tmap.contract &&
+      (cfg->variant == 6 || (cfg->variant == 0 && g.cells > kSmallCgCells && getenv("PA_NO_RESIDENT") == nullptr))) {
+    PA_CUDA(cudaMemcpyAsync(x_alt, x, vbytes, cudaMemcpyDeviceToDevice, stream));  // the static shell
+    if (launch_cg_resident<T>(stream, g, eq_cg, x, x_alt, (const T*)w.vec[0], (const T*)w.vec[1], w.st, cfg->max_it)) {
+      L.count += 2;
+      SolverState* hs = nullptr;
+      int rcp = poll_state(stream, w.st, &hs);
+      if (rcp != PA_OK) return rcp;
+      PA_CUDA(cudaGetLastError());
+      if (!hs->done) return fail(PA_ERR_CUDA, "resident CG kernel returned without latching `done`");
+      fill_report(rep, hs, L.count);
+      set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
+      return PA_OK;
+    }
+    cudaGetLastError();
+    if (cfg->variant == 6) return fail(PA_ERR_UNSUPPORTED, "resident CG: the grid does not fit the SMs' shared memory (2-D meshes only)");
   }
 
   // L2-resident grids: the whole solve as ONE cooperative launch of the two TMA phases (kernels_tma.cuh
@@ -1610,7 +1640,20 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
     std::swap(cur, nxt);
     ++done_steps;
   }
-  const int remaining = nsteps - done_steps;
+  int remaining = nsteps - done_steps;
+  // 2-D grids that fit the SMs' shared memory: all remaining steps in ONE launch, the field resident in shared
+  // memory (kernels_resident.cuh).  PA_EULER_VARIANT=stream keeps the per-step launches (A/B runs; read per call).
+  if (remaining >= 2 && !dist && stat && tma) {
+    bool linear = true;
+    for (int k = 0; k < peq->nops; ++k) linear &= peq->ops[k].kind == PA_OP_STAR;
+    const char* ev = getenv("PA_EULER_VARIANT");
+    if (linear && !(ev != nullptr && strcmp(ev, "stream") == 0) &&
+        launch_euler_resident<T>(s, g, *peq, eq_a, cur, nxt, rhs, (T)dt, remaining)) {
+      if (remaining & 1) std::swap(cur, nxt);
+      done_steps = nsteps;
+      remaining = 0;
+    }
+  }
   if (remaining >= 4) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;

@@ -1,0 +1,11 @@
+// Translation unit: shared-memory-resident kernels for 2-D grids (explicit Euler, whole-solve CG)
+#include "kernels_resident.cuh"
+namespace pa {
+#define PA_INST(T)                                                                                                  \
+  template bool launch_euler_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, T*, T*, \
+                                         const T*, T, int);                                                         \
+  template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*, const T*, SolverState*, int);
+PA_INST(double)
+PA_INST(float)
+#undef PA_INST
+}  // namespace pa

@@ -215,7 +215,8 @@ def _run_solver_case(case, **extra):
 
 
 @pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["auto", "generic", "tiled", "persistent", "fused_tma", "coop_tma"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6],
+                         ids=["auto", "generic", "tiled", "persistent", "fused_tma", "coop_tma", "resident"])
 def test_solver_fixtures(case, variant):
     """Parity bar per solver:
     CG        — iteration count EXACT, final tol to 1e-10 absolute, solution to 1e-9 relative.
