@@ -60,7 +60,7 @@ PA_EXTERN_APPLY(float)
   extern template bool launch_euler_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, \
                                                 T*, T*, const T*, T, int);                                         \
   extern template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*,      \
-                                             const T*, SolverState*, int);
+                                             const T*, SolverState*, int, int);
 PA_EXTERN_RES(double)
 PA_EXTERN_RES(float)
 #undef PA_EXTERN_RES
@@ -1031,7 +1031,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       !tmap.tile.wrap && !tmap.contract &&
       (cfg->variant == 6 || (cfg->variant == 0 && g.cells > kSmallCgCells && getenv("PA_NO_RESIDENT") == nullptr))) {
     PA_CUDA(cudaMemcpyAsync(x_alt, x, vbytes, cudaMemcpyDeviceToDevice, stream));  // the static shell
-    if (launch_cg_resident<T>(stream, g, eq_cg, x, x_alt, (const T*)w.vec[0], (const T*)w.vec[1], w.st, cfg->max_it)) {
+    if (launch_cg_resident<T>(stream, g, eq_cg, x, x_alt, (const T*)w.vec[0], (const T*)w.vec[1], w.st, cfg->max_it, res_coef_uniform(*peq) ? 1 : 0)) {
       L.count += 2;
       SolverState* hs = nullptr;
       int rcp = poll_state(stream, w.st, &hs);

@@ -28,6 +28,10 @@
 // boundary cells never change after the first BC application), single GPU, cooperative launch available
 // (co-residency is what makes waiting on another CTA legal).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels_tma_pw.cuh"
 
 namespace pa {
@@ -106,7 +110,7 @@ __device__ __forceinline__ void ldcg_vec(const T* p, T (&v)[VecOf<T>::N]) {
 struct ResCtx {
   int n2, nv;       // row length in cells / in vectors
   int row0, rows;   // first owned global row, owned rows
-  int dq, dr;       // kResThreads / nv, kResThreads % nv  (incremental (row, vector) walk)
+  int dq, dr;       // kResThreads / nv, kResThreads % nv  (incremental (position, vector) walk)
 };
 template <typename T>
 __device__ __forceinline__ void res_ctx_init(ResCtx& c, const GridDev& g, int R) {
@@ -125,16 +129,134 @@ struct ResLL {
   line* base;
   int n2, ctas;
   __device__ __forceinline__ line* row(unsigned parity, int cta, int side) const {
-    return base + (((long long)(parity & 1u) * ctas + cta) * 2 + side) * n2;
+    return base + (((int)(parity & 1u) * ctas + cta) * 2 + side) * n2;  // (< 2^31 lines, res_plan)
   }
 };
 
-// the operator sum at one cell of a 2-D grid: star_cells_eq (kernels_tma_pw.cuh) with K::FLAT, same operation
+// ---- the thread's work items of one pass --------------------------------------------------------------
+// ONE loop body serves every row of a pass -- the kernels' code must stay small: a first version with separate
+// code for boundary rows, a two-row register march for the interior and its remainders was > 64 KB of SASS per
+// kernel, every piece of it executed once per step, and ran at ~1 us per 1024-cell row (instruction fetch) against
+// 0.24 us of fp64 issue.
+// A pass visits the CTA's rows in positions 0 .. rows-1; the two boundary rows (first and last owned row) sit at
+// positions rs-1 and rs: rs = 1 puts them first, rs = rows-1 last, anything between in the middle of the pass.
+// Item i = tid + k * 512 is vector (i % nv) of the row at position (i / nv).
+struct ResIt {
+  int j, cv;
+};
+__device__ __forceinline__ ResIt res_it_first(const ResCtx& c) {
+  ResIt a;
+  a.j = (int)threadIdx.x / c.nv;
+  a.cv = (int)threadIdx.x - a.j * c.nv;
+  return a;
+}
+__device__ __forceinline__ ResIt res_it_next(const ResCtx& c, ResIt a) {
+  a.j += c.dq;
+  a.cv += c.dr;
+  if (a.cv >= c.nv) {
+    a.cv -= c.nv;
+    ++a.j;
+  }
+  return a;
+}
+__device__ __forceinline__ int res_row_at(const ResCtx& c, int rs, int j) {
+  if (c.rows < 2) return 0;
+  return j < rs - 1 ? j + 1 : (j == rs - 1 ? 0 : (j == rs ? c.rows - 1 : j - 1));
+}
+// neighbour rows of local row `row` that live in another CTA: bit 0 = the row above, bit 1 = the row below
+__device__ __forceinline__ unsigned res_halo_dirs(const ResCtx& c, int row) {
+  unsigned m = 0u;
+  if (row == 0 && blockIdx.x > 0) m |= 1u;
+  if (row == c.rows - 1 && blockIdx.x + 1 < gridDim.x) m |= 2u;
+  return m;
+}
+// One halo vector: from the neighbour's LL row (sequence number seq; seq == 0: from the global array g0, the state
+// before the first exchange) into the halo row of the resident buffer (`buf0` = its row 0; halo rows at -1 and at
+// c.rows).  Non-blocking calls return false when the line has not arrived yet.  The halo cell (side, column) is
+// private to the thread that computes the boundary vector of that column: no barrier between this store and the
+// thread's own later loads.
+template <typename T>
+__device__ __forceinline__ bool res_halo_get(const ResCtx& c, const ResLL<T>& ll, T* buf0, int col, int below,
+                                             unsigned parity, unsigned seq, const T* g0, bool blocking) {
+  constexpr int VEC = VecOf<T>::N;
+  T v[VEC];
+  T* dst = buf0 + (below ? c.rows : -1) * c.n2 + col;
+  if (seq == 0u) {
+    ldcg_vec<T>(g0 + (c.row0 + (below ? c.rows : -1)) * c.n2 + col, v);
+  } else {
+    const typename LLOf<T>::line* src = ll.row(parity, (int)blockIdx.x + (below ? 1 : -1), below ? 0 : 1) + col;
+    if (blocking) {
+      ll_load<T, VEC>(src, seq, v);
+    } else {
+      bool ok = true;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) ok &= ll_try(src + e, seq, v[e]);
+      if (!ok) return false;
+    }
+  }
+  sts_vec<T>(dst, v);
+  return true;
+}
+// Request the halo vectors of the thread's boundary items early, without waiting (`got`: one bit per halo vector in
+// item order).  What had not arrived is fetched again, blocking, when the item is computed (res_halo_need).
+template <typename T>
+__device__ __forceinline__ unsigned res_halo_prefetch(const ResCtx& c, const ResLL<T>& ll, T* buf0, int rs,
+                                                      unsigned parity, unsigned seq, const T* g0) {
+  unsigned got = 0u;
+  int bit = 0;
+  // the thread's items at the two boundary positions rs-1, rs (one position if the CTA owns a single row), in item
+  // order -- the order in which the pass meets them
+  const int lo = c.rows < 2 ? 0 : (rs - 1) * c.nv, hi = c.rows < 2 ? c.nv : (rs + 1) * c.nv;
+  for (int i = lo + (((int)threadIdx.x - lo) & (kResThreads - 1)); i < hi; i += kResThreads) {
+    const int j = c.rows < 2 ? 0 : (i < rs * c.nv ? rs - 1 : rs);
+    const int cv = i - j * c.nv;
+    const unsigned dirs = res_halo_dirs(c, res_row_at(c, rs, j));
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      if ((dirs >> b) & 1u) {
+        if (res_halo_get<T>(c, ll, buf0, cv * VecOf<T>::N, b, parity, seq, g0, false)) got |= 1u << (bit & 31);
+        ++bit;
+      }
+  }
+  return got;
+}
+template <typename T>
+__device__ __forceinline__ void res_halo_need(const ResCtx& c, const ResLL<T>& ll, T* buf0, int row, int col,
+                                              unsigned parity, unsigned seq, const T* g0, unsigned got, int& bit) {
+  if (row != 0 && row != c.rows - 1) return;
+  const unsigned dirs = res_halo_dirs(c, row);
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+    if ((dirs >> b) & 1u) {
+      if (!((got >> (bit & 31)) & 1u)) res_halo_get<T>(c, ll, buf0, col, b, parity, seq, g0, true);
+      ++bit;
+    }
+}
+// a vector of a boundary row goes to the neighbour(s) that read it
+template <typename T>
+__device__ __forceinline__ void res_send(const ResCtx& c, const ResLL<T>& ll, int row, int col, unsigned parity,
+                                         unsigned seq, const T (&v)[VecOf<T>::N]) {
+  if (row == 0 && blockIdx.x > 0) ll_store_vec<T, VecOf<T>::N>(ll.row(parity, blockIdx.x, 0) + col, seq, v);
+  if (row == c.rows - 1 && blockIdx.x + 1 < gridDim.x)
+    ll_store_vec<T, VecOf<T>::N>(ll.row(parity, blockIdx.x, 1) + col, seq, v);
+}
+
+// ---- the operator ---------------------------------------------------------------------------------------
+// The operator sum at one cell of a 2-D grid: star_cells_eq (kernels_tma_pw.cuh) with K::FLAT, same operation
 // order; the CG form (one operator + the implicit-Euler shift, star_cells of kernels_tma.cuh) is the same code
-// with nops == 1
+// with nops == 1.
+template <typename T, int NOPS>
+struct ResScales {
+  OpScale<T> sc[NOPS > 0 ? NOPS : kMaxOps];
+  __device__ __forceinline__ explicit ResScales(const EqDev<T>& eq) {
+#pragma unroll
+    for (int q = 0; q < (NOPS > 0 ? NOPS : kMaxOps); ++q)
+      if (q < (NOPS > 0 ? NOPS : eq.nops)) sc[q] = op_scale<T>(eq.op[q]);
+  }
+};
 template <typename T, bool LEAN, int NOPS>
-__device__ __forceinline__ T res_star(const EqDev<T>& eq, const OpScale<T> (&sc)[NOPS > 0 ? NOPS : kMaxOps], int clx,
-                                      int cz, T v0, T xp, T xm, T zp, T zm) {
+__device__ __forceinline__ T res_star(const EqDev<T>& eq, const ResScales<T, NOPS>& scs, int clx, int cz, T v0, T xp,
+                                      T xm, T zp, T zm) {
   constexpr int MAXO = NOPS > 0 ? NOPS : kMaxOps;
   const int nops = NOPS > 0 ? NOPS : eq.nops;
   const int ix = LEAN ? 0 : clx, iz = LEAN ? 0 : cz;
@@ -143,6 +265,7 @@ __device__ __forceinline__ T res_star(const EqDev<T>& eq, const OpScale<T> (&sc)
   for (int q = 0; q < MAXO; ++q) {
     if (q >= nops) break;
     const OpDev<T>& o = eq.op[q];
+    const OpScale<T>& sc = scs.sc[q];
     T s = o.coef[0][ix][0] * xp;
     s = s + o.coef[0][ix][1] * v0;
     s = s + o.coef[0][ix][2] * xm;
@@ -151,7 +274,7 @@ __device__ __forceinline__ T res_star(const EqDev<T>& eq, const OpScale<T> (&sc)
     s2 = s2 + o.coef[2][iz][1] * v0;
     s2 = s2 + o.coef[2][iz][2] * zm;
     acc = acc + s2;
-    if (sc[q].use) acc = acc * sc[q].scale;
+    if (sc.use) acc = acc * sc.scale;
     res = res + acc;
     if (o.has_shift) {
       const T m = o.shift * v0;
@@ -160,17 +283,42 @@ __device__ __forceinline__ T res_star(const EqDev<T>& eq, const OpScale<T> (&sc)
   }
   return res;
 }
-
-// A(phi) on one vector of the thread's cells: `c` points at the vector inside its resident row (for the columns
-// left and right of it), vm / vp are the same columns of the rows above / below.  emit(e, in_region, value).
-template <typename T, int NOPS, typename F>
-__device__ __forceinline__ void res_apply_vec(const GridDev& g, const EqDev<T>& eq,
-                                              const OpScale<T> (&sc)[NOPS > 0 ? NOPS : kMaxOps], const T* c, int n2,
-                                              int grow, int col, const T (&v0)[VecOf<T>::N],
-                                              const T (&vm)[VecOf<T>::N], const T (&vp)[VecOf<T>::N], F emit) {
+// boundary-adjacent cells (coefficient classes != 0, cells outside the region): two rows and two columns of the grid.
+// (Inline: as a real call it forced the vectors of EVERY item through local memory, 3 STL per item on the hot path;
+// cold code costs no instruction fetches.)
+template <typename T, int NOPS>
+__device__ __forceinline__ void res_apply_general(const GridDev& g, const EqDev<T>& eq, const ResScales<T, NOPS>& scs,
+                                                  int clx, int col, const T* v0,
+                                               const T* vm, const T* vp, T zl, T zr, T* ad, unsigned* inmask) {
   constexpr int VEC = VecOf<T>::N;
-  const T zl = col > 0 ? c[-1] : (T)0;
-  const T zr = col + VEC < n2 ? c[VEC] : (T)0;
+  unsigned m = 0u;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const int z = col + e;
+    const bool in = z >= g.lo[2] && z < g.hi[2];
+    const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
+    const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
+    T a = (T)0;
+    if (in) {
+      a = res_star<T, false, NOPS>(eq, scs, clx, coef_class(g, 2, z), v0[e], vp[e], vm[e], zp, zm);
+      m |= 1u << e;
+    }
+    ad[e] = a;
+  }
+  *inmask = m;
+}
+// A(phi) on one vector whose row is inside the region: ad[e] and the mask of region cells.  `p` points at the vector
+// inside a resident buffer (rows n2 apart, the rows above and below in place -- halo rows included).
+template <typename T, int NOPS>
+__device__ __forceinline__ unsigned res_apply_vec(const GridDev& g, const EqDev<T>& eq, const ResScales<T, NOPS>& scs,
+                                                  const T* p, int n2, int grow, int col,
+                                                  const T (&v0)[VecOf<T>::N], T (&ad)[VecOf<T>::N]) {
+  constexpr int VEC = VecOf<T>::N;
+  T vm[VEC], vp[VEC];
+  lds_vec<T>(p - n2, vm);
+  lds_vec<T>(p + n2, vp);
+  const T zl = col > 0 ? p[-1] : (T)0;
+  const T zr = col + VEC < n2 ? p[VEC] : (T)0;
   const int clx = coef_class(g, 0, grow);
   const int lo2 = g.lo[2] > 2 ? g.lo[2] : 2, hi2 = g.hi[2] < n2 - 2 ? g.hi[2] : n2 - 2;
   if (clx == 0 && col >= lo2 && col + VEC <= hi2) {
@@ -178,151 +326,131 @@ __device__ __forceinline__ void res_apply_vec(const GridDev& g, const EqDev<T>& 
     for (int e = 0; e < VEC; ++e) {
       const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
       const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
-      emit(e, true, res_star<T, true, NOPS>(eq, sc, 0, 0, v0[e], vp[e], vm[e], zp, zm));
+      ad[e] = res_star<T, true, NOPS>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
     }
-  } else {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int z = col + e;
-      const bool in = z >= g.lo[2] && z < g.hi[2];
-      const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
-      const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
-      T a = (T)0;
-      if (in) a = res_star<T, false, NOPS>(eq, sc, clx, coef_class(g, 2, z), v0[e], vp[e], vm[e], zp, zm);
-      emit(e, in, a);
-    }
+    return (1u << VEC) - 1u;
   }
-}
-
-// the same columns of the row above (dir -1) / below (+1) local row lr of a resident buffer `buf` (rows n2 apart):
-// from shared memory, or -- across the CTA's first / last row -- from the neighbour's LL row with sequence number
-// seq (seq == 0: from the global array `g0` instead, the state before the first exchange); rows outside the grid
-// read as zeros (they only reach shell cells, which are never computed)
-template <typename T>
-__device__ __forceinline__ void res_neighbour_row(const ResCtx& c, const ResLL<T>& ll, const T* buf, int lr, int col,
-                                                  int dir, unsigned parity, unsigned seq, const T* g0,
-                                                  T (&v)[VecOf<T>::N]) {
-  constexpr int VEC = VecOf<T>::N;
-  const int nr = lr + dir;
-  if (nr >= 0 && nr < c.rows) {
-    lds_vec<T>(buf + (long long)nr * c.n2 + col, v);
-    return;
-  }
-  const int ncta = (int)blockIdx.x + dir;
-  if (ncta < 0 || ncta >= (int)gridDim.x) {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) v[e] = (T)0;
-    return;
-  }
-  if (seq == 0u) {
-    ldcg_vec<T>(g0 + (long long)(c.row0 + nr) * c.n2 + col, v);
-    return;
-  }
-  ll_load<T, VEC>(ll.row(parity, ncta, dir < 0 ? 1 : 0) + col, seq, v);
-}
-
-// walk the vectors of local rows [ra, rb):  f(local row, column of the vector's first cell)
-template <typename F>
-__device__ __forceinline__ void res_rows(const ResCtx& c, int ra, int rb, F f) {
-  if (rb <= ra) return;
-  int lr = ra + (int)threadIdx.x / c.nv, cv = (int)threadIdx.x % c.nv;
-  while (lr < rb) {
-    f(lr, cv);
-    lr += c.dq;
-    cv += c.dr;
-    if (cv >= c.nv) {
-      cv -= c.nv;
-      ++lr;
-    }
-  }
-}
-// Interior rows as a MARCH: the thread keeps one column block and walks down a contiguous run of rows with the rows
-// above / at / below in registers (one 16-byte shared-memory load per row instead of three, no index arithmetic
-// per vector).  The general walk above costs more integer and address instructions per vector than the stencil has
-// fp64 instructions (measured: 0.55 us per 1024-cell row against 0.24 us of fp64 issue), so it is kept for the
-// boundary rows and for row lengths that do not map onto the 512 threads.
-// Mapping: nv >= 512: every thread takes columns tid, tid + 512, ... and all interior rows; nv < 512: G = 512 / nv
-// thread groups share the interior rows in contiguous runs.  `use`: the mapping keeps >= 85 % of the threads busy.
-struct ResMarch {
-  bool use;
-  int cv, cstep;  // first column block (in vectors) and the step to the next one
-  int ra, rb;     // local rows [ra, rb)
-};
-__device__ __forceinline__ ResMarch res_march(const ResCtx& c) {
-  ResMarch m;
-  const int nint = c.rows - 2;
-  m.cv = m.cstep = m.ra = m.rb = 0;
-  m.use = false;
-  if (nint < 1) return m;
-  if (c.nv >= kResThreads) {
-    const int passes = (c.nv + kResThreads - 1) / kResThreads;
-    m.use = c.nv * 20 >= passes * kResThreads * 17;
-    m.cv = threadIdx.x;
-    m.cstep = kResThreads;
-    m.ra = 1;
-    m.rb = c.rows - 1;
-  } else {
-    int G = kResThreads / c.nv;
-    if (G > nint) G = nint;
-    const int chunk = (nint + G - 1) / G;
-    m.use = (long long)nint * c.nv * 20 >= (long long)chunk * kResThreads * 17;
-    const int grp = threadIdx.x / c.nv;
-    m.cv = threadIdx.x - grp * c.nv;
-    m.cstep = c.nv;  // one column block per thread
-    m.ra = 1 + grp * chunk;
-    m.rb = min(m.ra + chunk, c.rows - 1);
-    if (grp >= G) m.rb = m.ra;
-  }
+  unsigned m;
+  res_apply_general<T, NOPS>(g, eq, scs, clx, col, v0, vm, vp, zl, zr, ad, &m);
   return m;
 }
-// f(local row, column, pointer to the vector in `buf`, v0, vm, vp) for the thread's share of the interior rows
-template <typename T, typename F>
-__device__ __forceinline__ void res_march_rows(const ResCtx& c, const ResMarch& m, const T* buf, F f) {
+
+// ---- the uniform-coefficient fast path ----------------------------------------------------------------
+// ncu on the item loop alone (1024^2): 2084 instructions per warp and step for 7 items of 58 fp64 instructions each,
+// 60 % issue-active, fp64 pipe 28 % -- the walk, the row mapping, the region / class tests and the addressing of the
+// general item cost four times the arithmetic, and one warp alone issues only every 4-6 cycles: a step is as slow as
+// its longest warp.  (A march over the class-0 interior only made it worse: the two warps that own the columns next to
+// the walls kept all their rows on the item loop and everybody waited for them.)
+// When the three coefficient classes of every operator hold the same numbers on both axes (UNI: no Neumann / Symmetry
+// face -- always the case here, every face is Dirichlet) no cell needs a class: a thread keeps ONE column block,
+// walks down its rows with the rows above / at / below in registers, two rows per trip, and runs nothing but loads,
+// stencil, a region select for the wall columns, and the store.  The CTA's first and last row are one more such trip,
+// fed from the halo rows.  All warps do the same work.
+// Mapping: nv a multiple of 512: every thread takes columns tid, tid + 512, ... and all rows; 512 a multiple of nv:
+// G = 512 / nv thread groups share the rows in contiguous runs, the last group takes the boundary rows as two of its
+// rows.  Other row lengths (and non-uniform coefficients) stay on the item loop.
+struct ResFast {
+  bool on;
+  bool boundary;   // this thread computes the CTA's first and last row (for its columns)
+  int ta, tb;      // this thread's interior rows [ta, tb)
+  int cv, cstep;   // this thread's first column block (vectors) and the step to its next one
+};
+template <typename T>
+__device__ __forceinline__ ResFast res_fast_init(const ResCtx& c, const GridDev& g, bool uni) {
+  ResFast f;
+  f.on = false;
+  f.boundary = false;
+  f.ta = f.tb = f.cv = 0;
+  f.cstep = 1;
+  // interior rows must all be region rows (every face Dirichlet: the region is the grid minus its shell)
+  if (!uni || g.lo[0] > 1 || g.hi[0] < g.n[0] - 1) return f;
+  const int nint = c.rows > 2 ? c.rows - 2 : 0;
+  if (c.nv % kResThreads == 0) {
+    f.on = true;
+    f.boundary = true;
+    f.cv = threadIdx.x;
+    f.cstep = kResThreads;
+    f.ta = 1;
+    f.tb = 1 + nint;
+  } else if (kResThreads % c.nv == 0) {
+    f.on = true;
+    const int G = kResThreads / c.nv, grp = (int)threadIdx.x / c.nv;
+    const int chunk = (nint + 2 + G - 1) / G;  // rows per group, the boundary rows counted as two
+    f.cv = (int)threadIdx.x - grp * c.nv;
+    f.cstep = c.nv;
+    f.ta = min(1 + grp * chunk, 1 + nint);
+    f.tb = grp == G - 1 ? 1 + nint : min(f.ta + chunk, 1 + nint);
+    f.boundary = grp == G - 1;
+  }
+  return f;
+}
+// rows [ra, rb) of the thread's column blocks, two rows per trip (both rows are computed before either is stored:
+// the compiler must assume that `cur` and `nxt` alias):  cell(v0, vm, vp, zl, zr, local row, col) -> o, put(row, col, o)
+template <typename T, typename FC, typename FP>
+__device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f, const T* cur, int ra, int rb,
+                                               FC cell, FP put) {
   constexpr int VEC = VecOf<T>::N;
-  if (m.rb <= m.ra) return;
-  for (int cv = m.cv; cv < c.nv; cv += m.cstep) {
+  if (rb <= ra) return;
+  const int n2 = c.n2;
+  for (int cv = f.cv; cv < c.nv; cv += f.cstep) {
     const int col = cv * VEC;
-    const T* p = buf + (long long)m.ra * c.n2 + col;
-    T vm[VEC], v0[VEC], vp[VEC];
-    lds_vec<T>(p - c.n2, vm);
+    const T* p = cur + ra * n2 + col;
+    T vm[VEC], v0[VEC];
+    lds_vec<T>(p - n2, vm);
     lds_vec<T>(p, v0);
-    for (int lr = m.ra; lr < m.rb; ++lr) {
-      lds_vec<T>(p + c.n2, vp);
-      f(lr, col, p, v0, vm, vp);
+    int lr = ra;
+    for (; lr + 1 < rb; lr += 2) {
+      T v1[VEC], v2[VEC], oa[VEC], ob[VEC];
+      lds_vec<T>(p + n2, v1);
+      lds_vec<T>(p + 2 * n2, v2);
+      const T zla = p[-1], zra = p[VEC], zlb = p[n2 - 1], zrb = p[n2 + VEC];
+      cell(v0, vm, v1, zla, zra, lr, col, oa);
+      cell(v1, v0, v2, zlb, zrb, lr + 1, col, ob);
+      put(lr, col, oa);
+      put(lr + 1, col, ob);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        vm[e] = v0[e];
-        v0[e] = vp[e];
+        vm[e] = v1[e];
+        v0[e] = v2[e];
       }
-      p += c.n2;
+      p += 2 * n2;
+    }
+    if (lr < rb) {
+      T v1[VEC], oa[VEC];
+      lds_vec<T>(p + n2, v1);
+      const T zla = p[-1], zra = p[VEC];
+      cell(v0, vm, v1, zla, zra, lr, col, oa);
+      put(lr, col, oa);
     }
   }
 }
-
-// the same share of the interior rows without the register window:  f(local row, column)
-template <typename T, typename F>
-__device__ __forceinline__ void res_march_plain(const ResCtx& c, const ResMarch& m, F f) {
-  if (m.rb <= m.ra) return;
-  for (int cv = m.cv; cv < c.nv; cv += m.cstep)
-    for (int lr = m.ra; lr < m.rb; ++lr) f(lr, cv * VecOf<T>::N);
-}
-
-// the first and the last owned row (one row if the CTA owns a single one)
-template <typename F>
-__device__ __forceinline__ void res_boundary_rows(const ResCtx& c, F f) {
-  const int nb = c.rows > 1 ? 2 : 1;
-  for (int i = threadIdx.x; i < nb * c.nv; i += kResThreads) {
-    const int k = i >= c.nv ? 1 : 0;
-    f(k ? c.rows - 1 : 0, i - k * c.nv);
+// the CTA's first and last row (one row if it owns a single one) for the thread's column blocks, as ONE trip; the
+// halo rows of `cur` are in place (res_halo_need has run for these items)
+template <typename T, typename FC, typename FP>
+__device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const T* cur, int col, FC cell, FP put) {
+  constexpr int VEC = VecOf<T>::N;
+  const int n2 = c.n2;
+  const T* pa = cur + col;
+  T a0[VEC], am[VEC], ap[VEC], oa[VEC];
+  lds_vec<T>(pa, a0);
+  lds_vec<T>(pa - n2, am);
+  lds_vec<T>(pa + n2, ap);
+  const T zla = pa[-1], zra = pa[VEC];
+  if (c.rows < 2) {
+    cell(a0, am, ap, zla, zra, 0, col, oa);
+    put(0, col, oa);
+    return;
   }
-}
-// a vector of a boundary row goes to the neighbour(s) that read it
-template <typename T>
-__device__ __forceinline__ void res_send(const ResCtx& c, const ResLL<T>& ll, int lr, int col, unsigned parity,
-                                         unsigned seq, const T (&v)[VecOf<T>::N]) {
-  if (lr == 0 && blockIdx.x > 0) ll_store_vec<T, VecOf<T>::N>(ll.row(parity, blockIdx.x, 0) + col, seq, v);
-  if (lr == c.rows - 1 && blockIdx.x + 1 < gridDim.x)
-    ll_store_vec<T, VecOf<T>::N>(ll.row(parity, blockIdx.x, 1) + col, seq, v);
+  const T* pb = cur + (c.rows - 1) * n2 + col;
+  T b0[VEC], bm[VEC], bp[VEC], ob[VEC];
+  lds_vec<T>(pb, b0);
+  lds_vec<T>(pb - n2, bm);
+  lds_vec<T>(pb + n2, bp);
+  const T zlb = pb[-1], zrb = pb[VEC];
+  cell(a0, am, ap, zla, zra, 0, col, oa);
+  cell(b0, bm, bp, zlb, zrb, c.rows - 1, col, ob);
+  put(0, col, oa);
+  put(c.rows - 1, col, ob);
 }
 
 // =========================================================================================
@@ -330,86 +458,171 @@ __device__ __forceinline__ void res_send(const ResCtx& c, const ResLL<T>& ll, in
 // b0 holds phi on entry; step s reads buffer s&1 and writes (s+1)&1; the last TWO steps store every row to
 // global memory, so that on exit b[nsteps&1] is the result and the other array the step before it (VARo).
 // Sequence numbers seq0+1 .. seq0+nsteps are this launch's (never reused on the same exchange buffer).
+// The boundary rows sit in the MIDDLE of a step: the neighbours' lines (stored in the middle of their previous
+// step) are requested first, travel while the first part of the interior is computed, and this step's boundary
+// rows are on their way while the second part is.
 // =========================================================================================
 template <typename T, int NOPS, bool HAS_RHS>
 __global__ void __launch_bounds__(kResThreads, 1)
-k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0, T* __restrict__ b1, const T* __restrict__ rhs, T dt,
-                 int nsteps, int R, typename LLOf<T>::line* llbase, unsigned seq0) {
+k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
+                 T* __restrict__ b1, const T* __restrict__ rhs, T dt, int nsteps, int R,
+                 typename LLOf<T>::line* llbase, unsigned seq0, int uni, unsigned long long* dbg) {
   constexpr int VEC = VecOf<T>::N;
-  constexpr int MAXO = NOPS > 0 ? NOPS : kMaxOps;
+  // PA_RES_DEBUG: time stamps of one step, CTA gridDim/2, thread 0 (null in normal runs)
+  auto stamp = [&](int s, int k) {
+    if (dbg != nullptr && s == 8 && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) dbg[k] = global_timer_ns();
+  };
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
   ResCtx c;
   res_ctx_init<T>(c, g, R);
   const ResLL<T> ll{llbase, c.n2, (int)gridDim.x};
-  const long long rowlen = c.n2;
-  T* const sb0 = reinterpret_cast<T*>(base);
-  T* const sb1 = sb0 + (long long)R * rowlen;
+  const int rowlen = c.n2;  // (a resident grid has < 2^31 cells: 32-bit offsets everywhere)
+  // two buffers of R + 2 rows; sb* point at row 0, the halo rows are rows -1 and c.rows
+  T* const sb0 = reinterpret_cast<T*>(base) + rowlen;
+  T* const sb1 = sb0 + (R + 2) * rowlen;
 
-  for (int i = threadIdx.x; i < c.rows * c.nv; i += kResThreads) {  // resident copy of the owned rows
-    const int lr = i / c.nv, cv = i - lr * c.nv;
+  for (int i = threadIdx.x; i < (c.rows + 2) * c.nv; i += kResThreads) {  // resident copy, halo rows zeroed
+    const int lr = i / c.nv - 1, cv = i - (lr + 1) * c.nv;
     T v[VEC];
-    ldcg_vec<T>(b0 + (long long)(c.row0 + lr) * rowlen + cv * VEC, v);
-    sts_vec<T>(sb0 + (long long)lr * rowlen + cv * VEC, v);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = (T)0;
+    sts_vec<T>(sb1 + lr * rowlen + cv * VEC, v);
+    if (lr >= 0 && lr < c.rows) ldcg_vec<T>(b0 + (c.row0 + lr) * rowlen + cv * VEC, v);
+    sts_vec<T>(sb0 + lr * rowlen + cv * VEC, v);
   }
   __syncthreads();
 
-  OpScale<T> sc[MAXO];
-#pragma unroll
-  for (int q = 0; q < MAXO; ++q)
-    if (q < (NOPS > 0 ? NOPS : eq.nops)) sc[q] = op_scale<T>(eq.op[q]);
-
-  const ResMarch march = res_march(c);
+  const ResScales<T, NOPS> scs(eq);
+  const ResFast fast = res_fast_init<T>(c, g, uni != 0);
+  // item loop: the boundary rows in the middle of the pass; fast path: the thread's first 2/5 of its rows, its boundary
+  // trip, the rest of its rows
+  const int rs = c.rows < 2 ? 1 : 1 + ((c.rows - 2) * 2) / 5;
+  const int fsplit = fast.ta + ((fast.tb - fast.ta) * 2) / 5;
   for (int s = 0; s < nsteps; ++s) {
-    const T* cur = (s & 1) ? sb1 : sb0;
+    T* cur = (s & 1) ? sb1 : sb0;
     T* nxt = (s & 1) ? sb0 : sb1;
     T* gout = (s & 1) ? b0 : b1;
-    const bool all_rows = s + 2 >= nsteps;
+    const bool all_rows = s + 2 >= nsteps, send = s + 1 < nsteps;
     const unsigned seq_in = s == 0 ? 0u : seq0 + (unsigned)s, seq_out = seq0 + (unsigned)s + 1u;
-    auto finish = [&](int lr, int col, const T* p, const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC],
-                      bool boundary) {
-      const int grow = c.row0 + lr;
-      T o[VEC];
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) o[e] = v0[e];
-      if (grow >= g.lo[0] && grow < g.hi[0]) {
+    stamp(s, 0);
+    if (fast.on) {
+      // ---- uniform coefficients: every cell of the region is the class-0 stencil ------------------------
+      unsigned got = 0u;
+      if (fast.boundary) {  // request the neighbours' lines for my columns (bit 2k: above, 2k+1: below, block k)
+        int k = 0;
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+          if (blockIdx.x > 0 && res_halo_get<T>(c, ll, cur, cv * VEC, 0, (unsigned)s, seq_in, b0, false))
+            got |= 1u << (2 * k);
+          if (blockIdx.x + 1 < gridDim.x && res_halo_get<T>(c, ll, cur, cv * VEC, 1, (unsigned)s, seq_in, b0, false))
+            got |= 2u << (2 * k);
+        }
+      }
+      auto cell = [&](const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC], T zl, T zr, int row, int col,
+                      T (&o)[VEC]) {
+        const int grow = c.row0 + row;
         T av[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) av[e] = (T)0;
         if (HAS_RHS) {
           typedef typename VecOf<T>::type V;
-          V q = __ldg(reinterpret_cast<const V*>(rhs + (long long)grow * rowlen + col));
+          V q = __ldg(reinterpret_cast<const V*>(rhs + grow * rowlen + col));
           const T* qs = reinterpret_cast<const T*>(&q);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) av[e] = qs[e];
         }
-        res_apply_vec<T, NOPS>(g, eq, sc, p, c.n2, grow, col, v0, vm, vp, [&](int e, bool in, T a) {
-          if (in) {
-            const T res = av[e] - a;
-            o[e] = v0[e] + dt * res;
+        const bool rin = grow >= g.lo[0] && grow < g.hi[0];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
+          const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
+          const T a = res_star<T, true, NOPS>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+          const T res = av[e] - a;
+          const T xn = v0[e] + dt * res;
+          const int z = col + e;
+          o[e] = (rin && z >= g.lo[2] && z < g.hi[2]) ? xn : v0[e];  // the wall columns / rows keep their values
+        }
+      };
+      auto put = [&](int row, int col, const T (&o)[VEC]) {
+        sts_vec<T>(nxt + row * rowlen + col, o);
+        if (all_rows) sts_vec<T>(gout + (c.row0 + row) * rowlen + col, o);
+      };
+      auto put_boundary = [&](int row, int col, const T (&o)[VEC]) {
+        put(row, col, o);
+        if (send) res_send<T>(c, ll, row, col, (unsigned)(s + 1), seq_out, o);
+      };
+      for (int seg = 0; seg < 2; ++seg) {  // ONE instance of the march
+        res_fast_march<T>(c, fast, cur, seg == 0 ? fast.ta : fsplit, seg == 0 ? fsplit : fast.tb, cell, put);
+        if (seg == 0 && fast.boundary) {
+          int k = 0;
+          for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+            const int col = cv * VEC;
+            if (blockIdx.x > 0 && !((got >> (2 * k)) & 1u))
+              res_halo_get<T>(c, ll, cur, col, 0, (unsigned)s, seq_in, b0, true);
+            if (blockIdx.x + 1 < gridDim.x && !((got >> (2 * k + 1)) & 1u))
+              res_halo_get<T>(c, ll, cur, col, 1, (unsigned)s, seq_in, b0, true);
+            res_fast_boundary<T>(c, cur, col, cell, put_boundary);
           }
-        });
+        }
       }
-      sts_vec<T>(nxt + (long long)lr * rowlen + col, o);
-      if (boundary && s + 1 < nsteps) res_send<T>(c, ll, lr, col, (unsigned)(s + 1), seq_out, o);
-      if (all_rows) sts_vec<T>(gout + (long long)grow * rowlen + col, o);
-    };
-    auto cell_row = [&](int lr, int cv, bool boundary) {
-      const int col = cv * VEC;
-      const T* p = cur + (long long)lr * rowlen + col;
-      T v0[VEC], vm[VEC], vp[VEC];
-      lds_vec<T>(p, v0);
-      res_neighbour_row<T>(c, ll, cur, lr, col, -1, (unsigned)s, seq_in, b0, vm);
-      res_neighbour_row<T>(c, ll, cur, lr, col, +1, (unsigned)s, seq_in, b0, vp);
-      finish(lr, col, p, v0, vm, vp, boundary);
-    };
-    res_boundary_rows(c, [&](int lr, int cv) { cell_row(lr, cv, true); });
-    if (march.use)
-      res_march_rows<T>(c, march, cur, [&](int lr, int col, const T* p, const T (&v0)[VEC], const T (&vm)[VEC],
-                                           const T (&vp)[VEC]) { finish(lr, col, p, v0, vm, vp, false); });
-    else
-      res_rows(c, 1, c.rows - 1, [&](int lr, int cv) { cell_row(lr, cv, false); });
-    __syncthreads();  // end of step s: `cur` is free, `nxt` complete
+    } else {
+      // ---- any coefficients, any row length: the item loop ------------------------------------------------
+      const unsigned got = res_halo_prefetch<T>(c, ll, cur, rs, (unsigned)s, seq_in, b0);
+      int bit = 0;
+      // one item: the new values of a vector
+      auto compute = [&](ResIt a, int& row, int& col, T (&o)[VEC]) {
+        row = res_row_at(c, rs, a.j);
+        col = a.cv * VEC;
+        res_halo_need<T>(c, ll, cur, row, col, (unsigned)s, seq_in, b0, got, bit);
+        const int grow = c.row0 + row;
+        const T* p = cur + row * rowlen + col;
+        T v0[VEC];
+        lds_vec<T>(p, v0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[e] = v0[e];
+        if (grow >= g.lo[0] && grow < g.hi[0]) {
+          T av[VEC], ad[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) av[e] = (T)0;
+          if (HAS_RHS) {
+            typedef typename VecOf<T>::type V;
+            V q = __ldg(reinterpret_cast<const V*>(rhs + grow * rowlen + col));
+            const T* qs = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) av[e] = qs[e];
+          }
+          const unsigned in = res_apply_vec<T, NOPS>(g, eq, scs, p, c.n2, grow, col, v0, ad);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if ((in >> e) & 1u) {
+              const T res = av[e] - ad[e];
+              o[e] = v0[e] + dt * res;
+            }
+        }
+      };
+      auto emit = [&](int row, int col, const T (&o)[VEC]) {
+        sts_vec<T>(nxt + row * rowlen + col, o);
+        if (send && (row == 0 || row == c.rows - 1)) res_send<T>(c, ll, row, col, (unsigned)(s + 1), seq_out, o);
+        if (all_rows) sts_vec<T>(gout + (c.row0 + row) * rowlen + col, o);
+      };
+      // two items per trip: both are computed before either is stored
+      for (ResIt a = res_it_first(c); a.j < c.rows;) {
+        const ResIt b = res_it_next(c, a);
+        int ra, ca, rb = 0, cb = 0;
+        T oa[VEC], ob[VEC];
+        compute(a, ra, ca, oa);
+        const bool two = b.j < c.rows;
+        if (two) compute(b, rb, cb, ob);
+        emit(ra, ca, oa);
+        if (two) emit(rb, cb, ob);
+        a = res_it_next(c, b);
+      }
+    }
+    stamp(s, 1);
+    __syncthreads();  // end of step s: `cur` is free, `nxt` complete (but for its halo rows: next step's fetches)
+    stamp(s, 2);
+    if (dbg != nullptr && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && (s == 8 || s == nsteps - 1))
+      dbg[s == 8 ? 3 : 4] = global_timer_ns();
   }
 }
 
@@ -418,20 +631,30 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0, T* __restrict__ b1,
 // region and 0 elsewhere, d = r (PW_RESID writes both), st = k_state_init + ST_CG_INIT (rr in sum[R_RR]).
 // Sequence numbers: d rows of iteration k carry seq0 + k + 1, the all-reduce of epoch e carries seq0 + e.
 // =========================================================================================
+// All-CTA sum as an LL all-gather into private inboxes: CTA b stores its partial sums into line [parity][dst][b] of
+// EVERY CTA dst and polls only its own inbox, so that a line has exactly one writer and one reader.  (First version:
+// one slot per CTA, read back by all 148 CTAs -- 148 x 148 polling loads on 37 cache lines; measured 3.4-8.2 us per
+// all-reduce at 256^2, now 2.1-2.5.)  Every CTA adds the contributions in the same order: bit-identical sums.
 template <int NS>
-__device__ __forceinline__ void res_allsum(double (&v)[NS], uint4* slots, unsigned epoch, unsigned seq, double* red,
+__device__ __forceinline__ void res_allsum(double (&v)[NS], uint4* inbox, unsigned epoch, unsigned seq, double* red,
                                            double* bc) {
   block_sum<NS>(v, red);
   if (threadIdx.x == 0) {
-    uint4* mine = slots + ((long long)(epoch & 1u) * kResMaxCtas + blockIdx.x) * kResSlotLines;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) ll_store(mine + s, v[s], seq);
+    for (int s = 0; s < NS; ++s) bc[s] = v[s];
   }
+  __syncthreads();
   double acc[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) acc[s] = 0.0;
-  if (threadIdx.x < gridDim.x)
-    ll_load<double, NS>(slots + ((long long)(epoch & 1u) * kResMaxCtas + threadIdx.x) * kResSlotLines, seq, acc);
+  if (threadIdx.x < gridDim.x) {
+    uint4* par = inbox + (long long)(epoch & 1u) * kResMaxCtas * kResMaxCtas * kResSlotLines;
+    uint4* dst = par + ((long long)threadIdx.x * kResMaxCtas + blockIdx.x) * kResSlotLines;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) ll_store(dst + s, bc[s], seq);
+    ll_load<double, NS>(par + ((long long)blockIdx.x * kResMaxCtas + threadIdx.x) * kResSlotLines, seq, acc);
+  }
+  __syncthreads();  // bc has been read by every sender
   block_sum<NS>(acc, red);
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -440,14 +663,19 @@ __device__ __forceinline__ void res_allsum(double (&v)[NS], uint4* slots, unsign
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < NS; ++s) v[s] = bc[s];
+  __syncthreads();  // bc is free for the next reduction
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kResThreads, 1)
-k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, const T* __restrict__ r_in,
-              const T* __restrict__ d_in, SolverState* st, int R, typename LLOf<T>::line* llbase, uint4* slots,
-              unsigned seq0) {
+k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
+              T* __restrict__ xb, const T* __restrict__ r_in, const T* __restrict__ d_in, SolverState* st, int R,
+              typename LLOf<T>::line* llbase, uint4* inbox, unsigned seq0, int uni, unsigned long long* dbg,
+              int dbg_flags) {
   constexpr int VEC = VecOf<T>::N;
+  auto stamp = [&](unsigned i, int k) {
+    if (dbg != nullptr && i == 8u && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) dbg[k] = global_timer_ns();
+  };
   extern __shared__ unsigned char smem_dyn[];
   __shared__ SolverState ls;  // this CTA's copy of the solver state (bit-identical in every CTA)
   __shared__ double red[2 * 32];
@@ -456,16 +684,22 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, co
   ResCtx c;
   res_ctx_init<T>(c, g, R);
   const ResLL<T> ll{llbase, c.n2, (int)gridDim.x};
-  const long long rowlen = c.n2;
-  T* sd = reinterpret_cast<T*>(base);
-  T* sr = sd + (long long)R * rowlen;
-  T* sx = sr + (long long)R * rowlen;
+  const int rowlen = c.n2;
+  T* sd = reinterpret_cast<T*>(base) + rowlen;  // d: rows -1 .. R (halo rows at -1 and c.rows)
+  T* sr = sd + (R + 1) * rowlen;     // r: rows 0 .. R-1
+  T* sx = sr + R * rowlen;           // x: rows 0 .. R-1
 
   if (threadIdx.x == 0) ls = *st;
-  for (int i = threadIdx.x; i < c.rows * c.nv; i += kResThreads) {
-    const int lr = i / c.nv, cv = i - lr * c.nv;
-    const long long go = (long long)(c.row0 + lr) * rowlen + cv * VEC, so = (long long)lr * rowlen + cv * VEC;
+  for (int i = threadIdx.x; i < (c.rows + 2) * c.nv; i += kResThreads) {
+    const int lr = i / c.nv - 1, cv = i - (lr + 1) * c.nv;
+    const long long go = (c.row0 + lr) * rowlen + cv * VEC, so = lr * rowlen + cv * VEC;
     T v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = (T)0;
+    if (lr < 0 || lr >= c.rows) {
+      sts_vec<T>(sd + so, v);
+      continue;
+    }
     ldcg_vec<T>(d_in + go, v);
     sts_vec<T>(sd + so, v);
     ldcg_vec<T>(r_in + go, v);
@@ -475,22 +709,24 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, co
   }
   __syncthreads();
 
-  OpScale<T> sc[1];
-  sc[0] = op_scale<T>(eq.op[0]);
-  const ResMarch march = res_march(c);
+  const ResScales<T, 1> scs(eq);
+  const ResFast fast = res_fast_init<T>(c, g, uni != 0);
   unsigned epoch = 1u;
   unsigned it = 0;
   while (!ls.done) {
     const unsigned seq_d = seq0 + it + 1u;
+    if (dbg != nullptr && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && (it == 8u || it == 908u))
+      dbg[it == 8u ? 10 : 11] = global_timer_ns();
     // ---- phase A: d = r + beta d on the region (linalg.py:141), boundary rows first ---------------------
     const T beta = (T)ls.scal[S_BETA];
-    auto dupd = [&](int lr, int col, bool boundary) {
-      const int grow = c.row0 + lr;
-      T* dp = sd + (long long)lr * rowlen + col;
+    stamp(it, 0);
+    auto dupd = [&](int row, int col) {
+      const int grow = c.row0 + row;
+      T* dp = sd + row * rowlen + col;
       T dv[VEC], rv[VEC];
       lds_vec<T>(dp, dv);
       if (grow >= g.lo[0] && grow < g.hi[0]) {
-        lds_vec<T>(sr + (long long)lr * rowlen + col, rv);
+        lds_vec<T>(sr + row * rowlen + col, rv);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const int z = col + e;
@@ -498,66 +734,144 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, co
         }
         sts_vec<T>(dp, dv);
       }
-      if (boundary) res_send<T>(c, ll, lr, col, it, seq_d, dv);
+      if (row == 0 || row == c.rows - 1) res_send<T>(c, ll, row, col, it, seq_d, dv);
     };
+    if (fast.on) {
+      for (int cv = fast.cv; cv < c.nv; cv += fast.cstep) {
+        if (fast.boundary) {
+          dupd(0, cv * VEC);
+          if (c.rows > 1) dupd(c.rows - 1, cv * VEC);
+        }
+        for (int row = fast.ta; row < fast.tb; ++row) dupd(row, cv * VEC);
+      }
+    } else {
+      for (ResIt a = res_it_first(c); a.j < c.rows; a = res_it_next(c, a)) dupd(res_row_at(c, 1, a.j), a.cv * VEC);
+    }
+    __syncthreads();  // every own row of d is updated
+    stamp(it, 1);
+    // A(d) and d.A(d): the interior rows first -- the neighbours' rows, requested here, are still in flight
     double qa[1] = {0.0};
-    auto dad_fin = [&](int lr, int col, const T* dp, const T (&dv)[VEC], const T (&vm)[VEC], const T (&vp)[VEC]) {
-      const int grow = c.row0 + lr;
-      if (grow < g.lo[0] || grow >= g.hi[0]) return;
-      res_apply_vec<T, 1>(g, eq, sc, dp, c.n2, grow, col, dv, vm, vp, [&](int e, bool in, T a) {
-        if (in) {
-          const T q = dv[e] * a;
+    // A(d) on one item (0 outside the region)
+    auto apply_d = [&](int row, int col, T (&dv)[VEC], T (&ad)[VEC]) -> unsigned {
+      const int grow = c.row0 + row;
+      const T* dp = sd + row * rowlen + col;
+      lds_vec<T>(dp, dv);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) ad[e] = (T)0;
+      if (grow < g.lo[0] || grow >= g.hi[0]) return 0u;
+      return res_apply_vec<T, 1>(g, eq, scs, dp, c.n2, grow, col, dv, ad);
+    };
+    // uniform coefficients: the class-0 stencil on a vector, 0 where the cell is outside the region
+    auto fast_cell = [&](const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC], T zl, T zr, int row, int col,
+                         T (&ad)[VEC]) {
+      const int grow = c.row0 + row;
+      const bool rin = grow >= g.lo[0] && grow < g.hi[0];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
+        const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
+        const T a = res_star<T, true, 1>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+        const int z = col + e;
+        ad[e] = (rin && z >= g.lo[2] && z < g.hi[2]) ? a : (T)0;
+      }
+    };
+    // (d == 0 wherever ad was forced to 0 -- outside the region -- so the product adds an exact zero there)
+    auto dad_put = [&](int row, int col, const T (&ad)[VEC]) {
+      T dv[VEC];
+      lds_vec<T>(sd + row * rowlen + col, dv);
+      const int grow = c.row0 + row;
+      const bool rin = grow >= g.lo[0] && grow < g.hi[0];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int z = col + e;
+        if (rin && z >= g.lo[2] && z < g.hi[2]) {
+          const T q = dv[e] * ad[e];
           qa[0] += (double)q;
         }
-      });
+      }
     };
-    // general walk: the rows above / below from shared memory or, across the CTA's edge, from the neighbour's LL row
-    auto with_rows = [&](int lr, int cv, auto fin) {
-      const int col = cv * VEC;
-      const T* dp = sd + (long long)lr * rowlen + col;
-      T dv[VEC], vm[VEC], vp[VEC];
-      lds_vec<T>(dp, dv);
-      res_neighbour_row<T>(c, ll, sd, lr, col, -1, it, seq_d, (const T*)nullptr, vm);
-      res_neighbour_row<T>(c, ll, sd, lr, col, +1, it, seq_d, (const T*)nullptr, vp);
-      fin(lr, col, dp, dv, vm, vp);
-    };
-    res_boundary_rows(c, [&](int lr, int cv) { dupd(lr, cv * VEC, true); });
-    if (march.use)
-      res_march_plain<T>(c, march, [&](int lr, int col) { dupd(lr, col, false); });
-    else
-      res_rows(c, 1, c.rows - 1, [&](int lr, int cv) { dupd(lr, cv * VEC, false); });
-    __syncthreads();  // every own row of d is updated
-    // the interior rows first: the neighbours' rows are still in flight
-    if (march.use)
-      res_march_rows<T>(c, march, sd, dad_fin);
-    else
-      res_rows(c, 1, c.rows - 1, [&](int lr, int cv) { with_rows(lr, cv, dad_fin); });
-    res_boundary_rows(c, [&](int lr, int cv) { with_rows(lr, cv, dad_fin); });
-    res_allsum<1>(qa, slots, epoch, seq0 + epoch, red, bc);
+    if (fast.on) {
+      unsigned got = 0u;
+      if (fast.boundary) {
+        int k = 0;
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+          if (blockIdx.x > 0 && res_halo_get<T>(c, ll, sd, cv * VEC, 0, it, seq_d, (const T*)nullptr, false))
+            got |= 1u << (2 * k);
+          if (blockIdx.x + 1 < gridDim.x && res_halo_get<T>(c, ll, sd, cv * VEC, 1, it, seq_d, (const T*)nullptr, false))
+            got |= 2u << (2 * k);
+        }
+      }
+      res_fast_march<T>(c, fast, sd, fast.ta, fast.tb, fast_cell, dad_put);
+      if (fast.boundary) {
+        int k = 0;
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+          const int col = cv * VEC;
+          if (blockIdx.x > 0 && !((got >> (2 * k)) & 1u))
+            res_halo_get<T>(c, ll, sd, col, 0, it, seq_d, (const T*)nullptr, true);
+          if (blockIdx.x + 1 < gridDim.x && !((got >> (2 * k + 1)) & 1u))
+            res_halo_get<T>(c, ll, sd, col, 1, it, seq_d, (const T*)nullptr, true);
+          res_fast_boundary<T>(c, sd, col, fast_cell, dad_put);
+        }
+      }
+    } else {
+      const int rs_last = c.rows < 2 ? 1 : c.rows - 1;
+      const unsigned got = res_halo_prefetch<T>(c, ll, sd, rs_last, it, seq_d, (const T*)nullptr);
+      int bit = 0;
+      for (ResIt a = res_it_first(c); a.j < c.rows;) {
+        const ResIt b = res_it_next(c, a);
+        const bool two = b.j < c.rows;
+        const int ra = res_row_at(c, rs_last, a.j), ca = a.cv * VEC;
+        const int rb = two ? res_row_at(c, rs_last, b.j) : 0, cb = b.cv * VEC;
+        res_halo_need<T>(c, ll, sd, ra, ca, it, seq_d, (const T*)nullptr, got, bit);
+        if (two) res_halo_need<T>(c, ll, sd, rb, cb, it, seq_d, (const T*)nullptr, got, bit);
+        T da[VEC], db[VEC], aa[VEC], ab[VEC];
+        const unsigned ma = apply_d(ra, ca, da, aa);
+        const unsigned mb = two ? apply_d(rb, cb, db, ab) : 0u;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if ((ma >> e) & 1u) {
+            const T q = da[e] * aa[e];
+            qa[0] += (double)q;
+          }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if ((mb >> e) & 1u) {
+            const T q = db[e] * ab[e];
+            qa[0] += (double)q;
+          }
+        a = res_it_next(c, b);
+      }
+    }
+    stamp(it, 2);
+    res_allsum<1>(qa, inbox, epoch, seq0 + epoch, red, bc);
+    stamp(it, 3);
     ++epoch;
     if (threadIdx.x == 0) {
       ls.sum[R_A] = qa[0];
       finalize_stage<T>(ST_CG_DAD, &ls);  // alpha = rr / dAd (linalg.py:114-120)
     }
     __syncthreads();
+    stamp(it, 4);
     // ---- phase B: x_new = x + alpha d ; r -= alpha A(d) ; sums |r|^2, |dx|^2 (linalg.py:122-137) ------
+    // (A(d) is recomputed -- the halo rows of d are still in place -- instead of kept in 14 registers per thread)
     const T alpha = (T)ls.scal[S_ALPHA];
     T* gxn = ((it + 1u) & 1u) ? xb : xa;
     double qb[2] = {0.0, 0.0};
-    auto upd_fin = [&](int lr, int col, const T* dp, const T (&dv)[VEC], const T (&vm)[VEC], const T (&vp)[VEC]) {
-      const int grow = c.row0 + lr;
-      if (grow < g.lo[0] || grow >= g.hi[0]) return;
-      T* rp = sr + (long long)lr * rowlen + col;
-      T* xp = sx + (long long)lr * rowlen + col;
+    auto update = [&](int row, int col, unsigned m, const T (&dv)[VEC], const T (&ad)[VEC]) {
+      if (m == 0u) return;
+      const int grow = c.row0 + row;
+      T* rp = sr + row * rowlen + col;
+      T* xp = sx + row * rowlen + col;
       T rv[VEC], xv[VEC];
       lds_vec<T>(rp, rv);
       lds_vec<T>(xp, xv);
       const bool rshell = grow == 0 || grow == g.n[0] - 1;
-      res_apply_vec<T, 1>(g, eq, sc, dp, c.n2, grow, col, dv, vm, vp, [&](int e, bool in, T a) {
-        if (in) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        if ((m >> e) & 1u) {
           const T xo = xv[e];
           const T xn = xo + alpha * dv[e];
-          const T rn = rv[e] - alpha * a;
+          const T rn = rv[e] - alpha * ad[e];
           xv[e] = xn;
           rv[e] = rn;
           const T q = rn * rn;
@@ -569,17 +883,42 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, co
             qb[1] += (double)q2;
           }
         }
-      });
       sts_vec<T>(rp, rv);
       sts_vec<T>(xp, xv);
-      sts_vec<T>(gxn + (long long)grow * rowlen + col, xv);
+      if (!(dbg_flags & 1)) sts_vec<T>(gxn + grow * rowlen + col, xv);  // (PA_RES_DEBUG_FLAGS=1: timing experiment)
     };
-    res_boundary_rows(c, [&](int lr, int cv) { with_rows(lr, cv, upd_fin); });
-    if (march.use)
-      res_march_rows<T>(c, march, sd, upd_fin);
-    else
-      res_rows(c, 1, c.rows - 1, [&](int lr, int cv) { with_rows(lr, cv, upd_fin); });
-    res_allsum<2>(qb, slots, epoch, seq0 + epoch, red, bc);
+    if (fast.on) {
+      auto upd_put = [&](int row, int col, const T (&ad)[VEC]) {
+        T dv[VEC];
+        lds_vec<T>(sd + row * rowlen + col, dv);
+        const int grow = c.row0 + row;
+        unsigned m = 0u;
+        if (grow >= g.lo[0] && grow < g.hi[0]) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (col + e >= g.lo[2] && col + e < g.hi[2]) m |= 1u << e;
+        }
+        update(row, col, m, dv, ad);
+      };
+      if (fast.boundary)
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep) res_fast_boundary<T>(c, sd, cv * VEC, fast_cell, upd_put);
+      res_fast_march<T>(c, fast, sd, fast.ta, fast.tb, fast_cell, upd_put);
+    } else {
+      for (ResIt a = res_it_first(c); a.j < c.rows;) {
+        const ResIt b = res_it_next(c, a);
+        const bool two = b.j < c.rows;
+        const int ra = a.j, ca = a.cv * VEC, rb = two ? b.j : 0, cb = b.cv * VEC;
+        T da[VEC], db[VEC], aa[VEC], ab[VEC];
+        const unsigned ma = apply_d(ra, ca, da, aa);
+        const unsigned mb = two ? apply_d(rb, cb, db, ab) : 0u;
+        update(ra, ca, ma, da, aa);
+        update(rb, cb, mb, db, ab);
+        a = res_it_next(c, b);
+      }
+    }
+    stamp(it, 5);
+    res_allsum<2>(qb, inbox, epoch, seq0 + epoch, red, bc);
+    stamp(it, 6);
     ++epoch;
     if (threadIdx.x == 0) {
       ls.sum[R_A] = qb[0];
@@ -588,6 +927,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, co
       finalize_stage<T>(ST_CG_FIN, &ls);
     }
     __syncthreads();
+    stamp(it, 7);
     ++it;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = ls;
@@ -599,38 +939,42 @@ struct ResPlan {
   size_t smem;
 };
 
-// Exchange buffers (all-reduce slots + LL rows): a small per-device pool handed out round-robin (two resident
-// launches only run at the same time if they come from different streams and both fit the SMs).  Nothing is zeroed
-// per launch: every launch takes a fresh range of sequence numbers, so lines of earlier launches never match.
+// Exchange buffer (all-reduce inboxes + LL rows): ONE per device, grow-only.  Nothing is zeroed per launch: every
+// launch takes a fresh range of sequence numbers, so lines of earlier launches never match.  Resident launches of one
+// process on one device are serialised through an event (two of them would share the lines).
 struct ResBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
   unsigned next_seq = 1u;
+  cudaEvent_t last = nullptr;
 };
-constexpr size_t kResSlotBytes = 16384;  // [2][kResMaxCtas][kResSlotLines] uint4, rounded up
+constexpr size_t kResSlotBytes = (size_t)2 * kResMaxCtas * kResMaxCtas * kResSlotLines * 16;  // the inboxes, 1.4 MB
 
-inline ResBuf* res_exchange_buffer(size_t ll_bytes) {
-  constexpr int kPool = 4;
-  static ResBuf pool[kMaxDevices][kPool];
-  static unsigned rr[kMaxDevices] = {};
-  const int dev = current_device();
-  ResBuf& b = pool[dev][__atomic_fetch_add(&rr[dev], 1u, __ATOMIC_RELAXED) % kPool];
+inline ResBuf* res_exchange_buffer(size_t ll_bytes, cudaStream_t s) {
+  static ResBuf pool[kMaxDevices];
+  ResBuf& b = pool[current_device()];
   const size_t need = kResSlotBytes + ll_bytes;
   if (b.bytes < need) {
+    const size_t want = need > 2 * b.bytes ? need : 2 * b.bytes;
     if (b.ptr) cudaFree(b.ptr);  // (synchronises the device: no launch still uses it)
     b.ptr = nullptr;
     b.bytes = 0;
     // cudaMemset of device memory is asynchronous: without the synchronisation a launch on a non-blocking stream
     // can start first, and the late memset then erases lines the kernel is waiting for (observed: a hang)
-    if (cudaMalloc(&b.ptr, need) != cudaSuccess || cudaMemset(b.ptr, 0, need) != cudaSuccess ||
+    if (cudaMalloc(&b.ptr, want) != cudaSuccess || cudaMemset(b.ptr, 0, want) != cudaSuccess ||
         cudaDeviceSynchronize() != cudaSuccess) {
       cudaGetLastError();
       if (b.ptr) cudaFree(b.ptr);
       b.ptr = nullptr;
       return nullptr;
     }
-    b.bytes = need;  // (next_seq keeps counting: recycled memory may hold this pool entry's old lines)
+    b.bytes = want;  // (next_seq keeps counting: recycled memory may hold old lines)
   }
+  if (b.last == nullptr && cudaEventCreateWithFlags(&b.last, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (cudaStreamWaitEvent(s, b.last, 0) != cudaSuccess) cudaGetLastError();  // (never recorded yet: a no-op)
   return &b;
 }
 // the first of `count` fresh sequence numbers is seq0 + 1; on wrap-around the buffer is cleared on the stream
@@ -646,12 +990,32 @@ inline bool res_take_seq(ResBuf& b, unsigned count, cudaStream_t s, unsigned* se
   return true;
 }
 
-// resident rows per CTA: Euler 2R (two buffers), CG 3R (d, r, x)
+// PA_RES_DEBUG=1: device buffer for the kernels' phase time stamps, printed by the launcher after a synchronisation
+inline unsigned long long* res_debug_buffer() {
+  static unsigned long long* buf = nullptr;
+  if (getenv("PA_RES_DEBUG") == nullptr) return nullptr;
+  if (!buf && cudaMalloc(&buf, 16 * sizeof(unsigned long long)) != cudaSuccess) buf = nullptr;
+  if (buf) cudaMemset(buf, 0, 16 * sizeof(unsigned long long));
+  return buf;
+}
+inline void res_debug_print(const char* what, unsigned long long* dbg, int n, cudaStream_t s) {
+  if (!dbg) return;
+  unsigned long long h[16];
+  cudaStreamSynchronize(s);
+  cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[PA_RES_DEBUG] %s: phase stamps (ns since the first):", what);
+  for (int k = 1; k < n; ++k) fprintf(stderr, " %lld", (long long)(h[k] - h[0]));
+  if (h[11] > h[10]) fprintf(stderr, "  | 900 iterations: %.3f us each", (double)(h[11] - h[10]) / 900e3);
+  fprintf(stderr, "\n");
+}
+
+// resident rows per CTA: Euler 2 (R + 2) (two buffers with halo rows), CG 3R + 2 (d with halo rows, r, x)
 template <typename T>
 inline bool res_plan(const GridDev& g, bool cg, ResPlan& p) {
   constexpr int VEC = VecOf<T>::N;
   if (!g.act[0] || g.act[1] || !g.act[2]) return false;  // 2-D meshes: kernel axes (0, 2)
   if (g.n[2] % VEC != 0 || g.n[2] < 2 * VEC || g.n[0] < 3) return false;
+  if (g.n[2] / VEC > 6 * kResThreads) return false;  // <= 16 halo vectors per thread (res_halo_prefetch's bit mask)
   int dev = 0, coop = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -661,7 +1025,7 @@ inline bool res_plan(const GridDev& g, bool cg, ResPlan& p) {
   const int want = g.n[0] < sms ? g.n[0] : sms;
   p.R = (g.n[0] + want - 1) / want;
   p.ctas = (g.n[0] + p.R - 1) / p.R;
-  const long long rows = cg ? 3LL * p.R : 2LL * p.R;
+  const long long rows = cg ? 3LL * p.R + 2 : 2LL * (p.R + 2);
   const long long bytes = rows * g.n[2] * (long long)sizeof(T) + 128;
   if (bytes > kResSmemMax - 4096) return false;  // (static shared memory of the kernels: < 2 KB)
   p.smem = (size_t)bytes;
@@ -685,28 +1049,42 @@ inline bool res_eq_ok(const pa_equation& eq) {
   return true;
 }
 
+// the three coefficient classes of every operator hold the same numbers on both axes of the 2-D grid (no Neumann /
+// Symmetry face; compared bit for bit, like TmaPlan::coef_uniform)
+inline bool res_coef_uniform(const pa_equation& eq) {
+  for (int k = 0; k < eq.nops; ++k)
+    for (int a = 0; a < 3; a += 2)
+      for (int cls = 1; cls < 3; ++cls)
+        for (int q = 0; q < 3; ++q)
+          if (std::memcmp(&eq.ops[k].coef[a][cls][q], &eq.ops[k].coef[a][0][q], sizeof(double)) != 0) return false;
+  return true;
+}
+
 template <typename T, int NOPS, bool HAS_RHS>
 static bool launch_euler_resident_n(cudaStream_t s, const ResPlan& p, const GridDev& g, const EqDev<T>& eq, T* b0,
-                                    T* b1, const T* rhs, T dt, int nsteps) {
+                                    T* b1, const T* rhs, T dt, int nsteps, int uni) {
   if (cudaFuncSetAttribute(k_euler_resident<T, NOPS, HAS_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)p.smem) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p));
+  ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
   unsigned seq0 = 0;
   if (!buf || !res_take_seq(*buf, (unsigned)nsteps + 1u, s, &seq0)) return false;
   typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
   int R = p.R;
   GridDev gg = g;
   EqDev<T> e = eq;
+  unsigned long long* dbg = res_debug_buffer();
   void* args[] = {(void*)&gg, (void*)&e, (void*)&b0, (void*)&b1, (void*)&rhs, (void*)&dt, (void*)&nsteps, (void*)&R,
-                  (void*)&ll, (void*)&seq0};
+                  (void*)&ll, (void*)&seq0, (void*)&uni, (void*)&dbg};
   if (cudaLaunchCooperativeKernel((void*)k_euler_resident<T, NOPS, HAS_RHS>, dim3(p.ctas), dim3(kResThreads), args,
                                   p.smem, s) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  cudaEventRecord(buf->last, s);
+  res_debug_print("euler step 8: items | barrier | (3) | end of the last step", dbg, 5, s);
   return true;
 }
 
@@ -716,42 +1094,52 @@ bool launch_euler_resident(cudaStream_t s, const GridDev& g, const pa_equation& 
                            const T* rhs, T dt, int nsteps) {
   ResPlan p;
   if (!res_eq_ok<T>(peq) || !res_plan<T>(g, false, p)) return false;
+  const char* ev = getenv("PA_RES_PATH");  // "items": keep the general item loop (A/B runs, tests)
+  const int uni = (res_coef_uniform(peq) && !(ev != nullptr && strcmp(ev, "items") == 0)) ? 1 : 0;
   if (rhs) {
-    if (eq.nops == 1) return launch_euler_resident_n<T, 1, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
-    if (eq.nops == 2) return launch_euler_resident_n<T, 2, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
-    return launch_euler_resident_n<T, 0, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
+    if (eq.nops == 1) return launch_euler_resident_n<T, 1, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
+    if (eq.nops == 2) return launch_euler_resident_n<T, 2, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
+    return launch_euler_resident_n<T, 0, true>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
   }
-  if (eq.nops == 1) return launch_euler_resident_n<T, 1, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
-  if (eq.nops == 2) return launch_euler_resident_n<T, 2, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
-  return launch_euler_resident_n<T, 0, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps);
+  if (eq.nops == 1) return launch_euler_resident_n<T, 1, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
+  if (eq.nops == 2) return launch_euler_resident_n<T, 2, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
+  return launch_euler_resident_n<T, 0, false>(s, p, g, eq, b0, b1, rhs, dt, nsteps, uni);
 }
 
 // the whole CG solve in one launch (eq: ONE star operator, has_shift for the implicit-Euler term); at most
 // max_it + 1 iterations run (finalize_stage ST_CG_FIN)
 template <typename T>
 bool launch_cg_resident(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, T* xa, T* xb, const T* r, const T* d,
-                        SolverState* st, int max_it) {
+                        SolverState* st, int max_it, int uni) {
   ResPlan p;
   if (eq.nops != 1 || max_it < 0 || max_it > 1000000000 || !res_plan<T>(g, true, p)) return false;
   if (cudaFuncSetAttribute(k_cg_resident<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p));
+  ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
   unsigned seq0 = 0;
   if (!buf || !res_take_seq(*buf, 2u * ((unsigned)max_it + 3u) + 2u, s, &seq0)) return false;
-  uint4* slots = (uint4*)buf->ptr;
+  uint4* inbox = (uint4*)buf->ptr;
   typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
   int R = p.R;
   GridDev gg = g;
   EqDev<T> e = eq;
+  unsigned long long* dbg = res_debug_buffer();
+  const char* ev = getenv("PA_RES_PATH");  // "items": keep the general item loop (A/B runs, tests)
+  if (ev != nullptr && strcmp(ev, "items") == 0) uni = 0;
+  const char* df = getenv("PA_RES_DEBUG_FLAGS");
+  int dbg_flags = df ? atoi(df) : 0;
   void* args[] = {(void*)&gg, (void*)&e, (void*)&xa, (void*)&xb, (void*)&r, (void*)&d, (void*)&st, (void*)&R,
-                  (void*)&ll, (void*)&slots, (void*)&seq0};
+                  (void*)&ll, (void*)&inbox, (void*)&seq0, (void*)&uni, (void*)&dbg, (void*)&dbg_flags};
   if (cudaLaunchCooperativeKernel((void*)k_cg_resident<T>, dim3(p.ctas), dim3(kResThreads), args, p.smem, s) !=
       cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  cudaEventRecord(buf->last, s);
+  res_debug_print("cg iteration 8: d update+barrier | d.A(d) | all-reduce | alpha | x,r update | all-reduce | beta", dbg,
+                  8, s);
   return true;
 }
 

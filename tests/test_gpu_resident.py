@@ -18,21 +18,27 @@ DEV = "cuda"
 
 
 class _euler_variant:
+    """"resident" (default: uniform-coefficient fast path where it applies), "items" (resident, general item loop),
+    "stream" (per-step launches of the star engine)."""
+
     def __init__(self, v):
         self.v = v
 
     def __enter__(self):
-        self.prev = os.environ.get("PA_EULER_VARIANT")
+        self.prev = {k: os.environ.get(k) for k in ("PA_EULER_VARIANT", "PA_RES_PATH")}
+        os.environ.pop("PA_EULER_VARIANT", None)
+        os.environ.pop("PA_RES_PATH", None)
         if self.v == "stream":
             os.environ["PA_EULER_VARIANT"] = "stream"
-        else:
-            os.environ.pop("PA_EULER_VARIANT", None)
+        elif self.v == "items":
+            os.environ["PA_RES_PATH"] = "items"
 
     def __exit__(self, *a):
-        if self.prev is None:
-            os.environ.pop("PA_EULER_VARIANT", None)
-        else:
-            os.environ["PA_EULER_VARIANT"] = self.prev
+        for k, v in self.prev.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def _euler_run(shape, limiter, n_steps, dtype="double", with_rhs=False, seed=1234):
@@ -66,8 +72,10 @@ def _euler_run(shape, limiter, n_steps, dtype="double", with_rhs=False, seed=123
 @pytest.mark.parametrize("shape,n_steps", [([40, 64], 7), ([7, 16], 4), ([150, 128], 5), ([149, 32], 2),
                                            ([300, 96], 6), ([3, 8], 3), ([449, 1032], 3)])
 @pytest.mark.parametrize("with_rhs", [False, True])
-def test_euler_resident_vs_oracle(limiter, shape, n_steps, with_rhs):
-    mesh, var, phi0, src, dt, vals = _euler_run(shape, limiter, n_steps, with_rhs=with_rhs)
+@pytest.mark.parametrize("path", ["resident", "items"])
+def test_euler_resident_vs_oracle(limiter, shape, n_steps, with_rhs, path):
+    with _euler_variant(path):
+        mesh, var, phi0, src, dt, vals = _euler_run(shape, limiter, n_steps, with_rhs=with_rhs)
     nd = len(shape)
     xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
     bcs = [O.FaceBC(f, "dirichlet", v) for f, v in zip(O.FACES[: 2 * nd], vals)]
@@ -83,17 +91,19 @@ def test_euler_resident_vs_oracle(limiter, shape, n_steps, with_rhs):
 
 
 @pytest.mark.parametrize("dtype", ["double", "single"])
-@pytest.mark.parametrize("shape,n_steps", [([1024, 1024], 41), ([512, 2048], 12), ([1000, 520], 9)])
+@pytest.mark.parametrize("shape,n_steps", [([1024, 1024], 41), ([512, 2048], 12), ([1000, 520], 9), ([512, 512], 30),
+                                           ([256, 256], 30), ([300, 128], 11)])
 def test_euler_resident_equals_stream(dtype, shape, n_steps):
     """BASELINE config 3 size: the resident launch and the per-step star-engine launches agree bit for bit."""
     out = {}
-    for v in ("resident", "stream"):
+    for v in ("resident", "items", "stream"):
         with _euler_variant(v):
             _, var, *_ = _euler_run(shape, "upwind", n_steps, dtype=dtype)
         out[v] = (var().clone(), var.VARo.clone())
     assert torch.isfinite(out["stream"][0]).all()
-    assert torch.equal(out["resident"][0], out["stream"][0])
-    assert torch.equal(out["resident"][1], out["stream"][1])
+    for v in ("resident", "items"):
+        assert torch.equal(out[v][0], out["stream"][0]), v
+        assert torch.equal(out[v][1], out["stream"][1]), v
 
 
 def _cg_run(shape, variant, max_it, tol=1e-30, dtype="double", seed=1234, vals=None):
@@ -121,8 +131,10 @@ def _cg_run(shape, variant, max_it, tol=1e-30, dtype="double", seed=1234, vals=N
 
 @pytest.mark.parametrize("shape,max_it", [([64, 64], 30), ([150, 128], 25), ([149, 32], 25), ([7, 16], 10),
                                           ([300, 96], 40), ([1024, 1024], 60), ([449, 1032], 15)])
-def test_cg_resident_equals_fused(shape, max_it):
-    a, rep_a, _ = _cg_run(shape, 6, max_it)
+@pytest.mark.parametrize("path", ["resident", "items"])
+def test_cg_resident_equals_fused(shape, max_it, path):
+    with _euler_variant(path):
+        a, rep_a, _ = _cg_run(shape, 6, max_it)
     b, rep_b, _ = _cg_run(shape, 4, max_it)
     assert rep_a["itr"] == rep_b["itr"] == max_it + 1, (rep_a, rep_b)
     assert abs(rep_a["tol"] - rep_b["tol"]) <= 1e-10 * max(1.0, abs(rep_b["tol"])), (rep_a, rep_b)
@@ -132,9 +144,11 @@ def test_cg_resident_equals_fused(shape, max_it):
     assert a._last_launches < b._last_launches  # one launch instead of two per iteration
 
 
-@pytest.mark.parametrize("shape", [[40, 64], [96, 48]])
-def test_cg_resident_converged_vs_oracle(shape):
-    var, rep, vals = _cg_run(shape, 6, 2000, tol=1e-8)
+@pytest.mark.parametrize("shape", [[40, 64], [96, 48], [130, 256]])
+@pytest.mark.parametrize("path", ["resident", "items"])
+def test_cg_resident_converged_vs_oracle(shape, path):
+    with _euler_variant(path):
+        var, rep, vals = _cg_run(shape, 6, 2000, tol=1e-8)
     nd = len(shape)
     xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
     bcs = [O.FaceBC(f, "dirichlet", v) for f, v in zip(O.FACES[: 2 * nd], vals)]
