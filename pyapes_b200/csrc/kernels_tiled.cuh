@@ -70,6 +70,9 @@ struct TilePlan {
   int nz = 0;
   int work_slot = 0;  // entry of the launch in the work-counter pool (kernels_tma.cuh)
   int first_static = 0;  // 1: a CTA's first item is its block index, the counter serves the rest
+  // star engine: the three coefficient classes of every operator hold the same numbers on every active axis (no
+  // Neumann / Symmetry face), so the general path takes class 0 like the LEAN one (kernels_tma_pw.cuh, UNI)
+  int uni = 0;
 };
 
 __device__ __forceinline__ int tile_chunk(const TilePlan& p, int z) {

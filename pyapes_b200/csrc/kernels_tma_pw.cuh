@@ -6,6 +6,8 @@
 //   * one optional auxiliary own-tile input (rhs or r0) rides in the same pipeline stage.
 // Algorithmic traffic: R in (+halo), [R aux], W out  = 2-3 words per cell.
 #pragma once
+#include <type_traits>
+
 #include "kernels_tma.cuh"
 
 namespace pa {
@@ -120,7 +122,8 @@ __device__ __forceinline__ T star_diag(const EqDev<T>& eq, int clx, int cy, int 
 
 // sum over operators of sign*param*(star), reference order (ops.py:130-149, fdc.py:103-108).
 // Kernel axis 0 is always active here (pw_eligible: 3-D meshes, and 2-D meshes as FLAT tiles).
-template <typename T, typename K, bool LEAN, int NOPS, typename F>
+// UNI: the coefficient classes are bitwise equal (TilePlan::uni): class 0 everywhere, same bits, no per-cell selects.
+template <typename T, typename K, bool LEAN, int NOPS, bool UNI, typename F>
 __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<T, K>& c, int clx,
                                               const T (&vm)[K::RY][VecOf<T>::N],
                                               const T (&vc)[K::RY][VecOf<T>::N],
@@ -136,10 +139,10 @@ __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<
     if (q < nops) sc[q] = op_scale<T>(eq.op[q]);
 #pragma unroll
   for (int k = 0; k < K::RY; ++k) {
-    const int cy = LEAN ? 0 : c.cly[k];
+    const int cy = (LEAN || UNI) ? 0 : c.cly[k];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const int cz = LEAN ? 0 : c.clz[e];
+      const int cz = (LEAN || UNI) ? 0 : c.clz[e];
       const T v0 = vc[k][e];
       const T yp = (k == K::RY - 1) ? dn[e] : vc[k + 1 < K::RY ? k + 1 : k][e];
       const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
@@ -177,7 +180,10 @@ __device__ __forceinline__ void star_cells_eq(const EqDev<T>& eq, const ConsCtx<
   }
 }
 
-template <typename T, typename K, int MODE, bool LEAN, int NOPS>
+// UNI (general path only; the kernel dispatches on the CTA-uniform TilePlan::uni): coefficient class 0 on every axis
+// and the LEAN Jacobi quotient -- the edge tiles (56 % of the tiles of a 256^2 plane) then differ from the LEAN ones
+// only by their region / validity masks.
+template <typename T, typename K, int MODE, bool LEAN, int NOPS, bool UNI = false>
 __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g, const EqDev<T>& eq,
                                             T* __restrict__ out, T* __restrict__ out2, T dt, bool has_aux,
                                             unsigned char* stages, uint64_t* full, uint64_t* empty,
@@ -257,17 +263,17 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
             }
         }
       }
-      const int clx = coef_class(g, 0, x);
+      const int clx = UNI ? 0 : coef_class(g, 0, x);
       if (MODE == PW_GRAD) {
         // central gradient, one output array per mesh axis (fdc.py:80-87); op order of k_grad
         const OpDev<T>& o = eq.op[0];
 #pragma unroll
         for (int k = 0; k < K::RY; ++k) {
-          const int cy = LEAN ? 0 : c.cly[k];
+          const int cy = (LEAN || UNI) ? 0 : c.cly[k];
           T g0[VEC], g1[VEC], g2[VEC];
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
-            const int cz = LEAN ? 0 : c.clz[e];
+            const int cz = (LEAN || UNI) ? 0 : c.clz[e];
             const T v0 = vc[k][e];
             const T yp = (k == K::RY - 1) ? dn[e] : vc[k + 1 < K::RY ? k + 1 : k][e];
             const T ym = (k == 0) ? up[e] : vc[k > 0 ? k - 1 : 0][e];
@@ -304,9 +310,9 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
         release(sc);
         return;
       }
-      star_cells_eq<T, K, LEAN, NOPS>(eq, c, clx, vm, vc, vp, up, dn, zl, zr,
-                                      [&](int k, int e, T v) { ax[k][e] = v; });
-      if (MODE == PW_JACOBI && LEAN) {
+      star_cells_eq<T, K, LEAN, NOPS, UNI>(eq, c, clx, vm, vc, vp, up, dn, zl, zr,
+                                           [&](int k, int e, T v) { ax[k][e] = v; });
+      if (MODE == PW_JACOBI && (LEAN || UNI)) {
         dgl = star_diag<T, K, NOPS>(eq, clx, 0, 0);
         rcl = (T)1 / dgl;
         den_ok = exp_window(dgl, -DivWin<T>::DEN, DivWin<T>::DEN);
@@ -336,7 +342,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           T xn = xc;
           if (in) {
             const T res = av[e] - ax[k][e];
-            if (LEAN)
+            if (LEAN || UNI)
               xn = xc + div_rcp<T>(res, dgl, rcl, den_ok);
             else
               xn = xc + res / star_diag<T, K, NOPS>(eq, coef_class(g, 0, x), c.cly[k], c.clz[e]);
@@ -466,6 +472,9 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     if (full_tile && !edge)
       pw_consumer<T, K, MODE, true, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                            x1, acc);
+    else if (p.uni)
+      pw_consumer<T, K, MODE, false, NOPS, true>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0,
+                                                  x0, x1, acc);
     else
       pw_consumer<T, K, MODE, false, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                             x1, acc);
@@ -569,8 +578,8 @@ __device__ __forceinline__ void pw2_consumer(const TilePlan& p, const GridDev& g
         const T* vg = static_cast<const T*>(p.src1);
         wrap_halo<T, K>(g, c, x, up, dn, zl, zr, [&](long long i) { return rg[i] - alpha * vg[i]; });
       }
-      star_cells_eq<T, K, LEAN, NOPS>(eq, c, coef_class(g, 0, x), vm, vc, vp, up, dn, zl, zr,
-                                      [&](int k, int e, T v) { ax[k][e] = v; });
+      star_cells_eq<T, K, LEAN, NOPS, false>(eq, c, coef_class(g, 0, x), vm, vc, vp, up, dn, zl, zr,
+                                             [&](int k, int e, T v) { ax[k][e] = v; });
     }
 #pragma unroll
     for (int k = 0; k < K::RY; ++k) {
@@ -697,6 +706,18 @@ k_bi_st_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CU
 }
 
 // ---- host ------------------------------------------------------------------------------------
+// the three coefficient classes of every operator are bitwise equal on every active axis (TilePlan::uni)
+template <typename T>
+inline bool eq_uniform(const GridDev& g, const EqDev<T>& eq) {
+  for (int k = 0; k < eq.nops; ++k)
+    for (int a = 0; a < 3; ++a) {
+      if (!g.act[a]) continue;
+      for (int cls = 1; cls < 3; ++cls)
+        if (std::memcmp(&eq.op[k].coef[a][cls][0], &eq.op[k].coef[a][0][0], 3 * sizeof(T)) != 0) return false;
+    }
+  return true;
+}
+
 template <typename T>
 inline bool pw_eligible(const GridDev& g, const pa_equation& eq, int nfaces, const pa_face_bc* faces) {
   constexpr int VEC = VecOf<T>::N;
@@ -751,6 +772,7 @@ static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& 
   typedef PwCfg<T, K> C;
   TilePlan tile = tile_in;
   tile.src0 = in;  // wrap-around reads of periodic axes 1/2
+  tile.uni = eq_uniform<T>(g, eq) && getenv("PA_STAR_NO_UNI") == nullptr ? 1 : 0;
   CUtensorMap tm_in, tm_aux;
   if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
   if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::OBOXZ, C::TY)) return false;
@@ -842,6 +864,7 @@ static bool launch_star_grad_k(cudaStream_t s, const GridDev& g, const EqDev<T>&
   typedef PwCfg<T, K> C;
   TilePlan tile = tile_in;
   tile.src0 = in;
+  tile.uni = eq_uniform<T>(g, eq) && getenv("PA_STAR_NO_UNI") == nullptr ? 1 : 0;
   CUtensorMap tm_in;
   if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
   launch_star_tma_n<T, K, PW_GRAD, 1>(s, tm_in, tm_in, g, eq, tile, false, out, nullptr, (T)0, nullptr, nullptr, 0);
