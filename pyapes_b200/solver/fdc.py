@@ -139,8 +139,8 @@ class Discretizer:
                                              parallel.get_comm(phi.device), slab["rank"], slab["world"],
                                              N.current_stream(phi.device)))
         grid = L.lower_grid(var.nx, var.bcs, slab)  # (slab: coefficient classes follow the GLOBAL plane index)
-        if edge and var.mesh.coord_sys == "rz":
-            raise NotImplementedError("pyapes_b200: edge=True on rz meshes is not built")
+        # (edge=True on rz meshes: the one-sided face formulas of Laplacian / Grad carry no 1/r term, fdc.py:223-288 --
+        #  the rz coefficient tables act on the cells next to the faces only; fixtures tests/golden/rz_edge.pt)
         op, keep = L.lower_op(A_coeffs, nd, phi.dtype, edge=edge_code, dx=var.mesh._dx, adv_const=adv_const,
                               field_device=phi.device)
         code, stream = N.dtype_code(phi.dtype), N.current_stream(phi.device)

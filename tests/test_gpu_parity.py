@@ -19,6 +19,7 @@ OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
 EDGES = U.load("edges.pt")
 RZ = U.load("rz_ops.pt")
+RZ_EDGE = U.load("rz_edge.pt")
 DEV = "cuda"
 
 
@@ -158,6 +159,35 @@ def test_rz_operator_fixtures_bit_exact(case):
     var.set_var_tensor(phi.clone())
     _apply_bc_otf(var, mesh)
     same(var(), "bc_applied")
+
+
+@pytest.mark.parametrize("case", RZ_EDGE, ids=[c["name"] for c in RZ_EDGE])
+def test_rz_edge_fixtures_bit_exact(case):
+    """edge=True on axisymmetric meshes (fdc.py:203-288 on top of the rz coefficient tables), jacobian / hessian with
+    the (r, z) component names -- against the real reference's outputs (tests/golden/make_golden_rz_edge.py)."""
+    from pyapes_b200.solver.fdc import FDC, hessian, jacobian
+
+    mesh, var = U.product_field(case, DEV)
+    assert mesh.coord_sys == "rz"
+    var.set_var_tensor(case["phi"].to(DEV).clone())
+    out = case["out"]
+
+    def same(got, ref, key):
+        assert torch.equal(got.cpu(), ref), f"{key}: {(got.cpu() - ref).abs().max().item():.3e}"
+
+    same(FDC({"laplacian": {"edge": True}}).laplacian(var), out["lap_edge"], "lap_edge")
+    same(FDC({"grad": {"edge": True}}).grad(var), out["grad_edge"], "grad_edge")
+    assert out["div_edge_raises"]
+    with pytest.raises(IndexError):
+        FDC({"div": {"limiter": "upwind", "edge": True}}).div(case["u_const"], var)
+    FDC({"laplacian": {"edge": False}, "grad": {"edge": False}, "div": {"limiter": "none", "edge": False}})
+    jac = jacobian(var)
+    assert sorted(jac.keys) == ["r", "z"]
+    for k in jac.keys:
+        same(jac[k], out["jac"][k], "jac_" + k)
+    hess = hessian(var)
+    for k in ("rr", "rz", "zz"):
+        same(hess[k], out["hess"][k], "hess_" + k)
 
 
 def test_jac_hess_diffflux_like_reference_tests():

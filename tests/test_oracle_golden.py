@@ -13,6 +13,7 @@ OPS = U.load("ops.pt")
 SOL = U.load("solvers.pt")
 EDGES = U.load("edges.pt")
 RZ = U.load("rz_ops.pt")
+RZ_EDGE = U.load("rz_edge.pt")
 TILES = U.load("ops_tiles.pt")
 JACDIV = U.load("jacdiv.pt")
 
@@ -147,6 +148,27 @@ def test_rz_operator_fixtures(case):
     x = phi.clone()
     O.apply_bcs(x, xs, bcs)
     assert torch.equal(x, out["bc_applied"])
+
+
+@pytest.mark.parametrize("case", RZ_EDGE, ids=[c["name"] for c in RZ_EDGE])
+def test_rz_edge_fixtures(case):
+    """edge=True on axisymmetric meshes: the rz Laplacian / the (coordinate-free) Grad with their faces replaced by the
+    one-sided formulas (fdc.py:203-288), jacobian and hessian named (r, z)."""
+    dtype = U.TDTYPE[case["spec"]["dtype"]]
+    torch.set_default_dtype(dtype)
+    xs, dx = U.oracle_axes(case)
+    bcs = U.oracle_bcs(case)
+    phi, out = case["phi"].clone(), case["out"]
+    e = O.Equation([O.Term("laplacian", 1.0, None)], dx, xs, bcs, rz=True).build(phi)
+    assert torch.equal(O.edge_laplacian(e.aop(phi), phi, dx), out["lap_edge"])
+    grad = O.edge_grad(O.apply_grad(O.grad_coeffs(phi, dx, bcs), phi), phi, dx)
+    assert torch.equal(grad, out["grad_edge"])
+    assert out["div_edge_raises"]
+    names = "rz"
+    for a, j in enumerate(O.jacobian(phi, dx)):
+        assert torch.equal(j, out["jac"][names[a]])
+    for (a, b), h in O.hessian(phi, dx).items():
+        assert torch.equal(h, out["hess"][names[a] + names[b]])
 
 
 @pytest.mark.parametrize("case", SOL, ids=[c["name"] for c in SOL])
