@@ -559,34 +559,61 @@ def run_ours(args):
             _run_e2e(k_steps)
         torch.cuda.synchronize()
 
+    e2e_trace = {}
+
     def _run_e2e(k_steps):
         ev_in = [None, None]
+        # per-step events (timing enabled): what the copies and the solve of each step cost and where the step waits
+        tr = {"up0": [], "up1": [], "s0": [], "s1": [], "dn0": [], "dn1": []}
 
         def upload(k):
             with torch.cuda.stream(h2d_s):
+                a = torch.cuda.Event(enable_timing=True)
+                a.record(h2d_s)
                 rhs_buf[k % 2][:, olo:ohi].copy_(rhs_h, non_blocking=True)
-                ev_in[k % 2] = torch.cuda.Event()
+                ev_in[k % 2] = torch.cuda.Event(enable_timing=True)
                 ev_in[k % 2].record(h2d_s)
+                tr["up0"].append(a)
+                tr["up1"].append(ev_in[k % 2])
 
         upload(0)
         for k in range(k_steps):
             torch.cuda.current_stream().wait_event(ev_in[k % 2])
             if k + 1 < k_steps:
                 upload(k + 1)  # overlaps this step's solve
+            s0 = torch.cuda.Event(enable_timing=True)
+            s0.record()
             solver, var = new_solver(rhs_buf[k % 2])
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 solver.solve()  # returns when the device has finished this solve
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=True)
             done.record()
             sol = var()
             with torch.cuda.stream(d2h_s):
                 d2h_s.wait_event(done)
+                d0 = torch.cuda.Event(enable_timing=True)
+                d0.record(d2h_s)
                 out_h.copy_(sol[:, olo:ohi], non_blocking=True)  # overlaps the next solve
+                d1 = torch.cuda.Event(enable_timing=True)
+                d1.record(d2h_s)
             sol.record_stream(d2h_s)  # the allocator may recycle it only after the download
+            tr["s0"].append(s0)
+            tr["s1"].append(done)
+            tr["dn0"].append(d0)
+            tr["dn1"].append(d1)
             del solver, var, sol
         torch.cuda.current_stream().wait_stream(d2h_s)
         torch.cuda.synchronize()
+        med = lambda v: sorted(v)[len(v) // 2] if v else None
+        e2e_trace.clear()
+        e2e_trace.update({
+            "upload_ms_median": med([a.elapsed_time(b) for a, b in zip(tr["up0"], tr["up1"])]),
+            "solve_ms_median": med([a.elapsed_time(b) for a, b in zip(tr["s0"], tr["s1"])]),
+            "download_ms_median": med([a.elapsed_time(b) for a, b in zip(tr["dn0"], tr["dn1"])]),
+            # device time between the end of one solve and the start of the next (host work + waiting for the upload)
+            "gap_ms_median": med([tr["s1"][i].elapsed_time(tr["s0"][i + 1]) for i in range(len(tr["s0"]) - 1)]),
+            "note": "this rank's events; copies of step k+1 / k-1 run on their own streams during the solve of step k"})
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -718,7 +745,7 @@ def run_ours(args):
                                        "bc_faces+shell_norm_ms_per_iter": kt["small_ms"]},
                      "kernel_share_of_iteration": kt["share"]},
         "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": int(rhs_h.numel() * 8),
-                "d2h_bytes_per_step": int(out_h.numel() * 8), "clocks": clocks_e2e,
+                "d2h_bytes_per_step": int(out_h.numel() * 8), "clocks": clocks_e2e, "trace": dict(e2e_trace),
                 "h2d_GBps": copy_rates["h2d_GBps"], "d2h_GBps": copy_rates["d2h_GBps"],
                 "pinned_copy_rates": copy_rates,
                 "note": "copies of step k+1 / k-1 overlap the solve of step k; the first upload and the last "

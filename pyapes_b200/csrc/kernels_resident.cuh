@@ -5,22 +5,26 @@
 // would move in 2-3 us -- launch, pipeline fill and the row-by-row march of a 2-D "plane" dominate
 // (BASELINE config 3 at 1024^2: 0.30 of the HBM-equivalent roofline, CG 0.27).  Here the field never leaves
 // the SM between steps:
-//   * CTA b (one per SM) owns R consecutive rows of the (n0, n2) grid and keeps them in shared memory for the
-//     whole launch;
-//   * the rows a neighbour needs -- the CTA's FIRST and LAST row -- are computed first in every step and stored
-//     into a global exchange buffer as LL lines: every 8-byte word carries 4 bytes of data and a 4-byte sequence
-//     number (the scheme of NCCL's LL protocol; aligned 8-byte accesses are single transactions).  The consumer --
-//     the neighbour's thread that computes the same column of ITS boundary row in the next step -- loads the line
-//     and retries until both sequence numbers are the ones it expects.  No flag word, no fence, no polling lane,
-//     no barrier between CTAs: the dependency is per column, and the line is in flight while both CTAs compute
-//     their interior rows.  (First version: red.release per warp / a publishing lane + bulk async copies into halo
-//     rows -- 5.3 / 4.2 us per step at 1024^2 against 2 us of arithmetic; the gpu-scope fences and the flag polls
-//     sat on the step's critical path.)
-//   * CG keeps x, r and d resident, exchanges d's boundary rows the same way, and sums its two dot products over
-//     per-CTA LL slots that every CTA reads back and adds in slot order -- every CTA holds bit-identical Krylov
+//   * CTA b (one per SM) owns R consecutive rows of the (n0, n2) grid and keeps them, with one halo row above and
+//     below, in shared memory for the whole launch;
+//   * the rows a neighbour needs -- the CTA's FIRST and LAST row -- are stored into a global exchange buffer as LL
+//     lines: every 8-byte word carries 4 bytes of data and a 4-byte sequence number (the scheme of NCCL's LL
+//     protocol; aligned 8-byte accesses are single transactions).  The consumer -- the neighbour's thread that
+//     computes the same column of ITS boundary row in the next step -- loads the line into its halo row and retries
+//     until both sequence numbers are the ones it expects.  No flag word, no fence, no polling lane, no barrier
+//     between CTAs: the dependency is per column.  Lines are requested at the start of a step without waiting and
+//     looked at when the boundary rows are due (after 2/5 of the interior), so that they travel while both CTAs
+//     compute.  (First version: red.release per warp / a publishing lane + bulk async copies into the halo rows --
+//     5.3 / 4.2 us per step at 1024^2 against 2 us of arithmetic; the gpu-scope fences and the flag polls sat on the
+//     step's critical path.)
+//   * CG keeps x, r and d resident, exchanges d's boundary rows the same way, and sums its two dot products by an LL
+//     all-gather into per-CTA inboxes (res_allsum), added in slot order -- every CTA holds bit-identical Krylov
 //     scalars and runs the scalar stage (finalize_stage) redundantly, as k_cg_persistent does.  x_new is streamed
 //     to the global ping-pong buffers every iteration, so that on exit they hold the last two iterates exactly
 //     like the fused kernels leave them (the loser is the reference's VARo).
+//   * two code paths per kernel: the uniform-coefficient fast path (ResFast: every face Dirichlet => the coefficient
+//     classes are bitwise equal => every region cell is the class-0 stencil; thread-fixed columns, two rows per trip)
+//     and the general item loop (any coefficients, any row length).
 // Arithmetic: the star engine's operation order (star_cells_eq, FLAT), one rounding per reference operation ->
 // Euler is bit-identical to the streaming path; CG differs only in the summation order of the dot products
 // (as between any two kernel variants).
