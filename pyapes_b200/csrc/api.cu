@@ -244,6 +244,28 @@ static void launch_bcs(Launcher& L, const GridDev& g, int nfaces, const pa_face_
     int blocks = (int)((ncell + kBlock - 1) / kBlock);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
     if (blocks < 1) blocks = 1;
+    // The next face of the list is the other side of this axis: one launch for both when that keeps the list-order
+    // semantics -- two non-periodic faces (they touch and read disjoint planes once n >= 5), or the periodic pair
+    // lower-then-upper (the upper face is the new lower value, column by column).  Single GPU only (on slabs an x
+    // face may belong to another rank).  6 -> 3 boundary launches per sweep for a full 3-D face list.
+    if (!dist && f + 1 < nfaces && faces[f + 1].axis == faces[f].axis && faces[f + 1].side == -faces[f].side &&
+        g.n[fd.axis] >= 5) {
+      const bool p0 = faces[f].kind == PA_BC_PERIODIC, p1 = faces[f + 1].kind == PA_BC_PERIODIC;
+      const bool pair_np = !p0 && !p1;
+      const bool pair_per = p0 && p1 && faces[f].side < 0 && faces[f].values == nullptr && faces[f + 1].values == nullptr;
+      if (pair_np || pair_per) {
+        FaceDev<T> fe;
+        fe.axis = faces[f + 1].axis;
+        fe.side = faces[f + 1].side;
+        fe.kind = faces[f + 1].kind;
+        fe.value = (T)faces[f + 1].value;
+        fe.values = (const T*)faces[f + 1].values;
+        k_bc_face_pair<T><<<dim3(blocks, pair_per ? 1 : 2), kBlock, 0, L.s>>>(g, fd, fe, pair_per ? 1 : 0, phi, st);
+        ++L.count;
+        ++f;
+        continue;
+      }
+    }
     k_bc_face<T><<<blocks, kBlock, 0, L.s>>>(g, fd, phi, st);
     ++L.count;
   }

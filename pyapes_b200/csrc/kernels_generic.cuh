@@ -350,6 +350,34 @@ __global__ void __launch_bounds__(kBlock) k_apply_shell(GridDev g, EqDev<T> eq, 
 // ---------------------------------------------------------------------------------------
 // boundary conditions: one launch per face, in list order (bcs.py:197-280)
 // ---------------------------------------------------------------------------------------
+// value of face cell k (column `base` of the two other axes) of face f, from the current phi
+template <typename T>
+__device__ __forceinline__ T bc_face_value(const FaceDev<T>& f, const T* phi, long long base, long long k, long long sa,
+                                           int n) {
+  // planes: face, 1 and 2 inward, 1 and 2 "forward" (wrapped), as the rolled masks give
+  const int pf = f.side < 0 ? 0 : n - 1;
+  const int p1 = ((pf - f.side) % n + n) % n, p2 = ((pf - 2 * f.side) % n + n) % n;
+  const int f1 = ((pf + f.side) % n + n) % n, f2 = ((pf + 2 * f.side) % n + n) % n;
+  switch (f.kind) {
+    case PA_BC_DIRICHLET:
+      return f.values ? f.values[k] : f.value;
+    case PA_BC_NEUMANN: {
+      T cterm = f.values ? f.values[k] : f.value;
+      T t = (T)(4.0 / 3.0) * phi[base + p1 * sa];
+      t = t - (T)(1.0 / 3.0) * phi[base + p2 * sa];
+      return t + cterm;
+    }
+    case PA_BC_SYMMETRY:
+      return phi[base + p1 * sa];
+    default:  // periodic
+      if (f.side < 0) {
+        T t = phi[base + p1 * sa] - phi[base + f1 * sa];
+        return t + phi[base + f2 * sa];
+      }
+      return phi[base + f1 * sa];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_bc_face(GridDev g, FaceDev<T> f, T* __restrict__ phi,
                                                     const SolverState* st) {
@@ -359,38 +387,38 @@ __global__ void __launch_bounds__(kBlock) k_bc_face(GridDev g, FaceDev<T> f, T* 
   const long long ncell = (long long)g.n[b] * g.n[c];
   const long long sa = stride_of(g, a), sb = stride_of(g, b), sc = stride_of(g, c);
   const int n = g.n[a];
-  // planes: face, 1 and 2 inward, 1 and 2 "forward" (wrapped), as the rolled masks give
   const int pf = f.side < 0 ? 0 : n - 1;
-  const int p1 = ((pf - f.side) % n + n) % n, p2 = ((pf - 2 * f.side) % n + n) % n;
-  const int f1 = ((pf + f.side) % n + n) % n, f2 = ((pf + 2 * f.side) % n + n) % n;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ncell;
        k += (long long)gridDim.x * blockDim.x) {
     long long ib = k / g.n[c], ic = k - ib * g.n[c];
     long long base = ib * sb + ic * sc;
-    T out;
-    switch (f.kind) {
-      case PA_BC_DIRICHLET:
-        out = f.values ? f.values[k] : f.value;
-        break;
-      case PA_BC_NEUMANN: {
-        T cterm = f.values ? f.values[k] : f.value;
-        T t = (T)(4.0 / 3.0) * phi[base + p1 * sa];
-        t = t - (T)(1.0 / 3.0) * phi[base + p2 * sa];
-        out = t + cterm;
-      } break;
-      case PA_BC_SYMMETRY:
-        out = phi[base + p1 * sa];
-        break;
-      default:  // periodic
-        if (f.side < 0) {
-          T t = phi[base + p1 * sa] - phi[base + f1 * sa];
-          out = t + phi[base + f2 * sa];
-        } else {
-          out = phi[base + f1 * sa];
-        }
-        break;
-    }
-    phi[base + pf * sa] = out;
+    phi[base + pf * sa] = bc_face_value<T>(f, phi, base, k, sa, n);
+  }
+}
+
+// Two consecutive faces of the list that are the two sides of ONE axis, as one launch (api.cu launch_bcs decides when
+// that keeps the list-order semantics): non-periodic pairs touch and read disjoint planes (n >= 5), blockIdx.y picks
+// the face; a periodic pair (lower, then upper) is done column by column by one thread -- the upper face is the new
+// lower face value (bcs.py:262-280).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_bc_face_pair(GridDev g, FaceDev<T> f0, FaceDev<T> f1, int periodic_pair,
+                                                         T* phi, const SolverState* st) {
+  if (st != nullptr && st->done) return;
+  const int a = f0.axis;
+  const int b = (a == 0) ? 1 : 0, c = (a == 2) ? 1 : 2;
+  const long long ncell = (long long)g.n[b] * g.n[c];
+  const long long sa = stride_of(g, a), sb = stride_of(g, b), sc = stride_of(g, c);
+  const int n = g.n[a];
+  if (periodic_pair && blockIdx.y != 0) return;
+  const FaceDev<T>& f = (blockIdx.y == 0) ? f0 : f1;
+  const int pf = f.side < 0 ? 0 : n - 1;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ncell;
+       k += (long long)gridDim.x * blockDim.x) {
+    long long ib = k / g.n[c], ic = k - ib * g.n[c];
+    long long base = ib * sb + ic * sc;
+    const T v = bc_face_value<T>(f, phi, base, k, sa, n);
+    phi[base + pf * sa] = v;
+    if (periodic_pair) phi[base + (long long)(f1.side < 0 ? 0 : n - 1) * sa] = v;  // upper = the new lower value
   }
 }
 

@@ -79,12 +79,16 @@ __device__ __forceinline__ bool ll_try(const uint2* p, unsigned seq, float& v) {
 // N consecutive lines: all loads are issued before the first check
 template <typename T, int N>
 __device__ __forceinline__ void ll_load(const typename LLOf<T>::line* p, unsigned seq, T (&v)[N]) {
+  unsigned ns = 32u;
   while (true) {
     bool ok = true;
 #pragma unroll
     for (int e = 0; e < N; ++e) ok &= ll_try(p + e, seq, v[e]);
     if (ok) break;
-    __nanosleep(40);  // back off: hundreds of waiting threads re-reading at full rate only load the L2
+    // back off (32 .. 256 ns): hundreds of waiting threads re-reading at full rate only load the L2 slices the
+    // awaited stores have to get through
+    __nanosleep(ns);
+    if (ns < 256u) ns <<= 1;
   }
 }
 template <typename T, int N>

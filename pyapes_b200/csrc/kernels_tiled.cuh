@@ -70,8 +70,9 @@ struct TilePlan {
   int nz = 0;
   int work_slot = 0;  // entry of the launch in the work-counter pool (kernels_tma.cuh)
   int first_static = 0;  // 1: a CTA's first item is its block index, the counter serves the rest
-  // star engine: the three coefficient classes of every operator hold the same numbers on every active axis (no
-  // Neumann / Symmetry face), so the general path takes class 0 like the LEAN one (kernels_tma_pw.cuh, UNI)
+  // star engine: bit a = the three coefficient classes of every operator hold the same numbers on kernel axis a (no
+  // Neumann / Symmetry face there); tiles whose wall-adjacent cells only lie on such axes take class 0 like the LEAN
+  // path (kernels_tma_pw.cuh, UNI)
   int uni = 0;
 };
 

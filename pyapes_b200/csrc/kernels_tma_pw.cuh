@@ -101,6 +101,16 @@ __device__ __forceinline__ T div_rcp(T a, T d, T rcp, bool den_ok) {
   return a / d;
 }
 
+// the same quotient once the exponent windows have been checked (for a whole warp at a time, see pw_consumer)
+template <typename T>
+__device__ __forceinline__ T div_rcp_checked(T a, T d, T rcp) {
+  T q = a * rcp;
+  T e = fma(-d, q, a);
+  q = fma(e, rcp, q);
+  e = fma(-d, q, a);
+  return fma(e, rcp, q);
+}
+
 // diagonal of the operator sum for one coefficient-class triple (Jacobi)
 template <typename T, typename K, int NOPS>
 __device__ __forceinline__ T star_diag(const EqDev<T>& eq, int clx, int cy, int cz) {
@@ -263,7 +273,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
             }
         }
       }
-      const int clx = UNI ? 0 : coef_class(g, 0, x);
+      const int clx = coef_class(g, 0, x);  // (plane-uniform: a dynamic index costs nothing, LEAN and UNI included)
       if (MODE == PW_GRAD) {
         // central gradient, one output array per mesh axis (fdc.py:80-87); op order of k_grad
         const OpDev<T>& o = eq.op[0];
@@ -327,6 +337,20 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
 #pragma unroll
         for (int e = 0; e < VEC; ++e) av[e] = (T)0;
       }
+      // Jacobi with one diagonal per plane: the exponent windows of div_rcp are checked for the WARP's cells of this row
+      // in one vote -- per cell they were a compare chain and two branches, 80 of the ~290 instructions of a LEAN plane
+      // step (ncu source page) -- and the per-cell fallback only runs for a warp that holds a zero / tiny / huge residual
+      bool jac_fast = false;
+      if (MODE == PW_JACOBI && (LEAN || UNI)) {
+        bool okw = den_ok;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const bool in = xreg && (LEAN || ((c.inreg >> (k * VEC + e)) & 1u));
+          const T res = av[e] - ax[k][e];
+          okw = okw && (!in || exp_window(res, -DivWin<T>::NUM, DivWin<T>::NUM));
+        }
+        jac_fast = __all_sync(0xffffffffu, okw) != 0;
+      }
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const bool in = xreg && (LEAN || ((c.inreg >> (k * VEC + e)) & 1u));
@@ -343,7 +367,7 @@ __device__ __forceinline__ void pw_consumer(const TilePlan& p, const GridDev& g,
           if (in) {
             const T res = av[e] - ax[k][e];
             if (LEAN || UNI)
-              xn = xc + div_rcp<T>(res, dgl, rcl, den_ok);
+              xn = xc + (jac_fast ? div_rcp_checked<T>(res, dgl, rcl) : div_rcp<T>(res, dgl, rcl, den_ok));
             else
               xn = xc + res / star_diag<T, K, NOPS>(eq, coef_class(g, 0, x), c.cly[k], c.clz[e]);
           }
@@ -468,11 +492,16 @@ k_star_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     }
   } else {
     const bool full_tile = (C::FLAT || y0 + C::TY <= g.n[1]) && (z0 + C::TZ <= g.n[2]);
-    const bool edge = (!C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2))) || (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
-    if (full_tile && !edge)
+    const bool edge_y = !C::FLAT && ((y0 < 2) || (y0 + C::TY > g.n[1] - 2));
+    const bool edge_z = (z0 < 2) || (z0 + C::TZ > g.n[2] - 2);
+    // class-free tile: on each tiled axis either the classes hold the same numbers (TilePlan::uni bit) or the tile has
+    // no cell next to a wall (its classes are 0 anyway) -- with Neumann / Symmetry faces on ONE axis (config 4) only
+    // the two tile rows along those walls keep the per-cell class selects and the true division of Jacobi
+    const bool uni_tile = (!edge_y || (p.uni & 2)) && (!edge_z || (p.uni & 4));
+    if (full_tile && !edge_y && !edge_z)
       pw_consumer<T, K, MODE, true, NOPS>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0, x0,
                                            x1, acc);
-    else if (p.uni)
+    else if (uni_tile)
       pw_consumer<T, K, MODE, false, NOPS, true>(p, g, eq, out, out2, dt, has_aux != 0, stages, full, empty, y0, z0,
                                                   x0, x1, acc);
     else
@@ -706,16 +735,18 @@ k_bi_st_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CU
 }
 
 // ---- host ------------------------------------------------------------------------------------
-// the three coefficient classes of every operator are bitwise equal on every active axis (TilePlan::uni)
+// TilePlan::uni: bit a set = the three coefficient classes of every operator are bitwise equal on kernel axis a
 template <typename T>
-inline bool eq_uniform(const GridDev& g, const EqDev<T>& eq) {
-  for (int k = 0; k < eq.nops; ++k)
-    for (int a = 0; a < 3; ++a) {
-      if (!g.act[a]) continue;
+inline int eq_uniform(const GridDev& g, const EqDev<T>& eq) {
+  int mask = 0;
+  for (int a = 0; a < 3; ++a) {
+    bool same = true;
+    for (int k = 0; k < eq.nops; ++k)
       for (int cls = 1; cls < 3; ++cls)
-        if (std::memcmp(&eq.op[k].coef[a][cls][0], &eq.op[k].coef[a][0][0], 3 * sizeof(T)) != 0) return false;
-    }
-  return true;
+        if (std::memcmp(&eq.op[k].coef[a][cls][0], &eq.op[k].coef[a][0][0], 3 * sizeof(T)) != 0) same = false;
+    if (same || !g.act[a]) mask |= 1 << a;
+  }
+  return mask;
 }
 
 template <typename T>
@@ -772,7 +803,7 @@ static bool launch_star_tma_k(cudaStream_t s, const GridDev& g, const EqDev<T>& 
   typedef PwCfg<T, K> C;
   TilePlan tile = tile_in;
   tile.src0 = in;  // wrap-around reads of periodic axes 1/2
-  tile.uni = eq_uniform<T>(g, eq) && getenv("PA_STAR_NO_UNI") == nullptr ? 1 : 0;
+  tile.uni = getenv("PA_STAR_NO_UNI") == nullptr ? eq_uniform<T>(g, eq) : 0;
   CUtensorMap tm_in, tm_aux;
   if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
   if (!make_map<T>(&tm_aux, aux ? aux : in, g, C::OBOXZ, C::TY)) return false;
@@ -864,7 +895,7 @@ static bool launch_star_grad_k(cudaStream_t s, const GridDev& g, const EqDev<T>&
   typedef PwCfg<T, K> C;
   TilePlan tile = tile_in;
   tile.src0 = in;
-  tile.uni = eq_uniform<T>(g, eq) && getenv("PA_STAR_NO_UNI") == nullptr ? 1 : 0;
+  tile.uni = getenv("PA_STAR_NO_UNI") == nullptr ? eq_uniform<T>(g, eq) : 0;
   CUtensorMap tm_in;
   if (!make_map<T>(&tm_in, in, g, C::BOXZ, C::BOXY)) return false;
   launch_star_tma_n<T, K, PW_GRAD, 1>(s, tm_in, tm_in, g, eq, tile, false, out, nullptr, (T)0, nullptr, nullptr, 0);

@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import fd_oracle as O
 from tests import _util as U
 from tests.golden.bc_callables import CALLABLES
 
@@ -320,3 +321,49 @@ def test_contraction_mode_is_opt_in_and_within_tolerance(shape):
     (re, xe), (rc, xc) = run(1e-8, 5000, False), run(1e-8, 5000, True)
     assert re["converge"] and rc["converge"] and abs(re["itr"] - rc["itr"]) <= 1, (re, rc)
     assert (xe - xc).abs().max().item() <= 1e-8 * xe.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [[40, 36, 128], [96, 256]])
+@pytest.mark.parametrize("kinds", ["dirichlet", "mixed"])
+def test_jacobi_quotient_fallback_is_bit_exact(shape, kinds):
+    """The TMA Jacobi sweep divides by a reciprocal plus two FMA corrections when a warp-wide vote finds every residual
+    inside a safe exponent window, and falls back to the true division otherwise (kernels_tma_pw.cuh).  A right-hand
+    side with patches of exact zeros and of 1e-200 must give the oracle's bits on both routes (lockstep sweeps)."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    nd = len(shape)
+    if kinds == "dirichlet":
+        ks, vs = ["dirichlet"] * (2 * nd), [0.0, 0.25, -0.5, 1.0, 0.0, 0.5][: 2 * nd]
+    elif nd == 3:
+        ks, vs = ["dirichlet", "dirichlet", "neumann", "symmetry", "dirichlet", "dirichlet"], [0.0, 0.25, 0.5, None, 0.0, 1.0]
+    else:
+        ks, vs = ["neumann", "dirichlet", "dirichlet", "dirichlet"], [0.2, 0.0, 1.0, 0.0]
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, "cuda", "double")
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vs, ks), "obstacle": None})
+    g = torch.Generator().manual_seed(3)
+    rhs = torch.rand(1, *shape, generator=g, dtype=torch.float64) - 0.5
+    sl = [slice(None)] * (nd + 1)
+    sl[1] = slice(2, 9)
+    rhs[tuple(sl)] = 0.0          # exact zeros: x = 0 there at first, so the residual is an exact zero
+    sl[1] = slice(12, 15)
+    rhs[tuple(sl)] *= 1e-200      # below the window (a patch above it would overflow the norm: RuntimeError in both)
+    sweeps = 4
+    s = Solver({"fdm": {"method": "jacobi", "tol": 1e-300, "max_it": sweeps - 1, "report": False}})
+    s.set_eq(FDM().laplacian(1.0, var) == rhs.to("cuda"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rep = s.solve()
+    xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
+    bcs = [O.FaceBC(f, k, v) for f, k, v in zip(O.FACES[: 2 * nd], ks, vs)]
+    x0 = torch.zeros(1, *shape, dtype=torch.float64)
+    eq = O.Equation([O.Term("laplacian", 1.0, 1.0)], dx, xs, bcs).build(x0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol, rep_o, _ = O.jacobi(eq, x0, eq.adjust_rhs(x0, rhs.clone()), 1e-300, sweeps - 1)
+    assert rep["itr"] == rep_o["itr"] == sweeps
+    assert torch.equal(var().cpu(), sol), (var().cpu() - sol).abs().max().item()

@@ -73,3 +73,14 @@ def test_headline_cg_kernels_use_tma_and_mbarriers():
         sass = subprocess.run([CUOBJDUMP, "-sass", "-fun", hits[0], LIB], capture_output=True, text=True).stdout
         assert "UTMALDG" in sass, f"{pat}: no TMA tensor loads in the SASS"
         assert "SYNCS" in sass, f"{pat}: no mbarrier instructions in the SASS"
+
+
+def test_resident_kernels_do_not_spill_and_fit_one_cta_of_512_threads():
+    """The shared-memory-resident kernels (kernels_resident.cuh) run ONE 512-thread CTA per SM: <= 128 registers, and
+    no spill stack -- a noinline call of the general cell path once pushed every item's vectors through local memory."""
+    res = _resources()
+    hits = {k: v for k, v in res.items() if re.search(r"k_(euler|cg)_resident<", k)}
+    assert len(hits) >= 14, sorted(hits)
+    for name, (_, regs, stack) in hits.items():
+        assert stack == 0, f"{name.split('(')[0]}: {stack} B of spill stack"
+        assert regs <= 128, f"{name.split('(')[0]}: {regs} registers"
