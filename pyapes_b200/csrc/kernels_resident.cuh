@@ -263,7 +263,10 @@ struct ResScales {
       if (q < (NOPS > 0 ? NOPS : eq.nops)) sc[q] = op_scale<T>(eq.op[q]);
   }
 };
-template <typename T, bool LEAN, int NOPS>
+// SHIFT = false: the equation has no implicit-Euler shift (explicit Euler), the test is compiled out.
+// The scale factor is applied unconditionally: when it is not "used" it is exactly 1 and x * 1 == x bit for bit, and a
+// multiplication is cheaper than the two selects per value a run-time `use` costs (ncu: 139 FSEL per warp and step).
+template <typename T, bool LEAN, int NOPS, bool SHIFT = true>
 __device__ __forceinline__ T res_star(const EqDev<T>& eq, const ResScales<T, NOPS>& scs, int clx, int cz, T v0, T xp,
                                       T xm, T zp, T zm) {
   constexpr int MAXO = NOPS > 0 ? NOPS : kMaxOps;
@@ -283,9 +286,9 @@ __device__ __forceinline__ T res_star(const EqDev<T>& eq, const ResScales<T, NOP
     s2 = s2 + o.coef[2][iz][1] * v0;
     s2 = s2 + o.coef[2][iz][2] * zm;
     acc = acc + s2;
-    if (sc.use) acc = acc * sc.scale;
+    acc = acc * sc.scale;
     res = res + acc;
-    if (o.has_shift) {
+    if (SHIFT && o.has_shift) {
       const T m = o.shift * v0;
       res = m + res;
     }
@@ -393,16 +396,28 @@ __device__ __forceinline__ ResFast res_fast_init(const ResCtx& c, const GridDev&
   }
   return f;
 }
+// mask of the vector's cells that lie inside the region along the contiguous axis (all ones but for the two wall columns)
+template <typename T>
+__device__ __forceinline__ unsigned res_col_mask(const GridDev& g, int col) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int e = 0; e < VecOf<T>::N; ++e)
+    if (col + e >= g.lo[2] && col + e < g.hi[2]) m |= 1u << e;
+  return m;
+}
 // rows [ra, rb) of the thread's column blocks, two rows per trip (both rows are computed before either is stored:
-// the compiler must assume that `cur` and `nxt` alias):  cell(v0, vm, vp, zl, zr, local row, col) -> o, put(row, col, o)
+// the compiler must assume that `cur` and `nxt` alias):
+//   cell(v0, vm, vp, zl, zr, local row, col, column mask, row inside the region) -> o,   put(row, col, o)
+// (interior rows of a CTA are region rows: res_fast_init)
 template <typename T, typename FC, typename FP>
-__device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f, const T* cur, int ra, int rb,
-                                               FC cell, FP put) {
+__device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f, const GridDev& g, const T* cur, int ra,
+                                               int rb, FC cell, FP put) {
   constexpr int VEC = VecOf<T>::N;
   if (rb <= ra) return;
   const int n2 = c.n2;
   for (int cv = f.cv; cv < c.nv; cv += f.cstep) {
     const int col = cv * VEC;
+    const unsigned cm = res_col_mask<T>(g, col);
     const T* p = cur + ra * n2 + col;
     T vm[VEC], v0[VEC];
     lds_vec<T>(p - n2, vm);
@@ -413,8 +428,8 @@ __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f
       lds_vec<T>(p + n2, v1);
       lds_vec<T>(p + 2 * n2, v2);
       const T zla = p[-1], zra = p[VEC], zlb = p[n2 - 1], zrb = p[n2 + VEC];
-      cell(v0, vm, v1, zla, zra, lr, col, oa);
-      cell(v1, v0, v2, zlb, zrb, lr + 1, col, ob);
+      cell(v0, vm, v1, zla, zra, lr, col, cm, true, oa);
+      cell(v1, v0, v2, zlb, zrb, lr + 1, col, cm, true, ob);
       put(lr, col, oa);
       put(lr + 1, col, ob);
 #pragma unroll
@@ -428,7 +443,7 @@ __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f
       T v1[VEC], oa[VEC];
       lds_vec<T>(p + n2, v1);
       const T zla = p[-1], zra = p[VEC];
-      cell(v0, vm, v1, zla, zra, lr, col, oa);
+      cell(v0, vm, v1, zla, zra, lr, col, cm, true, oa);
       put(lr, col, oa);
     }
   }
@@ -436,9 +451,13 @@ __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f
 // the CTA's first and last row (one row if it owns a single one) for the thread's column blocks, as ONE trip; the
 // halo rows of `cur` are in place (res_halo_need has run for these items)
 template <typename T, typename FC, typename FP>
-__device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const T* cur, int col, FC cell, FP put) {
+__device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const GridDev& g, const T* cur, int col, FC cell,
+                                                  FP put) {
   constexpr int VEC = VecOf<T>::N;
   const int n2 = c.n2;
+  const unsigned cm = res_col_mask<T>(g, col);
+  const bool ra_in = c.row0 >= g.lo[0] && c.row0 < g.hi[0];
+  const bool rb_in = c.row0 + c.rows - 1 >= g.lo[0] && c.row0 + c.rows - 1 < g.hi[0];
   const T* pa = cur + col;
   T a0[VEC], am[VEC], ap[VEC], oa[VEC];
   lds_vec<T>(pa, a0);
@@ -446,7 +465,7 @@ __device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const T* cur,
   lds_vec<T>(pa + n2, ap);
   const T zla = pa[-1], zra = pa[VEC];
   if (c.rows < 2) {
-    cell(a0, am, ap, zla, zra, 0, col, oa);
+    cell(a0, am, ap, zla, zra, 0, col, cm, ra_in, oa);
     put(0, col, oa);
     return;
   }
@@ -456,8 +475,8 @@ __device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const T* cur,
   lds_vec<T>(pb - n2, bm);
   lds_vec<T>(pb + n2, bp);
   const T zlb = pb[-1], zrb = pb[VEC];
-  cell(a0, am, ap, zla, zra, 0, col, oa);
-  cell(b0, bm, bp, zlb, zrb, c.rows - 1, col, ob);
+  cell(a0, am, ap, zla, zra, 0, col, cm, ra_in, oa);
+  cell(b0, bm, bp, zlb, zrb, c.rows - 1, col, cm, rb_in, ob);
   put(0, col, oa);
   put(c.rows - 1, col, ob);
 }
@@ -528,28 +547,30 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
         }
       }
       auto cell = [&](const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC], T zl, T zr, int row, int col,
-                      T (&o)[VEC]) {
-        const int grow = c.row0 + row;
+                      unsigned cm, bool rin, T (&o)[VEC]) {
         T av[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) av[e] = (T)0;
         if (HAS_RHS) {
           typedef typename VecOf<T>::type V;
-          V q = __ldg(reinterpret_cast<const V*>(rhs + grow * rowlen + col));
+          V q = __ldg(reinterpret_cast<const V*>(rhs + (c.row0 + row) * rowlen + col));
           const T* qs = reinterpret_cast<const T*>(&q);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) av[e] = qs[e];
         }
-        const bool rin = grow >= g.lo[0] && grow < g.hi[0];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
           const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
-          const T a = res_star<T, true, NOPS>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+          const T a = res_star<T, true, NOPS, false>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
           const T res = av[e] - a;
-          const T xn = v0[e] + dt * res;
-          const int z = col + e;
-          o[e] = (rin && z >= g.lo[2] && z < g.hi[2]) ? xn : v0[e];  // the wall columns / rows keep their values
+          o[e] = v0[e] + dt * res;
+        }
+        // the wall columns / rows keep their values: a branch that all but two warps of a CTA never take
+        if (!rin || cm != (1u << VEC) - 1u) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (!rin || !((cm >> e) & 1u)) o[e] = v0[e];
         }
       };
       auto put = [&](int row, int col, const T (&o)[VEC]) {
@@ -561,7 +582,7 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
         if (send) res_send<T>(c, ll, row, col, (unsigned)(s + 1), seq_out, o);
       };
       for (int seg = 0; seg < 2; ++seg) {  // ONE instance of the march
-        res_fast_march<T>(c, fast, cur, seg == 0 ? fast.ta : fsplit, seg == 0 ? fsplit : fast.tb, cell, put);
+        res_fast_march<T>(c, fast, g, cur, seg == 0 ? fast.ta : fsplit, seg == 0 ? fsplit : fast.tb, cell, put);
         if (seg == 0 && fast.boundary) {
           int k = 0;
           for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
@@ -570,7 +591,7 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
               res_halo_get<T>(c, ll, cur, col, 0, (unsigned)s, seq_in, b0, true);
             if (blockIdx.x + 1 < gridDim.x && !((got >> (2 * k + 1)) & 1u))
               res_halo_get<T>(c, ll, cur, col, 1, (unsigned)s, seq_in, b0, true);
-            res_fast_boundary<T>(c, cur, col, cell, put_boundary);
+            res_fast_boundary<T>(c, g, cur, col, cell, put_boundary);
           }
         }
       }
@@ -772,16 +793,17 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
     };
     // uniform coefficients: the class-0 stencil on a vector, 0 where the cell is outside the region
     auto fast_cell = [&](const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC], T zl, T zr, int row, int col,
-                         T (&ad)[VEC]) {
-      const int grow = c.row0 + row;
-      const bool rin = grow >= g.lo[0] && grow < g.hi[0];
+                         unsigned cm, bool rin, T (&ad)[VEC]) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
         const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
-        const T a = res_star<T, true, 1>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
-        const int z = col + e;
-        ad[e] = (rin && z >= g.lo[2] && z < g.hi[2]) ? a : (T)0;
+        ad[e] = res_star<T, true, 1>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+      }
+      if (!rin || cm != (1u << VEC) - 1u) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if (!rin || !((cm >> e) & 1u)) ad[e] = (T)0;
       }
     };
     // (d == 0 wherever ad was forced to 0 -- outside the region -- so the product adds an exact zero there)
@@ -810,7 +832,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
             got |= 2u << (2 * k);
         }
       }
-      res_fast_march<T>(c, fast, sd, fast.ta, fast.tb, fast_cell, dad_put);
+      res_fast_march<T>(c, fast, g, sd, fast.ta, fast.tb, fast_cell, dad_put);
       if (fast.boundary) {
         int k = 0;
         for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
@@ -819,7 +841,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
             res_halo_get<T>(c, ll, sd, col, 0, it, seq_d, (const T*)nullptr, true);
           if (blockIdx.x + 1 < gridDim.x && !((got >> (2 * k + 1)) & 1u))
             res_halo_get<T>(c, ll, sd, col, 1, it, seq_d, (const T*)nullptr, true);
-          res_fast_boundary<T>(c, sd, col, fast_cell, dad_put);
+          res_fast_boundary<T>(c, g, sd, col, fast_cell, dad_put);
         }
       }
     } else {
@@ -910,8 +932,8 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
         update(row, col, m, dv, ad);
       };
       if (fast.boundary)
-        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep) res_fast_boundary<T>(c, sd, cv * VEC, fast_cell, upd_put);
-      res_fast_march<T>(c, fast, sd, fast.ta, fast.tb, fast_cell, upd_put);
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep) res_fast_boundary<T>(c, g, sd, cv * VEC, fast_cell, upd_put);
+      res_fast_march<T>(c, fast, g, sd, fast.ta, fast.tb, fast_cell, upd_put);
     } else {
       for (ResIt a = res_it_first(c); a.j < c.rows;) {
         const ResIt b = res_it_next(c, a);
