@@ -59,6 +59,8 @@ PA_EXTERN_APPLY(float)
 #define PA_EXTERN_RES(T)                                                                                           \
   extern template bool launch_euler_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, \
                                                 T*, T*, const T*, T, int);                                         \
+  extern template bool launch_apply_direct2d<T, false>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*); \
+  extern template bool launch_apply_direct2d<T, true>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*);  \
   extern template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*,      \
                                              const T*, SolverState*, int, int);
 PA_EXTERN_RES(double)
@@ -343,20 +345,38 @@ static int method_nvec(int method) {
   }
 }
 
-// pinned mailbox for polling the device-side state
+// Mailbox for polling the device-side state: MAPPED pinned memory that a one-thread kernel writes straight from the
+// device.  (It used to be a 200-byte cudaMemcpyAsync: a device-to-host copy queues on the copy engine behind whatever
+// bulk download the caller has in flight on another stream -- in the end-to-end loop of bench.py the solution of the
+// previous step, 129 ms per GiB with eight ranks sharing the host link -- and every poll of the solver then idled the
+// GPU until that download had finished: 383 instead of 307 ms per solve at N = 8, e2e 0.78 of the device-resident
+// value.  A kernel's stores do not go through a copy engine.)
 static SolverState* host_mailbox() {
   static SolverState* p = nullptr;
   if (!p) {
-    if (cudaHostAlloc((void**)&p, sizeof(SolverState), cudaHostAllocDefault) != cudaSuccess)
+    if (cudaHostAlloc((void**)&p, sizeof(SolverState), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
       p = nullptr;
+    }
   }
   return p;
+}
+
+__global__ void k_state_mirror(const SolverState* dev, SolverState* host) {
+  *host = *dev;
+  __threadfence_system();
 }
 
 static int poll_state(cudaStream_t s, const SolverState* dev, SolverState** out) {
   SolverState* h = host_mailbox();
   if (!h) return fail(PA_ERR_CUDA, "cudaHostAlloc failed");
-  PA_CUDA(cudaMemcpyAsync(h, dev, sizeof(SolverState), cudaMemcpyDeviceToHost, s));
+  SolverState* hd = nullptr;
+  if (cudaHostGetDevicePointer((void**)&hd, h, 0) == cudaSuccess && hd != nullptr) {
+    k_state_mirror<<<1, 1, 0, s>>>(dev, hd);
+  } else {  // no mapped memory on this platform: the copy engine it is
+    cudaGetLastError();
+    PA_CUDA(cudaMemcpyAsync(h, dev, sizeof(SolverState), cudaMemcpyDeviceToHost, s));
+  }
   PA_CUDA(cudaStreamSynchronize(s));
   *out = h;
   return PA_OK;
@@ -1199,10 +1219,17 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
   return PA_OK;
 }
 
-// PA_APPLY_VARIANT=generic forces k_apply / k_grad (A/B runs of the two paths; read per call)
+// PA_APPLY_VARIANT=generic forces k_apply / k_grad, =tma the TMA star engine, =direct the direct 2-D kernel wherever
+// it applies (A/B runs of the paths; read per call).  Default: 2-D grids up to kDirect2dCells cells take the direct
+// kernel (no pipeline to fill: 1024^2 in ~4 us instead of ~10), everything else eligible the TMA engine.
 static bool apply_force_generic() {
   const char* e = getenv("PA_APPLY_VARIANT");
   return e != nullptr && strcmp(e, "generic") == 0;
+}
+static bool apply_use_direct2d(bool eligible) {
+  const char* e = getenv("PA_APPLY_VARIANT");
+  if (e != nullptr && (strcmp(e, "tma") == 0 || strcmp(e, "generic") == 0)) return false;
+  return eligible;
 }
 
 static inline dim3 shell_grid(const GridDev& g) {
@@ -1224,7 +1251,10 @@ static int apply_impl(const pa_grid* pg, const pa_equation* peq, const T* phi, T
                       cudaStream_t s) {
   GridDev g = make_grid(*pg);
   EqDev<T> eq = make_eq<T>(*peq);
-  if (!apply_force_generic() && apply_eligible<T>(g, *peq)) {
+  if (apply_use_direct2d(direct2d_eligible<T>(g, *peq))) {
+    if (!launch_apply_direct2d<T, false>(s, g, eq, phi, out)) return fail(PA_ERR_CUDA, "k_apply_direct2d launch failed");
+    if (peq->ops[0].edge != 0) k_apply_shell<T, false><<<shell_grid(g), kBlock, 0, s>>>(g, eq, phi, out);
+  } else if (!apply_force_generic() && apply_eligible<T>(g, *peq)) {
     TilePlan tile;
     apply_tile_plan<T>(g, tile);
     if (!launch_star_tma<T, PW_APPLY>(s, g, eq, tile, phi, nullptr, out, nullptr, (T)0, nullptr, nullptr, ST_NONE))
@@ -1311,7 +1341,10 @@ static int grad_impl(const pa_grid* pg, const pa_op* op, const T* phi, T* out, c
   e.nops = 1;
   e.ops[0] = *op;
   EqDev<T> eq = make_eq<T>(e);
-  if (!apply_force_generic() && apply_eligible<T>(g, e)) {  // PW_GRAD, 1 + d words per cell
+  if (apply_use_direct2d(direct2d_eligible<T>(g, e))) {
+    if (!launch_apply_direct2d<T, true>(s, g, eq, phi, out)) return fail(PA_ERR_CUDA, "k_apply_direct2d launch failed");
+    if (op->edge != 0) k_apply_shell<T, true><<<shell_grid(g), kBlock, 0, s>>>(g, eq, phi, out);
+  } else if (!apply_force_generic() && apply_eligible<T>(g, e)) {  // PW_GRAD, 1 + d words per cell
     TilePlan tile;
     apply_tile_plan<T>(g, tile);
     if (!launch_star_grad<T>(s, g, eq, tile, phi, out))

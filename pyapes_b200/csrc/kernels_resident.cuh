@@ -1080,6 +1080,98 @@ inline bool res_eq_ok(const pa_equation& eq) {
   return true;
 }
 
+// =========================================================================================
+// Explicit operators on small / medium 2-D grids: one thread per 16-byte vector, neighbours straight from global
+// memory.  The TMA star engine walks a 2-D grid row by row through a producer / consumer pipeline; a single
+// application of an operator on 1024^2 then costs ~10 us of pipeline latency for 3 us of traffic (0.25 of the
+// roofline, launch- and latency-bound).  Here there is no pipeline to fill: 512 K independent threads, every row is
+// read three times but from L1 / L2.  Same semantics as PW_APPLY / PW_GRAD: defined on EVERY cell with torch.roll's
+// wrap-around on both axes (fdc.py:171-200), class-indexed coefficients next to the walls, same operation order.
+// =========================================================================================
+template <typename T, int NOPS, bool GRAD>
+__global__ void __launch_bounds__(256)
+k_apply_direct2d(GridDev g, EqDev<T> eq, const T* __restrict__ phi, T* __restrict__ out) {
+  constexpr int VEC = VecOf<T>::N;
+  const int n0 = g.n[0], n2 = g.n[2], nv = n2 / VEC;
+  const ResScales<T, NOPS> scs(eq);
+  const int total = n0 * nv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i / nv, col = (i - row * nv) * VEC;
+    const int rm = row == 0 ? n0 - 1 : row - 1, rp = row == n0 - 1 ? 0 : row + 1;
+    const T* p = phi + row * n2 + col;
+    T v0[VEC], vm[VEC], vp[VEC];
+    lds_vec<T>(p, v0);
+    lds_vec<T>(phi + rm * n2 + col, vm);
+    lds_vec<T>(phi + rp * n2 + col, vp);
+    const T zl = col > 0 ? p[-1] : phi[row * n2 + n2 - 1];
+    const T zr = col + VEC < n2 ? p[VEC] : phi[row * n2];
+    const int clx = coef_class(g, 0, row);
+    const bool lean = clx == 0 && col >= 2 && col + VEC <= n2 - 2;
+    T o0[VEC], o2[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
+      const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
+      if (GRAD) {
+        // central gradient, one output array per mesh axis (fdc.py:80-87), op order of k_grad / PW_GRAD
+        const OpDev<T>& o = eq.op[0];
+        const int cz = lean ? 0 : coef_class(g, 2, col + e);
+        T s = o.coef[0][clx][0] * vp[e];
+        s = s + o.coef[0][clx][1] * v0[e];
+        s = s + o.coef[0][clx][2] * vm[e];
+        if (o.has_param) s = s * o.param;
+        o0[e] = s;
+        s = o.coef[2][cz][0] * zp;
+        s = s + o.coef[2][cz][1] * v0[e];
+        s = s + o.coef[2][cz][2] * zm;
+        if (o.has_param) s = s * o.param;
+        o2[e] = s;
+      } else if (lean) {
+        o0[e] = res_star<T, true, NOPS, false>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+      } else {
+        o0[e] = res_star<T, false, NOPS, false>(eq, scs, clx, coef_class(g, 2, col + e), v0[e], vp[e], vm[e], zp, zm);
+      }
+    }
+    typedef typename VecOf<T>::type V;
+    V q;
+    T* qs = reinterpret_cast<T*>(&q);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) qs[e] = o0[e];
+    __stcs(reinterpret_cast<V*>(out + row * n2 + col), q);
+    if (GRAD) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) qs[e] = o2[e];
+      __stcs(reinterpret_cast<V*>(out + total * VEC + row * n2 + col), q);
+    }
+  }
+}
+
+// 2-D meshes up to kDirect2dCells cells (32-bit offsets; beyond, the TMA engine's streaming wins anyway)
+constexpr long long kDirect2dCells = 1LL << 23;
+template <typename T>
+inline bool direct2d_eligible(const GridDev& g, const pa_equation& eq) {
+  constexpr int VEC = VecOf<T>::N;
+  if (!g.act[0] || g.act[1] || !g.act[2]) return false;
+  if (g.n[2] % VEC != 0 || g.n[2] < 2 * VEC || g.n[0] < 3) return false;
+  if (g.cells > kDirect2dCells) return false;
+  return res_eq_ok<T>(eq);
+}
+template <typename T, bool GRAD>
+bool launch_apply_direct2d(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, const T* phi, T* out) {
+  const long long vecs = g.cells / VecOf<T>::N;
+  long long blocks = (vecs + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (GRAD)
+    k_apply_direct2d<T, 1, true><<<(int)blocks, 256, 0, s>>>(g, eq, phi, out);
+  else if (eq.nops == 1)
+    k_apply_direct2d<T, 1, false><<<(int)blocks, 256, 0, s>>>(g, eq, phi, out);
+  else if (eq.nops == 2)
+    k_apply_direct2d<T, 2, false><<<(int)blocks, 256, 0, s>>>(g, eq, phi, out);
+  else
+    k_apply_direct2d<T, 0, false><<<(int)blocks, 256, 0, s>>>(g, eq, phi, out);
+  return cudaGetLastError() == cudaSuccess;
+}
+
 // the three coefficient classes of every operator hold the same numbers on both axes of the 2-D grid (no Neumann /
 // Symmetry face; compared bit for bit, like TmaPlan::coef_uniform)
 inline bool res_coef_uniform(const pa_equation& eq) {

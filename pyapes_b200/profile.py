@@ -51,7 +51,7 @@ def cg_kernel_times(n, iters: int = 20, variant: int = 0, dtype: str = "double",
             "kernels": names, "share": {"phaseA": a / tot, "phaseB": b / tot, "bc+shell": c / tot}}
 
 
-def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", reps: int = 20, variant: str = "tma",
+def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", reps: int = 20, variant: str = "auto",
                          kinds=None, vals=None, device: str = "cuda") -> dict:
     """Device time of ONE explicit operator application (`pa_stencil_apply` / `pa_grad_apply` through the C
     ABI, exactly what `Solver.Aop` / `FDC().laplacian/.grad/.div` call), CUDA events on the launching stream
@@ -106,9 +106,11 @@ def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", re
         def call(i):
             N.check(lib.pa_stencil_apply(grid, eq, code, ins[i].data_ptr(), outs[i].data_ptr(), stream))
 
+    # "auto": the library's choice (direct 2-D kernel up to 8 M cells, TMA star engine elsewhere); "tma" / "generic":
+    # forced paths (PA_APPLY_VARIANT, read per call)
     prev = os.environ.get("PA_APPLY_VARIANT")
-    if variant == "generic":
-        os.environ["PA_APPLY_VARIANT"] = "generic"
+    if variant in ("generic", "tma"):
+        os.environ["PA_APPLY_VARIANT"] = variant
     else:
         os.environ.pop("PA_APPLY_VARIANT", None)
     try:

@@ -25,9 +25,9 @@ class _variant:
 
     def __enter__(self):
         self.prev = os.environ.get("PA_APPLY_VARIANT")
-        if self.name == "generic":
-            os.environ["PA_APPLY_VARIANT"] = "generic"
-        else:
+        if self.name in ("generic", "tma"):  # forced paths
+            os.environ["PA_APPLY_VARIANT"] = self.name
+        else:  # "auto": the direct 2-D kernel on 2-D grids up to 8 M cells, the TMA engine elsewhere
             os.environ.pop("PA_APPLY_VARIANT", None)
 
     def __exit__(self, *a):
@@ -37,7 +37,7 @@ class _variant:
             os.environ["PA_APPLY_VARIANT"] = self.prev
 
 
-@pytest.mark.parametrize("variant", ["tma", "generic"])
+@pytest.mark.parametrize("variant", ["tma", "generic", "auto"])
 @pytest.mark.parametrize("case", TILES, ids=[c["name"] for c in TILES])
 def test_tile_fixtures_bit_exact(case, variant):
     mesh, var = U.product_field(case, DEV)
@@ -120,4 +120,9 @@ def test_tma_equals_generic_at_baseline_sizes(nx, dtype):
     for key in b:
         assert torch.equal(a[key], b[key]), f"{key}: max|d|={(a[key] - b[key]).abs().max().item():.3e}"
         del a[key]
+    if nd == 2:  # the direct 2-D kernel (auto picks it up to 8 M cells)
+        with _variant("auto"):
+            c = U.product_tile_outputs(case, var)
+        for key in b:
+            assert torch.equal(c[key], b[key]), f"direct {key}: max|d|={(c[key] - b[key]).abs().max().item():.3e}"
     assert torch.isfinite(b["lap"]).all()

@@ -18,7 +18,7 @@ if quick:
     shapes = shapes[1:3]
 for shape, dt in shapes:
     for op in ("laplacian", "grad", "div_upwind", "advdiff"):
-        for variant in ("tma", "generic"):
+        for variant in (("auto", "tma", "generic") if len(shape) == 2 else ("tma", "generic")):
             r = P.operator_apply_times(shape, op, dt, reps=10 if len(shape) == 3 and shape[0] >= 512 else 30,
                                        variant=variant)
             r["hbm_frac"] = round(r["GB/s"] / HBM, 3)
