@@ -61,6 +61,8 @@ PA_EXTERN_APPLY(float)
                                                 T*, T*, const T*, T, int);                                         \
   extern template bool launch_apply_direct2d<T, false>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*); \
   extern template bool launch_apply_direct2d<T, true>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*);  \
+  extern template bool launch_jacobi_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&,  \
+                                                 T*, T*, const T*, SolverState*, int);                               \
   extern template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*,      \
                                              const T*, SolverState*, int, int);
 PA_EXTERN_RES(double)
@@ -347,10 +349,8 @@ static int method_nvec(int method) {
 
 // Mailbox for polling the device-side state: MAPPED pinned memory that a one-thread kernel writes straight from the
 // device.  (It used to be a 200-byte cudaMemcpyAsync: a device-to-host copy queues on the copy engine behind whatever
-// bulk download the caller has in flight on another stream -- in the end-to-end loop of bench.py the solution of the
-// previous step, 129 ms per GiB with eight ranks sharing the host link -- and every poll of the solver then idled the
-// GPU until that download had finished: 383 instead of 307 ms per solve at N = 8, e2e 0.78 of the device-resident
-// value.  A kernel's stores do not go through a copy engine.)
+// bulk download the caller has in flight on another stream, and a solver that polls every 32 iterations then idles
+// the GPU until that download has finished.  A kernel's stores do not go through a copy engine.)
 static SolverState* host_mailbox() {
   static SolverState* p = nullptr;
   if (!p) {
@@ -1055,6 +1055,25 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       return PA_OK;
     }
     if (cfg->variant == 3) return fail(PA_ERR_UNSUPPORTED, "cooperative launch is not available on this device");
+  }
+
+  // Jacobi on a 2-D grid that fits the SMs' shared memory: the whole solve as ONE cooperative launch
+  // (kernels_resident.cuh k_jacobi_resident: uniform coefficients, every face Dirichlet).  variant 6 or auto.
+  if (method == PA_METHOD_JACOBI && !dist && !nonlinear && pw_ok && tma_flat(g) && static_shell(nfaces, faces) &&
+      (cfg->variant == 6 || (cfg->variant == 0 && getenv("PA_NO_RESIDENT") == nullptr))) {
+    PA_CUDA(cudaMemcpyAsync(x_alt, x, vbytes, cudaMemcpyDeviceToDevice, stream));  // the static shell
+    if (launch_jacobi_resident<T>(stream, g, *peq, eq, x, x_alt, rhs, w.st, cfg->max_it)) {
+      L.count += 2;
+      SolverState* hs = nullptr;
+      int rcp = poll_state(stream, w.st, &hs);
+      if (rcp != PA_OK) return rcp;
+      PA_CUDA(cudaGetLastError());
+      if (!hs->done) return fail(PA_ERR_CUDA, "resident Jacobi kernel returned without latching `done`");
+      fill_report(rep, hs, L.count);
+      set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
+      return PA_OK;
+    }
+    cudaGetLastError();
   }
 
   // fused TMA CG kernels with an implicit-Euler term: operator 0 + diagonal shift (plan_tma)

@@ -964,6 +964,119 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = ls;
 }
 
+// =========================================================================================
+// Jacobi, the whole solve (uniform-coefficient fast path only; the host falls back to the streaming sweeps otherwise).
+// x lives in two resident buffers like the Euler field; a sweep is an Euler-like pass
+//     x_new = x + (rhs - A(x)) / diag     on the region            (oracle jacobi)
+// followed by ONE all-reduce of |x_new - x|^2 and the scalar stage ST_JA_FIN in every CTA.  x_new is streamed to the
+// global ping-pong buffers every sweep (the loser is VARo).  The quotient is div_rcp, the streaming sweep's: the
+// correctly rounded one.  Sequence numbers: rows of sweep k carry seq0 + k + 1, the all-reduce of sweep k the same.
+// =========================================================================================
+template <typename T, int NOPS>
+__global__ void __launch_bounds__(kResThreads, 1)
+k_jacobi_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb, const T* __restrict__ rhs,
+                  SolverState* st, int R, typename LLOf<T>::line* llbase, uint4* inbox, unsigned seq0) {
+  constexpr int VEC = VecOf<T>::N;
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ SolverState ls;
+  __shared__ double red[32];
+  __shared__ double bc[1];
+  unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  ResCtx c;
+  res_ctx_init<T>(c, g, R);
+  const ResLL<T> ll{llbase, c.n2, (int)gridDim.x};
+  const int rowlen = c.n2;
+  T* const sb0 = reinterpret_cast<T*>(base) + rowlen;
+  T* const sb1 = sb0 + (R + 2) * rowlen;
+  if (threadIdx.x == 0) ls = *st;
+  for (int i = threadIdx.x; i < (c.rows + 2) * c.nv; i += kResThreads) {
+    const int lr = i / c.nv - 1, cv = i - (lr + 1) * c.nv;
+    T v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = (T)0;
+    sts_vec<T>(sb1 + lr * rowlen + cv * VEC, v);
+    if (lr >= 0 && lr < c.rows) ldcg_vec<T>(xa + (c.row0 + lr) * rowlen + cv * VEC, v);
+    sts_vec<T>(sb0 + lr * rowlen + cv * VEC, v);
+  }
+  __syncthreads();
+
+  const ResScales<T, NOPS> scs(eq);
+  const ResFast fast = res_fast_init<T>(c, g, true);  // (the host launches this kernel for uniform coefficients only)
+  const int fsplit = fast.ta + ((fast.tb - fast.ta) * 2) / 5;
+  const T dgl = star_diag<T, KFlat, NOPS>(eq, 0, 0, 0);
+  const T rcl = (T)1 / dgl;
+  const bool den_ok = exp_window(dgl, -DivWin<T>::DEN, DivWin<T>::DEN);
+  unsigned s = 0;
+  while (!ls.done) {
+    T* cur = (s & 1u) ? sb1 : sb0;
+    T* nxt = (s & 1u) ? sb0 : sb1;
+    T* gout = ((s + 1u) & 1u) ? xb : xa;
+    const unsigned seq_in = s == 0u ? 0u : seq0 + s, seq_out = seq0 + s + 1u;
+    double qs[1] = {0.0};
+    unsigned got = 0u;
+    if (fast.boundary) {
+      int k = 0;
+      for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+        if (blockIdx.x > 0 && res_halo_get<T>(c, ll, cur, cv * VEC, 0, s, seq_in, xa, false)) got |= 1u << (2 * k);
+        if (blockIdx.x + 1 < gridDim.x && res_halo_get<T>(c, ll, cur, cv * VEC, 1, s, seq_in, xa, false))
+          got |= 2u << (2 * k);
+      }
+    }
+    auto cell = [&](const T (&v0)[VEC], const T (&vm)[VEC], const T (&vp)[VEC], T zl, T zr, int row, int col,
+                    unsigned cm, bool rin, T (&o)[VEC]) {
+      typedef typename VecOf<T>::type V;
+      V q = __ldg(reinterpret_cast<const V*>(rhs + (c.row0 + row) * rowlen + col));
+      const T* av = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T zp = (e == VEC - 1) ? zr : v0[e + 1 < VEC ? e + 1 : e];
+        const T zm = (e == 0) ? zl : v0[e > 0 ? e - 1 : 0];
+        const T a = res_star<T, true, NOPS>(eq, scs, 0, 0, v0[e], vp[e], vm[e], zp, zm);
+        const T res = av[e] - a;
+        const bool in = rin && ((cm >> e) & 1u);
+        T xn = v0[e];
+        if (in) {
+          xn = v0[e] + div_rcp<T>(res, dgl, rcl, den_ok);
+          const T df = xn - v0[e];  // (every face Dirichlet: the region is the grid minus its shell)
+          const T q2 = df * df;
+          qs[0] += (double)q2;
+        }
+        o[e] = xn;
+      }
+    };
+    auto put = [&](int row, int col, const T (&o)[VEC]) {
+      sts_vec<T>(nxt + row * rowlen + col, o);
+      sts_vec<T>(gout + (c.row0 + row) * rowlen + col, o);
+    };
+    auto put_boundary = [&](int row, int col, const T (&o)[VEC]) {
+      put(row, col, o);
+      res_send<T>(c, ll, row, col, s + 1u, seq_out, o);
+    };
+    for (int seg = 0; seg < 2; ++seg) {
+      res_fast_march<T>(c, fast, g, cur, seg == 0 ? fast.ta : fsplit, seg == 0 ? fsplit : fast.tb, cell, put);
+      if (seg == 0 && fast.boundary) {
+        int k = 0;
+        for (int cv = fast.cv; cv < c.nv; cv += fast.cstep, ++k) {
+          const int col = cv * VEC;
+          if (blockIdx.x > 0 && !((got >> (2 * k)) & 1u)) res_halo_get<T>(c, ll, cur, col, 0, s, seq_in, xa, true);
+          if (blockIdx.x + 1 < gridDim.x && !((got >> (2 * k + 1)) & 1u))
+            res_halo_get<T>(c, ll, cur, col, 1, s, seq_in, xa, true);
+          res_fast_boundary<T>(c, g, cur, col, cell, put_boundary);
+        }
+      }
+    }
+    res_allsum<1>(qs, inbox, s + 1u, seq_out, red, bc);
+    if (threadIdx.x == 0) {
+      ls.sum[R_B] = qs[0];
+      ls.sum[R_SHELL] = 0.0;  // static shell
+      finalize_stage<T>(ST_JA_FIN, &ls);
+    }
+    __syncthreads();
+    ++s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st = ls;
+}
+
 // ---- host ------------------------------------------------------------------------------------
 struct ResPlan {
   int ctas, R;
@@ -1264,6 +1377,50 @@ bool launch_cg_resident(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, T*
   res_debug_print("cg iteration 8: d update+barrier | d.A(d) | all-reduce | alpha | x,r update | all-reduce | beta", dbg,
                   8, s);
   return true;
+}
+
+// the whole Jacobi solve in one launch: 2-D mesh, every face Dirichlet, uniform coefficients, a thread mapping with
+// fixed columns (row length a multiple or a divisor of 512 vectors); false: not launched (streaming sweeps instead)
+template <typename T, int NOPS>
+static bool launch_jacobi_resident_n(cudaStream_t s, const ResPlan& p, const GridDev& g, const EqDev<T>& eq, T* xa, T* xb,
+                                     const T* rhs, SolverState* st, int max_it) {
+  if (cudaFuncSetAttribute(k_jacobi_resident<T, NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
+  unsigned seq0 = 0;
+  if (!buf || !res_take_seq(*buf, (unsigned)max_it + 4u, s, &seq0)) return false;
+  uint4* inbox = (uint4*)buf->ptr;
+  typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
+  int R = p.R;
+  GridDev gg = g;
+  EqDev<T> e = eq;
+  void* args[] = {(void*)&gg, (void*)&e, (void*)&xa, (void*)&xb, (void*)&rhs, (void*)&st, (void*)&R, (void*)&ll,
+                  (void*)&inbox, (void*)&seq0};
+  if (cudaLaunchCooperativeKernel((void*)k_jacobi_resident<T, NOPS>, dim3(p.ctas), dim3(kResThreads), args, p.smem, s) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaEventRecord(buf->last, s);
+  return true;
+}
+template <typename T>
+bool launch_jacobi_resident(cudaStream_t s, const GridDev& g, const pa_equation& peq, const EqDev<T>& eq, T* xa, T* xb,
+                            const T* rhs, SolverState* st, int max_it) {
+  ResPlan p;
+  if (max_it < 0 || max_it > 1000000000 || !res_eq_ok<T>(peq) || !res_coef_uniform(peq) || !res_plan<T>(g, false, p))
+    return false;
+  const int nv = g.n[2] / VecOf<T>::N;
+  if (nv % kResThreads != 0 && kResThreads % nv != 0) return false;  // the fast path's thread mapping (res_fast_init)
+  if (g.lo[0] > 1 || g.hi[0] < g.n[0] - 1) return false;
+  const char* ev = getenv("PA_RES_PATH");
+  if (ev != nullptr && strcmp(ev, "items") == 0) return false;
+  if (eq.nops == 1) return launch_jacobi_resident_n<T, 1>(s, p, g, eq, xa, xb, rhs, st, max_it);
+  if (eq.nops == 2) return launch_jacobi_resident_n<T, 2>(s, p, g, eq, xa, xb, rhs, st, max_it);
+  return false;
 }
 
 }  // namespace pa

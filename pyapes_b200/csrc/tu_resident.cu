@@ -6,6 +6,8 @@ namespace pa {
                                          const T*, T, int);                                                         \
   template bool launch_apply_direct2d<T, false>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*);           \
   template bool launch_apply_direct2d<T, true>(cudaStream_t, const GridDev&, const EqDev<T>&, const T*, T*);            \
+  template bool launch_jacobi_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, T*, T*,   \
+                                          const T*, SolverState*, int);                                              \
   template bool launch_cg_resident<T>(cudaStream_t, const GridDev&, const EqDev<T>&, T*, T*, const T*, const T*, SolverState*, int, int);
 PA_INST(double)
 PA_INST(float)

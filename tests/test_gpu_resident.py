@@ -174,3 +174,58 @@ def test_cg_resident_fp32_and_auto():
     d, rep_d, _ = _cg_run([512, 512], 6, 30)
     assert c._last_launches == d._last_launches
     assert torch.equal(c(), d())
+
+
+def _jacobi_run(shape, variant, max_it, tol=1e-300, dtype="double", seed=77):
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    nd = len(shape)
+    mesh = Mesh(Box([0.0] * nd, [1.0] * nd), None, shape, DEV, dtype)
+    vals = [0.0, 0.5, -1.0, 2.0][: 2 * nd]
+    var = Field("p", 1, mesh, {"domain": mixed_bcs(vals, ["dirichlet"] * (2 * nd)), "obstacle": None})
+    g = torch.Generator().manual_seed(seed)
+    rhs = (torch.rand(1, *shape, generator=g, dtype=torch.float64) - 0.5).to(var().dtype)
+    s = Solver({"fdm": {"method": "jacobi", "tol": tol, "max_it": max_it, "report": False, "variant": variant}})
+    s.set_eq(FDM().laplacian(1.0, var) == rhs.to(DEV))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rep = s.solve()
+    torch.set_default_dtype(torch.float64)
+    return var, rep, vals, rhs
+
+
+@pytest.mark.parametrize("shape,sweeps", [([64, 64], 9), ([150, 128], 6), ([300, 1024], 5), ([1024, 1024], 12),
+                                          ([7, 16], 4), ([449, 512], 7)])
+def test_jacobi_resident_vs_oracle_and_stream(shape, sweeps):
+    """The resident Jacobi solve (one cooperative launch) against the oracle -- bit-identical iterate after a fixed
+    number of sweeps, same sweep count -- and against the streaming sweeps (variant 4) incl. the previous iterate."""
+    a, rep_a, vals, rhs = _jacobi_run(shape, 6, sweeps - 1)
+    b, rep_b, _, _ = _jacobi_run(shape, 4, sweeps - 1)
+    assert rep_a["itr"] == rep_b["itr"] == sweeps, (rep_a, rep_b)
+    assert a._last_launches < b._last_launches  # one launch instead of one per sweep
+    assert torch.equal(a(), b())
+    assert torch.equal(a.VARo, b.VARo)
+    assert abs(rep_a["tol"] - rep_b["tol"]) <= 1e-12 * max(1.0, abs(rep_b["tol"]))
+    if shape[0] * shape[1] <= 200000:
+        nd = len(shape)
+        xs, dx = O.make_axes([0.0] * nd, [1.0] * nd, shape)
+        bcs = [O.FaceBC(f, "dirichlet", v) for f, v in zip(O.FACES[: 2 * nd], vals)]
+        x0 = torch.zeros(1, *shape, dtype=torch.float64)
+        eq = O.Equation([O.Term("laplacian", 1.0, 1.0)], dx, xs, bcs).build(x0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sol, rep_o, _ = O.jacobi(eq, x0, eq.adjust_rhs(x0, rhs.clone()), 1e-300, sweeps - 1)
+        assert rep_o["itr"] == sweeps
+        assert torch.equal(a().cpu(), sol), (a().cpu() - sol).abs().max().item()
+
+
+def test_jacobi_resident_converges_like_stream():
+    a, rep_a, _, _ = _jacobi_run([96, 64], 6, 20000, tol=1e-6)
+    b, rep_b, _, _ = _jacobi_run([96, 64], 4, 20000, tol=1e-6)
+    assert rep_a["converge"] and rep_a["itr"] == rep_b["itr"], (rep_a, rep_b)
+    assert torch.equal(a(), b())
