@@ -229,3 +229,45 @@ def test_jacobi_resident_converges_like_stream():
     b, rep_b, _, _ = _jacobi_run([96, 64], 4, 20000, tol=1e-6)
     assert rep_a["converge"] and rep_a["itr"] == rep_b["itr"], (rep_a, rep_b)
     assert torch.equal(a(), b())
+
+
+@pytest.mark.parametrize("method", ["cg", "jacobi"])
+def test_implicit_euler_through_resident_kernels(method):
+    """fdm.ddt + a linear-solver method = implicit Euler: (1/dt) phi' - nu lap(phi') = rhs + (1/dt) phi.  On a 2-D
+    Dirichlet grid the resident CG takes the 1/dt term as its shift (OpDev::shift), the resident Jacobi as a second
+    operator; both must reproduce the streaming kernels (variant 4) step for step."""
+    from pyapes_b200.geometry import Box
+    from pyapes_b200.mesh import Mesh
+    from pyapes_b200.solver.fdm import FDM
+    from pyapes_b200.solver.ops import Solver
+    from pyapes_b200.variables import Field
+    from pyapes_b200.variables.bcs import mixed_bcs
+
+    shape = [300, 512]
+    out = {}
+    for variant in (6, 4):
+        mesh = Mesh(Box([0.0, 0.0], [1.0, 1.0]), None, shape, DEV, "double")
+        var = Field("c", 1, mesh, {"domain": mixed_bcs([0.0, 1.0, 0.5, -0.25], ["dirichlet"] * 4), "obstacle": None})
+        g = torch.Generator().manual_seed(99)
+        var.set_var_tensor(torch.rand(1, *shape, generator=g, dtype=torch.float64).to(DEV))
+        src = torch.rand(1, *shape, generator=g, dtype=torch.float64).to(DEV)
+        nu = 0.1
+        var.set_time(5.0 * min(mesh._dx) ** 2 / nu, 0.0)
+        tol, max_it = (1e-9, 4000) if method == "cg" else (1e-300, 30)
+        solver = Solver({"fdm": {"method": method, "tol": tol, "max_it": max_it, "report": False, "n_steps": 2,
+                                 "variant": variant}})
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fdm = FDM()
+            solver.set_eq(fdm.ddt(var) - fdm.laplacian(nu, var) == src)
+            rep = solver.solve()
+        out[variant] = (rep, var().clone(), var._last_launches)
+        torch.set_default_dtype(torch.float64)
+    (ra, xa, la), (rb, xb, lb) = out[6], out[4]
+    assert ra["itr"] == rb["itr"], (ra, rb)
+    assert la < lb  # whole-solve launches
+    if method == "jacobi":
+        assert torch.equal(xa, xb)
+    else:
+        assert abs(ra["tol"] - rb["tol"]) <= 1e-10
+        assert (xa - xb).abs().max().item() <= 1e-9 * xb.abs().max().item()
