@@ -394,6 +394,12 @@ def secondary_single(hbm, sampler):
         clk = sampler.window(r["t0"], r["t1"]) if sampler is not None else None
         if clk is not None:
             out[f"{tag}_sm_mhz"] = clk
+        if tag.startswith("cfg3_euler"):
+            # the adv-diff Euler step is bound by the fp64 ISSUE rate, not by HBM: one rounding per reference operation
+            # means 41 (3-D) / 29 (2-D) non-fusable DADD / DMUL per cell; the pipe issues 64 lanes per SM and clock
+            ops = 41 if "256" in tag else 29
+            out[f"{tag}_fp64_ops_per_lup"] = ops
+            out[f"{tag}_fp64_issue_frac"] = round(r["GLUP/s"] * 1e9 * ops / (148 * 64 * 1965e6), 4)
 
     def timed(fn):
         t0 = time.time()
@@ -432,8 +438,11 @@ def secondary_single(hbm, sampler):
         torch.set_default_dtype(torch.float64)
         torch.cuda.empty_cache()
     out["note"] = ("fixed-count runs through the public API, CUDA events; hbm_frac = GLUP/s x words x element size / "
-                   "measured HBM peak; words per LUP from SURVEY.md 8d (BiCGSTAB: the canonical 17); 1024^2 cases are "
-                   "L2-resident and launch-latency bound")
+                   "measured HBM peak; words per LUP from SURVEY.md 8d (BiCGSTAB: the canonical 17); 1024^2 Euler / CG run "
+                   "as ONE cooperative launch with the field resident in the SMs' shared memory (hbm_frac is then the "
+                   "HBM-equivalent of their LUP rate); the single 1024^2 operator application is launch-latency bound; "
+                   "cfg3 fp64_issue_frac = GLUP/s x non-fusable fp64 operations per LUP / (148 SMs x 64 lanes x 1965 MHz), "
+                   "the bound of the bit-exact Euler step (ncu: fp64 pipe 67 % active at 256^3)")
     return out
 
 
