@@ -1068,6 +1068,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       int rcp = poll_state(stream, w.st, &hs);
       if (rcp != PA_OK) return rcp;
       PA_CUDA(cudaGetLastError());
+      if (res_check_abort()) return fail(PA_ERR_CUDA, "resident Jacobi kernel: a row / sum exchange timed out (watchdog)");
       if (!hs->done) return fail(PA_ERR_CUDA, "resident Jacobi kernel returned without latching `done`");
       fill_report(rep, hs, L.count);
       set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
@@ -1098,6 +1099,7 @@ static int run_solver(int method, const pa_grid* pg, const pa_equation* peq, int
       int rcp = poll_state(stream, w.st, &hs);
       if (rcp != PA_OK) return rcp;
       PA_CUDA(cudaGetLastError());
+      if (res_check_abort()) return fail(PA_ERR_CUDA, "resident CG kernel: a row / sum exchange timed out (watchdog)");
       if (!hs->done) return fail(PA_ERR_CUDA, "resident CG kernel returned without latching `done`");
       fill_report(rep, hs, L.count);
       set_swaps(rep, hs->itr + (hs->status == PA_BAD_TOL ? 1 : 0));
@@ -1726,6 +1728,8 @@ static int euler_impl(const pa_grid* pg, const pa_equation* peq, int nfaces,
       if (remaining & 1) std::swap(cur, nxt);
       done_steps = nsteps;
       remaining = 0;
+      PA_CUDA(cudaStreamSynchronize(s));
+      if (res_check_abort()) return fail(PA_ERR_CUDA, "resident Euler kernel: a row exchange timed out (watchdog)");
     }
   }
   if (remaining >= 4) {

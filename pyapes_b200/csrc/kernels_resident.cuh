@@ -76,10 +76,19 @@ __device__ __forceinline__ bool ll_try(const uint2* p, unsigned seq, float& v) {
   v = __uint_as_float(a);
   return b == seq;
 }
+// Watchdog of the waits: a line that has not arrived after kResTimeoutNs (a CTA that died, a bug) must not leave the
+// GPU spinning for ever.  The waiter raises g_res_abort, every other wait sees it within ~100 us and gives up as
+// well, the kernels leave their loops, and the host reports PA_ERR_CUDA (res_check_abort).  The word lives in the
+// translation unit that instantiates the kernels (tu_resident.cu); one resident launch runs at a time (ResBuf::last).
+constexpr unsigned long long kResTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+static __device__ unsigned int g_res_abort;
+__device__ __forceinline__ bool res_aborted() { return *(volatile unsigned int*)&g_res_abort != 0u; }
+
 // N consecutive lines: all loads are issued before the first check
 template <typename T, int N>
 __device__ __forceinline__ void ll_load(const typename LLOf<T>::line* p, unsigned seq, T (&v)[N]) {
-  unsigned ns = 32u;
+  unsigned ns = 32u, spins = 0u;
+  unsigned long long t0 = 0ull;
   while (true) {
     bool ok = true;
 #pragma unroll
@@ -89,6 +98,17 @@ __device__ __forceinline__ void ll_load(const typename LLOf<T>::line* p, unsigne
     // awaited stores have to get through
     __nanosleep(ns);
     if (ns < 256u) ns <<= 1;
+    if ((++spins & 255u) == 0u) {  // every ~65 us of waiting
+      if (res_aborted()) break;
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0ull) {
+        t0 = now;
+      } else if (now - t0 > kResTimeoutNs) {
+        *(volatile unsigned int*)&g_res_abort = 1u;
+        __threadfence();
+        break;
+      }
+    }
   }
 }
 template <typename T, int N>
@@ -528,6 +548,9 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
   const int rs = c.rows < 2 ? 1 : 1 + ((c.rows - 2) * 2) / 5;
   const int fsplit = fast.ta + ((fast.tb - fast.ta) * 2) / 5;
   for (int s = 0; s < nsteps; ++s) {
+    // (watchdog: the host reports the failure.  Looked at every 256 steps only -- the load is an L2 round trip on the
+    //  step's critical path; once the word is raised every wait gives up within ~65 us anyway)
+    if ((s & 255) == 255 && res_aborted()) break;
     T* cur = (s & 1) ? sb1 : sb0;
     T* nxt = (s & 1) ? sb0 : sb1;
     T* gout = (s & 1) ? b0 : b1;
@@ -744,6 +767,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
   unsigned epoch = 1u;
   unsigned it = 0;
   while (!ls.done) {
+    if ((it & 63u) == 63u && res_aborted()) break;  // (watchdog, every 64 iterations: see k_euler_resident)
     const unsigned seq_d = seq0 + it + 1u;
     if (dbg != nullptr && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && (it == 8u || it == 908u))
       dbg[it == 8u ? 10 : 11] = global_timer_ns();
@@ -1008,6 +1032,7 @@ k_jacobi_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb
   const bool den_ok = exp_window(dgl, -DivWin<T>::DEN, DivWin<T>::DEN);
   unsigned s = 0;
   while (!ls.done) {
+    if ((s & 63u) == 63u && res_aborted()) break;  // (watchdog, every 64 sweeps: see k_euler_resident)
     T* cur = (s & 1u) ? sb1 : sb0;
     T* nxt = (s & 1u) ? sb0 : sb1;
     T* gout = ((s + 1u) & 1u) ? xb : xa;
@@ -1099,7 +1124,10 @@ inline ResBuf* res_exchange_buffer(size_t ll_bytes, cudaStream_t s) {
   ResBuf& b = pool[current_device()];
   const size_t need = kResSlotBytes + ll_bytes;
   if (b.bytes < need) {
-    const size_t want = need > 2 * b.bytes ? need : 2 * b.bytes;
+    // first allocation: 32 MiB (covers 1024^2 fp64 with room to spare), so that a process that starts on small grids
+    // does not walk through a series of re-allocations; beyond that geometric growth
+    size_t want = need > 2 * b.bytes ? need : 2 * b.bytes;
+    if (want < ((size_t)32 << 20)) want = (size_t)32 << 20;
     if (b.ptr) cudaFree(b.ptr);  // (synchronises the device: no launch still uses it)
     b.ptr = nullptr;
     b.bytes = 0;
@@ -1121,6 +1149,18 @@ inline ResBuf* res_exchange_buffer(size_t ll_bytes, cudaStream_t s) {
   if (cudaStreamWaitEvent(s, b.last, 0) != cudaSuccess) cudaGetLastError();  // (never recorded yet: a no-op)
   return &b;
 }
+// watchdog word: cleared on the launch stream in front of every resident launch, read back after the caller's
+// synchronisation (res_check_abort; only meaningful inside the translation unit that owns g_res_abort)
+inline bool res_clear_abort(cudaStream_t s) {
+  const unsigned int zero = 0u;
+  return cudaMemcpyToSymbolAsync(g_res_abort, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, s) == cudaSuccess;
+}
+inline bool res_abort_raised() {
+  unsigned int v = 0u;
+  if (cudaMemcpyFromSymbol(&v, g_res_abort, sizeof(v), 0, cudaMemcpyDeviceToHost) != cudaSuccess) return true;
+  return v != 0u;
+}
+
 // the first of `count` fresh sequence numbers is seq0 + 1; on wrap-around the buffer is cleared on the stream
 inline bool res_take_seq(ResBuf& b, unsigned count, cudaStream_t s, unsigned* seq0) {
   if (b.next_seq > 0xffffffffu - count - 16u) {
@@ -1306,7 +1346,7 @@ static bool launch_euler_resident_n(cudaStream_t s, const ResPlan& p, const Grid
   }
   ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
   unsigned seq0 = 0;
-  if (!buf || !res_take_seq(*buf, (unsigned)nsteps + 1u, s, &seq0)) return false;
+  if (!buf || !res_take_seq(*buf, (unsigned)nsteps + 1u, s, &seq0) || !res_clear_abort(s)) return false;
   typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
   int R = p.R;
   GridDev gg = g;
@@ -1323,6 +1363,9 @@ static bool launch_euler_resident_n(cudaStream_t s, const ResPlan& p, const Grid
   res_debug_print("euler step 8: items | barrier | (3) | end of the last step", dbg, 5, s);
   return true;
 }
+
+// after the stream of a resident launch has been synchronised: true if its watchdog fired (tu_resident.cu)
+bool res_check_abort();
 
 // nsteps explicit Euler steps in one launch; false: not launched (the caller takes the streaming path)
 template <typename T>
@@ -1355,7 +1398,7 @@ bool launch_cg_resident(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, T*
   }
   ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
   unsigned seq0 = 0;
-  if (!buf || !res_take_seq(*buf, 2u * ((unsigned)max_it + 3u) + 2u, s, &seq0)) return false;
+  if (!buf || !res_take_seq(*buf, 2u * ((unsigned)max_it + 3u) + 2u, s, &seq0) || !res_clear_abort(s)) return false;
   uint4* inbox = (uint4*)buf->ptr;
   typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
   int R = p.R;
@@ -1391,7 +1434,7 @@ static bool launch_jacobi_resident_n(cudaStream_t s, const ResPlan& p, const Gri
   }
   ResBuf* buf = res_exchange_buffer(res_ll_bytes<T>(g, p), s);
   unsigned seq0 = 0;
-  if (!buf || !res_take_seq(*buf, (unsigned)max_it + 4u, s, &seq0)) return false;
+  if (!buf || !res_take_seq(*buf, (unsigned)max_it + 4u, s, &seq0) || !res_clear_abort(s)) return false;
   uint4* inbox = (uint4*)buf->ptr;
   typename LLOf<T>::line* ll = (typename LLOf<T>::line*)((char*)buf->ptr + kResSlotBytes);
   int R = p.R;

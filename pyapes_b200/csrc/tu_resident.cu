@@ -1,6 +1,7 @@
 // Translation unit: shared-memory-resident kernels for 2-D grids (explicit Euler, whole-solve CG)
 #include "kernels_resident.cuh"
 namespace pa {
+bool res_check_abort() { return res_abort_raised(); }
 #define PA_INST(T)                                                                                                  \
   template bool launch_euler_resident<T>(cudaStream_t, const GridDev&, const pa_equation&, const EqDev<T>&, T*, T*, \
                                          const T*, T, int);                                                         \
