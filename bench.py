@@ -412,13 +412,13 @@ def secondary_single(hbm, sampler):
     MIX = P.MIXED_BCS
     cases = [
         ("cfg2_cg_256", lambda: P.solver_throughput([256] * 3, "cg", 200, *D6, reps=3)),
-        ("cfg3_euler_1024sq_upwind", lambda: P.euler_throughput([1024, 1024], "upwind", 2000)),
-        ("cfg3_euler_1024sq_upwind_fd", lambda: P.euler_throughput([1024, 1024], "upwind_fd", 2000)),
+        ("cfg3_euler_1024sq_upwind", lambda: P.euler_throughput([1024, 1024], "upwind", 2000, warm=3)),
+        ("cfg3_euler_1024sq_upwind_fd", lambda: P.euler_throughput([1024, 1024], "upwind_fd", 2000, warm=3)),
         ("cfg3_euler_256_upwind", lambda: P.euler_throughput([256] * 3, "upwind", 400)),
         ("cfg3_euler_256_upwind_fd", lambda: P.euler_throughput([256] * 3, "upwind_fd", 400)),
         ("cfg4_bicgstab_512_mixed", lambda: P.solver_throughput([512] * 3, "bicgstab", 100, *MIX)),
         ("cfg4_jacobi_512_mixed", lambda: P.solver_throughput([512] * 3, "jacobi", 100, *MIX)),
-        ("cg_1024sq", lambda: P.solver_throughput([1024, 1024], "cg", 1000, *D4)),
+        ("cg_1024sq", lambda: P.solver_throughput([1024, 1024], "cg", 1000, *D4, warm=3)),
         ("cg_512_fp32", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, dtype="single", reps=3)),
         # opt-in FMA contraction (PA_FLAG_CONTRACT): the headline solve with ~40 % fewer fp64 instructions
         ("cg_512_contract", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, reps=3, contract=True)),

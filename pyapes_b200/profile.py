@@ -142,9 +142,11 @@ def operator_apply_times(shape, op: str = "laplacian", dtype: str = "double", re
 MIXED_BCS = (["periodic", "periodic", "neumann", "symmetry", "dirichlet", "dirichlet"], [None, None, 0.5, None, 0.0, 0.0])
 
 
-def _event_time(fn, reps: int = 1) -> float:
-    """Device ms of `reps` calls of fn after one warm-up call (CUDA events, current stream)."""
-    fn()
+def _event_time(fn, reps: int = 1, warm: int = 1) -> float:
+    """Device ms of `reps` calls of fn after `warm` warm-up calls (CUDA events, current stream).  Solves that last only
+    a few ms take warm > 1: a launch that starts on an idle-clocked GPU is over before the clocks are up."""
+    for _ in range(max(1, warm)):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -156,7 +158,7 @@ def _event_time(fn, reps: int = 1) -> float:
 
 
 def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dtype: str = "double", variant: int = 0,
-                      device: str = "cuda", reps: int = 1, contract: bool = False) -> dict:
+                      device: str = "cuda", reps: int = 1, contract: bool = False, warm: int = 1) -> dict:
     """Fixed-count solve (tol 1e-300) of the Poisson problem through the public API; GLUP/s = cells x
     iterations / device time of solver.solve().  words per LUP: SURVEY.md §8d (CG 8, BiCGSTAB 17 canonical,
     Jacobi 3)."""
@@ -193,7 +195,7 @@ def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dty
         assert rep["itr"] == iters, rep
         launches[0] = getattr(var, "_last_launches", 0)
 
-    ms = _event_time(run, reps)
+    ms = _event_time(run, reps, warm)
     torch.set_default_dtype(torch.float64)
     cells = 1
     for v in shape:
@@ -205,7 +207,7 @@ def solver_throughput(shape, method: str, iters: int, kinds=None, vals=None, dty
             "words_per_lup": words, "GB/s": glups * words * esz, "launches": launches[0]}
 
 
-def euler_throughput(shape, limiter: str, steps: int, dtype: str = "double", device: str = "cuda") -> dict:
+def euler_throughput(shape, limiter: str, steps: int, dtype: str = "double", device: str = "cuda", warm: int = 1) -> dict:
     """Config 3: explicit Euler steps of the advection-diffusion equation ddt + div(u phi) - nu lap(phi) = 0,
     u = 1, nu = 0.1, Dirichlet 0, phi0 = rand(seed 1234); 2 words per LUP (R phi, W phi_new)."""
     from pyapes_b200.geometry import Box
@@ -228,7 +230,7 @@ def euler_throughput(shape, limiter: str, steps: int, dtype: str = "double", dev
     fdm = FDM({"div": {"limiter": limiter, "edge": False}})
     s = Solver({"fdm": {"method": "euler", "tol": 0.0, "max_it": 0, "report": False, "n_steps": steps}})
     s.set_eq(fdm.ddt(var) + fdm.div(u, var) - fdm.laplacian(nu, var) == 0.0)
-    ms = _event_time(lambda: s.solve(), 1)
+    ms = _event_time(lambda: s.solve(), 1, warm)
     torch.set_default_dtype(torch.float64)
     cells = 1
     for v in shape:
