@@ -419,7 +419,7 @@ def secondary_single(hbm, sampler):
         ("cfg4_bicgstab_512_mixed", lambda: P.solver_throughput([512] * 3, "bicgstab", 100, *MIX)),
         ("cfg4_jacobi_512_mixed", lambda: P.solver_throughput([512] * 3, "jacobi", 100, *MIX)),
         ("cg_1024sq", lambda: P.solver_throughput([1024, 1024], "cg", 1000, *D4, warm=3)),
-        ("cg_512_fp32", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, dtype="single", reps=3)),
+        ("cg_512_fp32", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, dtype="single", reps=3, warm=2)),
         # opt-in FMA contraction (PA_FLAG_CONTRACT): the headline solve with ~40 % fewer fp64 instructions
         ("cg_512_contract", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, reps=3, contract=True)),
         ("cg_512_exact_same_run", lambda: P.solver_throughput([512] * 3, "cg", 200, *D6, reps=3)),
