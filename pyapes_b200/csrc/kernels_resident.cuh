@@ -723,8 +723,7 @@ template <typename T>
 __global__ void __launch_bounds__(kResThreads, 1)
 k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
               T* __restrict__ xb, const T* __restrict__ r_in, const T* __restrict__ d_in, SolverState* st, int R,
-              typename LLOf<T>::line* llbase, uint4* inbox, unsigned seq0, int uni, unsigned long long* dbg,
-              int dbg_flags) {
+              typename LLOf<T>::line* llbase, uint4* inbox, unsigned seq0, int uni, unsigned long long* dbg) {
   constexpr int VEC = VecOf<T>::N;
   auto stamp = [&](unsigned i, int k) {
     if (dbg != nullptr && i == 8u && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) dbg[k] = global_timer_ns();
@@ -940,7 +939,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
         }
       sts_vec<T>(rp, rv);
       sts_vec<T>(xp, xv);
-      if (!(dbg_flags & 1)) sts_vec<T>(gxn + grow * rowlen + col, xv);  // (PA_RES_DEBUG_FLAGS=1: timing experiment)
+      sts_vec<T>(gxn + grow * rowlen + col, xv);
     };
     if (fast.on) {
       auto upd_put = [&](int row, int col, const T (&ad)[VEC]) {
@@ -1407,10 +1406,8 @@ bool launch_cg_resident(cudaStream_t s, const GridDev& g, const EqDev<T>& eq, T*
   unsigned long long* dbg = res_debug_buffer();
   const char* ev = getenv("PA_RES_PATH");  // "items": keep the general item loop (A/B runs, tests)
   if (ev != nullptr && strcmp(ev, "items") == 0) uni = 0;
-  const char* df = getenv("PA_RES_DEBUG_FLAGS");
-  int dbg_flags = df ? atoi(df) : 0;
   void* args[] = {(void*)&gg, (void*)&e, (void*)&xa, (void*)&xb, (void*)&r, (void*)&d, (void*)&st, (void*)&R,
-                  (void*)&ll, (void*)&inbox, (void*)&seq0, (void*)&uni, (void*)&dbg, (void*)&dbg_flags};
+                  (void*)&ll, (void*)&inbox, (void*)&seq0, (void*)&uni, (void*)&dbg};
   if (cudaLaunchCooperativeKernel((void*)k_cg_resident<T>, dim3(p.ctas), dim3(kResThreads), args, p.smem, s) !=
       cudaSuccess) {
     cudaGetLastError();

@@ -33,9 +33,6 @@ cg([1000, 1024], "143 CTAs")
 cg([888, 1024], "R=6, 148 CTAs")
 cg([1024, 512], "half rows")
 cg([512, 512], "512^2")
-os.environ["PA_RES_DEBUG_FLAGS"] = "1"
-cg([1024, 1024], "no x stores")
-os.environ.pop("PA_RES_DEBUG_FLAGS")
 os.environ["PA_RES_PATH"] = "items"
 cg([1024, 1024], "item loop")
 os.environ.pop("PA_RES_PATH")
