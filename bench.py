@@ -411,7 +411,7 @@ def secondary_single(hbm, sampler):
     D4, D6 = (["dirichlet"] * 4, [0.0] * 4), (["dirichlet"] * 6, [0.0] * 6)
     MIX = P.MIXED_BCS
     cases = [
-        ("cfg2_cg_256", lambda: P.solver_throughput([256] * 3, "cg", 200, *D6, reps=3)),
+        ("cfg2_cg_256", lambda: P.solver_throughput([256] * 3, "cg", 200, *D6, reps=3, warm=3)),  # (first case after the CPU leg: clocks)
         ("cfg3_euler_1024sq_upwind", lambda: P.euler_throughput([1024, 1024], "upwind", 2000, warm=3)),
         ("cfg3_euler_1024sq_upwind_fd", lambda: P.euler_throughput([1024, 1024], "upwind_fd", 2000, warm=3)),
         ("cfg3_euler_256_upwind", lambda: P.euler_throughput([256] * 3, "upwind", 400)),
