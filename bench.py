@@ -57,10 +57,11 @@ def peaks():
 
 
 def kernel_source_hash():
-    """Content hash of the CUDA sources + header the library is built from (the same one the build uses)."""
+    """Content hash of the sources the headline CG kernels are compiled from (kernels_tma.cuh, what it includes, their
+    translation units, the nvcc flags)."""
     import __graft_entry__ as G
 
-    return G._source_hash()
+    return G._cg_kernel_hash()
 
 
 def ncu_traffic(key):

@@ -1,6 +1,7 @@
 """Write profiles/ncu_traffic.json from an `ncu --set full` capture of the headline kernels: per-launch
 dram__bytes_read.sum + dram__bytes_write.sum of CG phase B / phase A, stamped with the content hash of the
-kernel sources the capture was taken on (bench.py refuses a figure whose hash is not the current one).
+sources those kernels are compiled from (__graft_entry__._cg_kernel_hash: kernels_tma.cuh, what it includes, the two
+translation units, the nvcc flags); bench.py refuses a figure whose hash is not the current one.
 usage: python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep <n> [label]"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +25,7 @@ for r in rows[2:]:
     for tag, pat in (("phaseB", "k_cg_phaseB_tma"), ("phaseA", "k_cg_phaseA_tma")):
         if pat in r[ik]:
             acc.setdefault(tag, []).append((to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]), float(r[it].replace(",", ""))))
-out = {"source_hash": G._source_hash(), "capture": label, "how": "ncu --set full --clock-control none; mean over the captured launches"}
+out = {"source_hash": G._cg_kernel_hash(), "capture": label, "how": "ncu --set full --clock-control none; mean over the captured launches"}
 for tag, v in acc.items():
     out[f"{tag}_{n}"] = int(sum(b for b, _ in v) / len(v))
     out[f"{tag}_{n}_launches"] = len(v)
