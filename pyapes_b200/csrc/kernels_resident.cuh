@@ -427,7 +427,8 @@ __device__ __forceinline__ unsigned res_col_mask(const GridDev& g, int col) {
 }
 // rows [ra, rb) of the thread's column blocks, two rows per trip (both rows are computed before either is stored:
 // the compiler must assume that `cur` and `nxt` alias):
-//   cell(v0, vm, vp, zl, zr, local row, col, column mask, row inside the region) -> o,   put(row, col, o)
+//   cell(v0, vm, vp, zl, zr, local row, col, column mask, row inside the region) -> o,   put(row, col, o, mask)
+//   (mask = the vector's region cells: the column mask, or 0 for a row outside the region)
 // (interior rows of a CTA are region rows: res_fast_init)
 template <typename T, typename FC, typename FP>
 __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f, const GridDev& g, const T* cur, int ra,
@@ -450,8 +451,8 @@ __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f
       const T zla = p[-1], zra = p[VEC], zlb = p[n2 - 1], zrb = p[n2 + VEC];
       cell(v0, vm, v1, zla, zra, lr, col, cm, true, oa);
       cell(v1, v0, v2, zlb, zrb, lr + 1, col, cm, true, ob);
-      put(lr, col, oa);
-      put(lr + 1, col, ob);
+      put(lr, col, oa, cm);
+      put(lr + 1, col, ob, cm);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         vm[e] = v1[e];
@@ -464,7 +465,7 @@ __device__ __forceinline__ void res_fast_march(const ResCtx& c, const ResFast& f
       lds_vec<T>(p + n2, v1);
       const T zla = p[-1], zra = p[VEC];
       cell(v0, vm, v1, zla, zra, lr, col, cm, true, oa);
-      put(lr, col, oa);
+      put(lr, col, oa, cm);
     }
   }
 }
@@ -486,7 +487,7 @@ __device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const GridDev
   const T zla = pa[-1], zra = pa[VEC];
   if (c.rows < 2) {
     cell(a0, am, ap, zla, zra, 0, col, cm, ra_in, oa);
-    put(0, col, oa);
+    put(0, col, oa, ra_in ? cm : 0u);
     return;
   }
   const T* pb = cur + (c.rows - 1) * n2 + col;
@@ -497,8 +498,8 @@ __device__ __forceinline__ void res_fast_boundary(const ResCtx& c, const GridDev
   const T zlb = pb[-1], zrb = pb[VEC];
   cell(a0, am, ap, zla, zra, 0, col, cm, ra_in, oa);
   cell(b0, bm, bp, zlb, zrb, c.rows - 1, col, cm, rb_in, ob);
-  put(0, col, oa);
-  put(c.rows - 1, col, ob);
+  put(0, col, oa, ra_in ? cm : 0u);
+  put(c.rows - 1, col, ob, rb_in ? cm : 0u);
 }
 
 // =========================================================================================
@@ -596,12 +597,12 @@ k_euler_resident(GridDev g, EqDev<T> eq, T* __restrict__ b0,
             if (!rin || !((cm >> e) & 1u)) o[e] = v0[e];
         }
       };
-      auto put = [&](int row, int col, const T (&o)[VEC]) {
+      auto put = [&](int row, int col, const T (&o)[VEC], unsigned) {
         sts_vec<T>(nxt + row * rowlen + col, o);
         if (all_rows) sts_vec<T>(gout + (c.row0 + row) * rowlen + col, o);
       };
-      auto put_boundary = [&](int row, int col, const T (&o)[VEC]) {
-        put(row, col, o);
+      auto put_boundary = [&](int row, int col, const T (&o)[VEC], unsigned m) {
+        put(row, col, o, m);
         if (send) res_send<T>(c, ll, row, col, (unsigned)(s + 1), seq_out, o);
       };
       for (int seg = 0; seg < 2; ++seg) {  // ONE instance of the march
@@ -790,12 +791,25 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
       if (row == 0 || row == c.rows - 1) res_send<T>(c, ll, row, col, it, seq_d, dv);
     };
     if (fast.on) {
+      constexpr unsigned FULL = (1u << VEC) - 1u;
       for (int cv = fast.cv; cv < c.nv; cv += fast.cstep) {
+        const int col = cv * VEC;
         if (fast.boundary) {
-          dupd(0, cv * VEC);
-          if (c.rows > 1) dupd(c.rows - 1, cv * VEC);
+          dupd(0, col);
+          if (c.rows > 1) dupd(c.rows - 1, col);
         }
-        for (int row = fast.ta; row < fast.tb; ++row) dupd(row, cv * VEC);
+        // interior rows are region rows (res_fast_init): only the column mask is left to look at
+        const unsigned cm = res_col_mask<T>(g, col);
+        for (int row = fast.ta; row < fast.tb; ++row) {
+          T* dp = sd + row * rowlen + col;
+          T dv[VEC], rv[VEC];
+          lds_vec<T>(dp, dv);
+          lds_vec<T>(sr + row * rowlen + col, rv);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (cm == FULL || ((cm >> e) & 1u)) dv[e] = rv[e] + beta * dv[e];
+          sts_vec<T>(dp, dv);
+        }
       }
     } else {
       for (ResIt a = res_it_first(c); a.j < c.rows; a = res_it_next(c, a)) dupd(res_row_at(c, 1, a.j), a.cv * VEC);
@@ -829,20 +843,16 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
           if (!rin || !((cm >> e) & 1u)) ad[e] = (T)0;
       }
     };
-    // (d == 0 wherever ad was forced to 0 -- outside the region -- so the product adds an exact zero there)
-    auto dad_put = [&](int row, int col, const T (&ad)[VEC]) {
+    auto dad_put = [&](int row, int col, const T (&ad)[VEC], unsigned m) {
+      if (m == 0u) return;
       T dv[VEC];
       lds_vec<T>(sd + row * rowlen + col, dv);
-      const int grow = c.row0 + row;
-      const bool rin = grow >= g.lo[0] && grow < g.hi[0];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const int z = col + e;
-        if (rin && z >= g.lo[2] && z < g.hi[2]) {
+      for (int e = 0; e < VEC; ++e)
+        if (m == (1u << VEC) - 1u || ((m >> e) & 1u)) {
           const T q = dv[e] * ad[e];
           qa[0] += (double)q;
         }
-      }
     };
     if (fast.on) {
       unsigned got = 0u;
@@ -920,9 +930,11 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
       lds_vec<T>(rp, rv);
       lds_vec<T>(xp, xv);
       const bool rshell = grow == 0 || grow == g.n[0] - 1;
+      // (a vector whose cells are all region cells and that touches no wall: the common case, no per-cell tests)
+      const bool plain = m == (1u << VEC) - 1u && !rshell && col > 0 && col + VEC < c.n2;
 #pragma unroll
       for (int e = 0; e < VEC; ++e)
-        if ((m >> e) & 1u) {
+        if (plain || ((m >> e) & 1u)) {
           const T xo = xv[e];
           const T xn = xo + alpha * dv[e];
           const T rn = rv[e] - alpha * ad[e];
@@ -931,7 +943,7 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
           const T q = rn * rn;
           qb[0] += (double)q;
           const int z = col + e;
-          if (!rshell && z != 0 && z != c.n2 - 1) {
+          if (plain || (!rshell && z != 0 && z != c.n2 - 1)) {
             const T df = xn - xo;
             const T q2 = df * df;
             qb[1] += (double)q2;
@@ -942,16 +954,10 @@ k_cg_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa,
       sts_vec<T>(gxn + grow * rowlen + col, xv);
     };
     if (fast.on) {
-      auto upd_put = [&](int row, int col, const T (&ad)[VEC]) {
+      auto upd_put = [&](int row, int col, const T (&ad)[VEC], unsigned m) {
+        if (m == 0u) return;
         T dv[VEC];
         lds_vec<T>(sd + row * rowlen + col, dv);
-        const int grow = c.row0 + row;
-        unsigned m = 0u;
-        if (grow >= g.lo[0] && grow < g.hi[0]) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            if (col + e >= g.lo[2] && col + e < g.hi[2]) m |= 1u << e;
-        }
         update(row, col, m, dv, ad);
       };
       if (fast.boundary)
@@ -1068,12 +1074,12 @@ k_jacobi_resident(GridDev g, EqDev<T> eq, T* __restrict__ xa, T* __restrict__ xb
         o[e] = xn;
       }
     };
-    auto put = [&](int row, int col, const T (&o)[VEC]) {
+    auto put = [&](int row, int col, const T (&o)[VEC], unsigned) {
       sts_vec<T>(nxt + row * rowlen + col, o);
       sts_vec<T>(gout + (c.row0 + row) * rowlen + col, o);
     };
-    auto put_boundary = [&](int row, int col, const T (&o)[VEC]) {
-      put(row, col, o);
+    auto put_boundary = [&](int row, int col, const T (&o)[VEC], unsigned m) {
+      put(row, col, o, m);
       res_send<T>(c, ll, row, col, s + 1u, seq_out, o);
     };
     for (int seg = 0; seg < 2; ++seg) {
