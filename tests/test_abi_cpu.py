@@ -202,3 +202,21 @@ def test_header_is_plain_c():
         from pyapes_b200 import _native as N
 
         assert int(out[0]) == C.sizeof(N.Grid)
+
+
+def test_traffic_profile_is_stamped_with_the_current_cg_sources():
+    """bench.py refuses `roofline.traffic` (null, "stale") when profiles/ncu_traffic.json was captured on other sources
+    of the fused CG kernels than the ones in the tree.  This tripwire turns that into a red CPU test: after touching
+    kernels_tma.cuh (or what it includes) re-run tools/prof_cg.py under `ncu --set full` and tools/ncu_traffic.py."""
+    import json
+    import os
+
+    import __graft_entry__ as G
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        pytest.skip("no profiles/ncu_traffic.json")
+    with open(path) as f:
+        d = json.load(f)
+    assert d["source_hash"] == G._cg_kernel_hash(), "profiles/ncu_traffic.json is stale: re-capture the CG kernels"
+    assert 5.3e9 < d["phaseB_512"] < 6.0e9 and 3.2e9 < d["phaseA_512"] < 3.6e9  # 40 / 24 B per cell + halo re-reads
